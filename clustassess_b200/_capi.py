@@ -1,0 +1,139 @@
+"""ctypes binding of the C ABI declared in include/clustassess_b200.h.
+
+This is the Python twin of the R shim (r/clustassess_shim.c): it only marshals numpy buffers into the
+`extern "C"` entry points.  There is no fallback: if the shared library is missing, or no B200 is
+visible, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libclustassess_b200.so")
+
+CA_OK = 0
+CA_E_ARG = -3
+
+_I32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_F64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+# every symbol the header declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "ca_init": (C.c_int, [C.c_void_p, C.c_int]),
+    "ca_shutdown": (None, []),
+    "ca_last_error": (C.c_char_p, []),
+    "ca_version": (C.c_int, []),
+    "ca_set_stream": (C.c_int, [C.c_void_p]),
+    "ca_label_range": (C.c_int, [_I32, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ca_contingency": (C.c_int, [_I32, _I32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, C.c_void_p, C.c_void_p]),
+    "ca_ecs_pair": (C.c_int, [_I32, _I32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ca_ecs_pair_mean": (C.c_int, [_I32, _I32, C.c_int64, C.POINTER(C.c_double)]),
+    "ca_consistency": (C.c_int, [_I32, C.c_int64, C.c_int32, C.c_void_p, _F64, C.c_void_p]),
+    "ca_consistency_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, _F64, C.c_void_p]),
+    "ca_sim_matrix": (C.c_int, [_I32, C.c_int64, C.c_int32, _F64]),
+    "ca_sim_matrix_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _F64]),
+    "ca_agreement": (C.c_int, [_I32, _I32, C.c_int64, C.c_int32, _F64]),
+    "ca_merge_identical": (C.c_int, [_I32, C.c_int64, C.c_int32, C.c_void_p, _I32, _F64, C.POINTER(C.c_int32)]),
+    "ca_labels_create": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ca_labels_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ca_labels_upload_col": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "ca_labels_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "ca_labels_invalidate": (C.c_int, [C.c_void_p]),
+    "ca_labels_destroy": (C.c_int, [C.c_void_p]),
+    "ca_consistency_partial_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ca_consistency_finish_dev": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ca_get_profile": (C.c_int, [_F64, C.c_int]),
+    "ca_plan_blocks": (C.c_int, [_I32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _I32, _I32, C.c_int32,
+                                 C.POINTER(C.c_int64)]),
+}
+
+_lib = None
+
+
+class ClustAssessError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("clustassess_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """The loaded shared library (raises if it has not been built: there is no CPU fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "%s is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first. "
+                "clustassess_b200 has no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != CA_OK:
+        raise ClustAssessError(rc, lib().ca_last_error().decode("utf-8", "replace"))
+
+
+def _opt(a):
+    return None if a is None else a.ctypes.data
+
+
+def profile():
+    out = np.zeros(8, dtype=np.float64)
+    lib().ca_get_profile(out, 8)
+    keys = ["pack_ms", "transpose_ms", "plan_ms", "sort_ms", "rowblock_ms", "finish_ms", "call_ms", "rowblock_launches"]
+    return dict(zip(keys, out.tolist()))
+
+
+class DeviceLabels:
+    """A device-resident M x N int32 label matrix (ca_labels_t)."""
+
+    def __init__(self, n, m):
+        self.n, self.m = int(n), int(m)
+        h = C.c_void_p()
+        check(lib().ca_labels_create(self.n, self.m, C.byref(h)))
+        self._h = h
+
+    def upload(self, labels):
+        a = np.ascontiguousarray(labels, dtype=np.int32)
+        assert a.shape == (self.m, self.n)
+        check(lib().ca_labels_upload(self._h, a.ctypes.data))
+        return self
+
+    def upload_pinned(self, ptr):
+        check(lib().ca_labels_upload(self._h, ptr))
+        return self
+
+    @property
+    def device_ptr(self):
+        return lib().ca_labels_device_ptr(self._h)
+
+    def invalidate(self):
+        check(lib().ca_labels_invalidate(self._h))
+
+    def consistency_partial(self, weights, rank, world, ecc_ptr, sim_ptr):
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        check(lib().ca_consistency_partial_dev(self._h, _opt(w), rank, world, ecc_ptr, sim_ptr))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            lib().ca_labels_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def consistency_finish(n, m, weights, ecc_ptr, sim_ptr):
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    check(lib().ca_consistency_finish_dev(int(n), int(m), _opt(w), ecc_ptr, sim_ptr))

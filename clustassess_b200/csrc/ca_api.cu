@@ -1,0 +1,720 @@
+// ca_api.cu -- C ABI entry points, context, device-resident label sets and the batched pipeline.
+// See include/clustassess_b200.h for the contract and the reference lines every entry replaces.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <numeric>
+
+#include "ca_internal.h"
+
+namespace ca {
+
+// ---- errors / context -------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+Ctx& ctx() {
+    static Ctx c;
+    return c;
+}
+
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return CA_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        return CA_E_NOMEM;
+    }
+    cap = want;
+    return CA_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+static int do_init(int device) {
+    Ctx& c = ctx();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return CA_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        set_error("ca_init: device %d out of range (have %d)", device, count);
+        return CA_E_ARG;
+    }
+    if (c.inited && c.device == device) return CA_OK;
+    CA_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return CA_E_NO_DEVICE;
+    }
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    c.smem_optin = prop.sharedMemPerBlockOptin;
+    if (!c.own_stream) CA_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    if (!c.stream) c.stream = c.own_stream;
+    for (int i = 0; i < 8; i++)
+        if (!c.ev[i]) CA_CUDA(cudaEventCreate(&c.ev[i]));
+    c.inited = true;
+    return CA_OK;
+}
+
+int ensure_init() {
+    Ctx& c = ctx();
+    if (c.inited) {
+        CA_CUDA(cudaSetDevice(c.device));
+        return CA_OK;
+    }
+    return do_init(0);
+}
+
+// ---- label preparation ------------------------------------------------------------------------------
+static constexpr int64_t RANGE_LIMIT = 1ll << 24;        // per-partition label range (max-min+1)
+static constexpr int64_t TOTAL_RANGE_LIMIT = 1ll << 28;  // summed over partitions
+static constexpr int32_t K_LIMIT = 65535;                // compact labels are uint16
+
+int prepare_ranks(Labels& L) {
+    if (L.ranked) return CA_OK;
+    Ctx& c = ctx();
+    cudaStream_t s = c.stream;
+    const int32_t m = L.m;
+    const int64_t n = L.n;
+    L.h_min.assign(m, 0);
+    L.h_max.assign(m, 0);
+    L.h_k.assign(m, 0);
+    L.h_roff.assign(m + 1, 0);
+    CA_TRY(L.d_min.ensure((size_t)m * 4));
+    CA_TRY(L.d_max.ensure((size_t)m * 4));
+    CA_TRY(launch_minmax(L.d_raw, n, m, L.d_min.as<int32_t>(), L.d_max.as<int32_t>(), s));
+    CA_CUDA(cudaMemcpyAsync(L.h_min.data(), L.d_min.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    CA_CUDA(cudaMemcpyAsync(L.h_max.data(), L.d_max.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    int64_t max_range = 0;
+    for (int32_t p = 0; p < m; p++) {
+        if (L.h_min[p] == INT32_MIN) {
+            set_error("partition %d contains NA_integer_ (INT_MIN); NA labels are not supported", p);
+            return CA_E_NA_LABEL;
+        }
+        int64_t range = (int64_t)L.h_max[p] - (int64_t)L.h_min[p] + 1;
+        if (range > RANGE_LIMIT) {
+            set_error("partition %d: label range %lld exceeds the supported %lld", p, (long long)range, (long long)RANGE_LIMIT);
+            return CA_E_UNSUPPORTED;
+        }
+        L.h_roff[p + 1] = L.h_roff[p] + range;
+        max_range = std::max(max_range, range);
+    }
+    if (L.h_roff[m] > TOTAL_RANGE_LIMIT) {
+        set_error("summed label range %lld exceeds the supported %lld", (long long)L.h_roff[m], (long long)TOTAL_RANGE_LIMIT);
+        return CA_E_UNSUPPORTED;
+    }
+    const size_t tot = (size_t)L.h_roff[m];
+    CA_TRY(L.d_roff.ensure((size_t)(m + 1) * 8));
+    CA_TRY(L.d_cnt.ensure(tot * 4));
+    CA_TRY(L.d_rank.ensure(tot * 4));
+    CA_TRY(L.d_kcount.ensure((size_t)m * 4));
+    CA_CUDA(cudaMemcpyAsync(L.d_roff.p, L.h_roff.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, s));
+    CA_CUDA(cudaMemsetAsync(L.d_cnt.p, 0, tot * 4, s));
+    CA_TRY(launch_count(L.d_raw, n, m, L.d_min.as<int32_t>(), L.d_roff.as<int64_t>(), nullptr, (int32_t)max_range,
+                        L.d_cnt.as<uint32_t>(), s));
+    CA_TRY(launch_rank(L.d_cnt.as<uint32_t>(), L.d_roff.as<int64_t>(), nullptr, nullptr, m, L.d_rank.as<uint32_t>(),
+                       L.d_kcount.as<int32_t>(), s));
+    CA_CUDA(cudaMemcpyAsync(L.h_k.data(), L.d_kcount.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    L.kmax = 0;
+    L.identity = true;
+    for (int32_t p = 0; p < m; p++) {
+        L.kmax = std::max(L.kmax, L.h_k[p]);
+        if ((int64_t)L.h_k[p] != L.h_roff[p + 1] - L.h_roff[p]) L.identity = false;
+    }
+    if (L.kmax > K_LIMIT) {
+        set_error("a partition has %d clusters; the engine supports at most %d", L.kmax, K_LIMIT);
+        return CA_E_UNSUPPORTED;
+    }
+    L.kp = std::max(8, (L.kmax + 7) & ~7);
+    L.mpad = (m + 31) & ~31;
+    CA_TRY(L.d_sizes.ensure((size_t)m * L.kp * 4));
+    CA_CUDA(cudaMemsetAsync(L.d_sizes.p, 0, (size_t)m * L.kp * 4, s));
+    CA_TRY(launch_sizes(L.d_cnt.as<uint32_t>(), L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(), nullptr, nullptr, m,
+                        (int32_t)max_range, L.kp, L.d_sizes.as<int32_t>(), s));
+    L.h_sizes.assign((size_t)m * L.kp, 0);
+    CA_CUDA(cudaMemcpyAsync(L.h_sizes.data(), L.d_sizes.p, (size_t)m * L.kp * 4, cudaMemcpyDeviceToHost, s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    L.ranked = true;
+    return CA_OK;
+}
+
+int prepare_labels(Labels& L) {
+    if (L.prepared) return CA_OK;
+    Ctx& c = ctx();
+    cudaStream_t s = c.stream;
+    const int32_t m = L.m;
+    const int64_t n = L.n;
+    CA_TRY(prepare_ranks(L));
+    CA_CUDA(cudaEventRecord(c.ev[1], s));
+    CA_TRY(L.d_lab16.ensure((size_t)std::max<int64_t>(n, 1) * L.mpad * 2));
+    CA_TRY(launch_relabel_transpose(L.d_raw, n, m, L.mpad, L.d_min.as<int32_t>(),
+                                    L.identity ? nullptr : L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(),
+                                    L.d_lab16.as<uint16_t>(), s));
+    CA_CUDA(cudaEventRecord(c.ev[2], s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    L.prepared = true;
+    return CA_OK;
+}
+
+// zigzag owner of partition i among `world` ranks: 0..w-1, w-1..0, ... (balances sum of M-1-i)
+static inline int owner_of(int32_t i, int32_t world) {
+    int32_t r = i % (2 * world);
+    return r < world ? r : 2 * world - 1 - r;
+}
+
+struct Workspace {
+    DevBuf perm, cstart, crow, items, parts, slot_of, w;
+};
+static Workspace& ws() {
+    static Workspace w;
+    return w;
+}
+
+// The all-pairs job (or one rank's share of it).  pairs: for every owned partition i, partners j in
+// (i, m) -- or, in agreement mode, partition `ref_only` against all j in [0, m_partners).
+static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int32_t world, double* d_ecc, double* d_sim,
+                        int32_t ref_only, int32_t m_partners) {
+    Ctx& c = ctx();
+    cudaStream_t s = c.stream;
+    const int32_t m = L.m;
+    const int64_t n = L.n;
+    auto t_call0 = std::chrono::steady_clock::now();
+    for (double& v : c.prof) v = 0.0;
+    c.launches = 0;
+    CA_CUDA(cudaEventRecord(c.ev[0], s));
+    const bool was_prepared = L.prepared;
+    CA_TRY(prepare_labels(L));
+    if (was_prepared) {
+        CA_CUDA(cudaEventRecord(c.ev[1], s));
+        CA_CUDA(cudaEventRecord(c.ev[2], s));
+    }
+    if (n == 0) return CA_OK;
+
+    // ---- host planning ----------------------------------------------------------------------------
+    auto t_plan0 = std::chrono::steady_clock::now();
+    int32_t max_rows = 0;
+    const int smem_bytes = rowblock_smem_budget(L.kp, &max_rows);
+    if (max_rows < 1) {
+        set_error("%d clusters per partition need more shared memory per table row than one SM has", L.kmax);
+        return CA_E_UNSUPPORTED;
+    }
+    std::vector<int32_t> parts;  // owned partitions, in slot order
+    if (ref_only >= 0) {
+        parts.push_back(ref_only);
+    } else {
+        for (int32_t i = 0; i < m - 1; i++)
+            if (owner_of(i, world) == rank) parts.push_back(i);
+    }
+    const int32_t nparts = (int32_t)parts.size();
+    std::vector<int32_t> h_slot_of(m, -1);
+    std::vector<int32_t> h_cstart((size_t)std::max(nparts, 1) * L.kp, 0);
+    std::vector<uint16_t> h_crow((size_t)std::max(nparts, 1) * L.kp, 0);
+    std::vector<Item> items_narrow, items_wide;
+    int64_t perm_stride = 4;
+    PlanOut po;
+    for (int32_t sl = 0; sl < nparts; sl++) {
+        const int32_t p = parts[sl];
+        h_slot_of[p] = sl;
+        CA_TRY(plan_blocks(L.h_sizes.data() + (size_t)p * L.kp, L.h_k[p], RB_CPT, RB_CAP, max_rows, po));
+        perm_stride = std::max<int64_t>(perm_stride, (po.total_pos + 3) & ~3LL);
+        for (int32_t k = 0; k < L.h_k[p]; k++) {
+            h_cstart[(size_t)sl * L.kp + k] = po.cstart[k];
+            h_crow[(size_t)sl * L.kp + k] = (uint16_t)po.crow[k];
+        }
+        for (size_t t = 0; t < po.pos0.size(); t++) {
+            Item it;
+            it.m = p;
+            it.pos0 = po.pos0[t];
+            it.npos = po.npos[t];
+            it.nrows = po.nrows[t];
+            it.jbeg = ref_only >= 0 ? 0 : p + 1;
+            it.jend = ref_only >= 0 ? m_partners : m;
+            it.sa = po.sa[t];
+            it.pad_ = 0;
+            (po.wide[t] ? items_wide : items_narrow).push_back(it);
+        }
+    }
+    auto cost = [](const Item& a) { return (int64_t)a.npos * (a.jend - a.jbeg); };
+    auto by_cost = [&](const Item& a, const Item& b) { return cost(a) > cost(b); };
+    std::stable_sort(items_narrow.begin(), items_narrow.end(), by_cost);
+    std::stable_sort(items_wide.begin(), items_wide.end(), by_cost);
+    std::vector<double> h_w(L.mpad + RB_JW, 0.0);
+    double wsum = 0.0;
+    const int32_t mw = ref_only >= 0 ? m_partners : m;
+    for (int32_t p = 0; p < mw; p++) {
+        h_w[p] = weights_host ? weights_host[p] : 1.0;
+        wsum += h_w[p];
+    }
+    double inv_norm;
+    if (ref_only >= 0) {
+        h_w[ref_only] = 1.0;           // agreement: (1/m) * sum_j ECS(ref, j)
+        inv_norm = 1.0 / (double)m_partners;
+    } else {
+        inv_norm = 1.0 / (wsum * (wsum - 1.0) / 2.0);  // R/ECS.R:1471-1472
+    }
+    c.prof[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
+
+    // ---- upload plan, sort ------------------------------------------------------------------------
+    Workspace& W = ws();
+    const size_t nitems = items_narrow.size() + items_wide.size();
+    CA_TRY(W.perm.ensure((size_t)std::max(nparts, 1) * perm_stride * 4));
+    CA_TRY(W.cstart.ensure(h_cstart.size() * 4));
+    CA_TRY(W.crow.ensure(h_crow.size() * 2));
+    CA_TRY(W.items.ensure(std::max<size_t>(nitems, 1) * sizeof(Item)));
+    CA_TRY(W.parts.ensure((size_t)std::max(nparts, 1) * 4));
+    CA_TRY(W.slot_of.ensure((size_t)m * 4));
+    CA_TRY(W.w.ensure(h_w.size() * 8));
+    CA_CUDA(cudaMemcpyAsync(W.cstart.p, h_cstart.data(), h_cstart.size() * 4, cudaMemcpyHostToDevice, s));
+    CA_CUDA(cudaMemcpyAsync(W.crow.p, h_crow.data(), h_crow.size() * 2, cudaMemcpyHostToDevice, s));
+    if (nparts) CA_CUDA(cudaMemcpyAsync(W.parts.p, parts.data(), (size_t)nparts * 4, cudaMemcpyHostToDevice, s));
+    CA_CUDA(cudaMemcpyAsync(W.slot_of.p, h_slot_of.data(), (size_t)m * 4, cudaMemcpyHostToDevice, s));
+    CA_CUDA(cudaMemcpyAsync(W.w.p, h_w.data(), h_w.size() * 8, cudaMemcpyHostToDevice, s));
+    Item* d_items = W.items.as<Item>();
+    if (!items_narrow.empty())
+        CA_CUDA(cudaMemcpyAsync(d_items, items_narrow.data(), items_narrow.size() * sizeof(Item), cudaMemcpyHostToDevice, s));
+    if (!items_wide.empty())
+        CA_CUDA(cudaMemcpyAsync(d_items + items_narrow.size(), items_wide.data(), items_wide.size() * sizeof(Item),
+                                cudaMemcpyHostToDevice, s));
+    CA_CUDA(cudaEventRecord(c.ev[3], s));
+    CA_TRY(launch_sort(L.d_raw, n, L.d_min.as<int32_t>(), L.identity ? nullptr : L.d_rank.as<uint32_t>(),
+                       L.d_roff.as<int64_t>(), W.cstart.as<int32_t>(), L.kp, W.parts.as<int32_t>(), nparts,
+                       W.perm.as<int32_t>(), perm_stride, s));
+    CA_CUDA(cudaEventRecord(c.ev[4], s));
+
+    // ---- row-block kernels ------------------------------------------------------------------------
+    RowBlockParams P;
+    P.lab16 = L.d_lab16.as<uint16_t>();
+    P.perm = W.perm.as<int32_t>();
+    P.slot_of = W.slot_of.as<int32_t>();
+    P.sizes = L.d_sizes.as<int32_t>();
+    P.crow = W.crow.as<uint16_t>();
+    P.w = W.w.as<double>();
+    P.items = d_items;
+    P.ecc = d_ecc;
+    P.sim = d_sim;
+    P.perm_stride = perm_stride;
+    P.m = m;
+    P.mpad = L.mpad;
+    P.kp = L.kp;
+    P.smem_bytes = smem_bytes;
+    P.inv_norm = inv_norm;
+    int launches = 0;
+    if (d_ecc || d_sim) {
+        CA_TRY(launch_rowblock(P, (int32_t)items_narrow.size(), false, s, &launches));
+        P.items = d_items + items_narrow.size();
+        CA_TRY(launch_rowblock(P, (int32_t)items_wide.size(), true, s, &launches));
+    }
+    CA_CUDA(cudaEventRecord(c.ev[5], s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    float ms;
+    CA_CUDA(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
+    c.prof[0] = ms;
+    CA_CUDA(cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]));
+    c.prof[1] = ms;
+    CA_CUDA(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4]));
+    c.prof[3] = ms;
+    CA_CUDA(cudaEventElapsedTime(&ms, c.ev[4], c.ev[5]));
+    c.prof[4] = ms;
+    c.prof[7] = (double)c.launches;  // every kernel of this call (pack, transpose, sort, row-block)
+    (void)launches;
+    c.prof[6] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
+    return CA_OK;
+}
+
+static double ident_constant(const double* weights_host, int32_t m) {
+    // sum_i w_i/norm*(w_i-1)/2  (R/ECS.R:1475,1491)
+    double wsum = 0.0;
+    for (int32_t p = 0; p < m; p++) wsum += weights_host ? weights_host[p] : 1.0;
+    const double norm = wsum * (wsum - 1.0) / 2.0;
+    double c0 = 0.0;
+    for (int32_t p = 0; p < m; p++) {
+        double w = weights_host ? weights_host[p] : 1.0;
+        c0 += w / norm * (w - 1.0) / 2.0;
+    }
+    return c0;
+}
+
+}  // namespace ca
+
+using namespace ca;
+
+struct ca_labels {
+    Labels L;
+};
+namespace ca {
+Labels& labels_of(ca_labels_t* h) { return h->L; }
+}
+
+// =====================================================================================================
+extern "C" {
+
+int ca_version(void) { return 100; }
+const char* ca_last_error(void) { return g_err; }
+
+int ca_init(const int* devices, int ndev) {
+    int dev = (devices && ndev > 0) ? devices[0] : 0;
+    return do_init(dev);
+}
+
+void ca_shutdown(void) {
+    Ctx& c = ctx();
+    if (!c.inited) return;
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    Workspace& W = ws();
+    W.perm.release(); W.cstart.release(); W.crow.release(); W.items.release(); W.parts.release(); W.slot_of.release(); W.w.release();
+    for (int i = 0; i < 8; i++)
+        if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
+    if (c.own_stream) { cudaStreamDestroy(c.own_stream); c.own_stream = nullptr; }
+    c.stream = nullptr;
+    c.inited = false;
+}
+
+int ca_set_stream(void* cuda_stream) {
+    CA_TRY(ensure_init());
+    Ctx& c = ctx();
+    c.stream = cuda_stream ? (cudaStream_t)cuda_stream : c.own_stream;
+    return CA_OK;
+}
+
+int ca_get_profile(double* ms_out, int cap) {
+    if (!ms_out || cap <= 0) return 0;
+    int k = cap < 8 ? cap : 8;
+    for (int i = 0; i < k; i++) ms_out[i] = ctx().prof[i];
+    return k;
+}
+
+int ca_label_range(const int32_t* x, int64_t n, int32_t* min_out, int32_t* max_out) {
+    if (!x || n <= 0 || !min_out || !max_out) {
+        set_error("ca_label_range: NULL argument or n <= 0");
+        return CA_E_ARG;
+    }
+    int32_t lo = x[0], hi = x[0];
+    for (int64_t i = 1; i < n; i++) {
+        lo = x[i] < lo ? x[i] : lo;
+        hi = x[i] > hi ? x[i] : hi;
+    }
+    if (lo == INT32_MIN) {
+        set_error("label vector contains NA_integer_ (INT_MIN)");
+        return CA_E_NA_LABEL;
+    }
+    *min_out = lo;
+    *max_out = hi;
+    return CA_OK;
+}
+
+// ---- device-resident label sets ----------------------------------------------------------------------
+int ca_labels_create(int64_t n, int32_t m, ca_labels_t** out) {
+    if (!out || n < 0 || m < 1 || n > 0x7ffffff0LL) {
+        set_error("ca_labels_create: bad arguments (n=%lld m=%d)", (long long)n, m);
+        return CA_E_ARG;
+    }
+    CA_TRY(ensure_init());
+    ca_labels* h = new (std::nothrow) ca_labels();
+    if (!h) return CA_E_NOMEM;
+    h->L.n = n;
+    h->L.m = m;
+    size_t bytes = (size_t)std::max<int64_t>(n, 1) * (size_t)m * 4;
+    cudaError_t e = cudaMalloc(&h->L.d_raw, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) for the label matrix failed: %s", bytes, cudaGetErrorString(e));
+        delete h;
+        return CA_E_NOMEM;
+    }
+    *out = h;
+    return CA_OK;
+}
+
+int ca_labels_upload(ca_labels_t* h, const int32_t* labels) {
+    if (!h || !labels) { set_error("ca_labels_upload: NULL argument"); return CA_E_ARG; }
+    CA_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    CA_CUDA(cudaMemcpyAsync(h->L.d_raw, labels, (size_t)h->L.n * h->L.m * 4, cudaMemcpyHostToDevice, s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    h->L.prepared = h->L.ranked = false;
+    return CA_OK;
+}
+
+int ca_labels_upload_col(ca_labels_t* h, int32_t p, const int32_t* col) {
+    if (!h || !col || p < 0 || p >= h->L.m) { set_error("ca_labels_upload_col: bad argument"); return CA_E_ARG; }
+    CA_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    CA_CUDA(cudaMemcpyAsync(h->L.d_raw + (size_t)p * h->L.n, col, (size_t)h->L.n * 4, cudaMemcpyHostToDevice, s));
+    h->L.prepared = h->L.ranked = false;
+    return CA_OK;
+}
+
+void* ca_labels_device_ptr(ca_labels_t* h) { return h ? (void*)h->L.d_raw : nullptr; }
+
+int ca_labels_invalidate(ca_labels_t* h) {
+    if (!h) return CA_E_ARG;
+    h->L.prepared = h->L.ranked = false;
+    return CA_OK;
+}
+
+int ca_labels_destroy(ca_labels_t* h) {
+    if (!h) return CA_OK;
+    if (ctx().inited) cudaSetDevice(ctx().device);
+    Labels& L = h->L;
+    if (L.d_raw) cudaFree(L.d_raw);
+    L.d_min.release(); L.d_max.release(); L.d_cnt.release(); L.d_rank.release(); L.d_kcount.release();
+    L.d_roff.release(); L.d_sizes.release(); L.d_lab16.release();
+    delete h;
+    return CA_OK;
+}
+
+int ca_consistency_partial_dev(ca_labels_t* h, const double* weights_host, int32_t rank, int32_t world, double* ecc_dev,
+                               double* sim_dev) {
+    if (!h || world < 1 || rank < 0 || rank >= world) { set_error("ca_consistency_partial_dev: bad argument"); return CA_E_ARG; }
+    if (h->L.m < 2) { set_error("At least two clusterings are required to calculate the consistency."); return CA_E_ARG; }
+    CA_TRY(ensure_init());
+    if (h->L.n == 0) return CA_OK;
+    return run_allpairs(h->L, weights_host, rank, world, ecc_dev, sim_dev, -1, 0);
+}
+
+int ca_consistency_finish_dev(int64_t n, int32_t m, const double* weights_host, double* ecc_dev, double* sim_dev) {
+    CA_TRY(ensure_init());
+    Ctx& c = ctx();
+    CA_CUDA(cudaEventRecord(c.ev[6], c.stream));
+    CA_TRY(launch_finish(ecc_dev, n, ident_constant(weights_host, m), sim_dev, m, c.stream));
+    CA_CUDA(cudaEventRecord(c.ev[7], c.stream));
+    CA_CUDA(cudaStreamSynchronize(c.stream));
+    float ms;
+    CA_CUDA(cudaEventElapsedTime(&ms, c.ev[6], c.ev[7]));
+    c.prof[5] = ms;
+    c.prof[7] = (double)c.launches;
+    return CA_OK;
+}
+
+// ---- host-pointer batched entry points -----------------------------------------------------------------
+static int host_allpairs(const int32_t* labels, const int32_t* const* cols, int64_t n, int32_t m, const double* weights,
+                         double* ecc_out, double* sim_out) {
+    if ((!labels && !cols) || n < 0 || m < 1) { set_error("bad arguments (NULL labels, n < 0 or m < 1)"); return CA_E_ARG; }
+    CA_TRY(ensure_init());
+    if (n == 0) {  // nothing to compare: ecc is empty, mean() of an empty ECS vector is NaN in R
+        if (sim_out)
+            for (int32_t i = 0; i < m; i++)
+                for (int32_t j = 0; j < m; j++) sim_out[(size_t)i * m + j] = i == j ? 1.0 : 0.0 / 0.0;
+        return CA_OK;
+    }
+    cudaStream_t s = ctx().stream;
+    ca_labels_t* h = nullptr;
+    CA_TRY(ca_labels_create(n, m, &h));
+    int rc = CA_OK;
+    static DevBuf d_ecc, d_sim;
+    do {
+        if (labels) {
+            rc = ca_labels_upload(h, labels);
+        } else {
+            for (int32_t p = 0; p < m && rc == CA_OK; p++) {
+                if (!cols[p]) { set_error("NULL column pointer %d", p); rc = CA_E_ARG; break; }
+                rc = ca_labels_upload_col(h, p, cols[p]);
+            }
+        }
+        if (rc != CA_OK) break;
+        if (ecc_out) { rc = d_ecc.ensure((size_t)std::max<int64_t>(n, 1) * 8); if (rc) break; }
+        if (sim_out) { rc = d_sim.ensure((size_t)m * m * 8); if (rc) break; }
+        cudaError_t e = cudaSuccess;
+        if (ecc_out) e = cudaMemsetAsync(d_ecc.p, 0, (size_t)std::max<int64_t>(n, 1) * 8, s);
+        if (e == cudaSuccess && sim_out) e = cudaMemsetAsync(d_sim.p, 0, (size_t)m * m * 8, s);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e)); rc = CA_E_CUDA; break; }
+        if (m >= 2) {
+            rc = run_allpairs(h->L, weights, 0, 1, ecc_out ? d_ecc.as<double>() : nullptr, sim_out ? d_sim.as<double>() : nullptr, -1, 0);
+            if (rc) break;
+        }
+        rc = ca_consistency_finish_dev(n, m, weights, ecc_out ? d_ecc.as<double>() : nullptr, sim_out ? d_sim.as<double>() : nullptr);
+        if (rc) break;
+        if (ecc_out && n > 0) e = cudaMemcpyAsync(ecc_out, d_ecc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && sim_out) e = cudaMemcpyAsync(sim_out, d_sim.p, (size_t)m * m * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("device-to-host copy failed: %s", cudaGetErrorString(e)); rc = CA_E_CUDA; }
+    } while (0);
+    ca_labels_destroy(h);
+    return rc;
+}
+
+int ca_consistency(const int32_t* labels, int64_t n, int32_t m, const double* weights, double* ecc_out, double* sim_out) {
+    if (m < 2) { set_error("At least two clusterings are required to calculate the consistency."); return CA_E_ARG; }
+    if (!ecc_out) { set_error("ca_consistency: ecc_out is NULL"); return CA_E_ARG; }
+    return host_allpairs(labels, nullptr, n, m, weights, ecc_out, sim_out);
+}
+int ca_consistency_cols(const int32_t* const* cols, int64_t n, int32_t m, const double* weights, double* ecc_out, double* sim_out) {
+    if (m < 2) { set_error("At least two clusterings are required to calculate the consistency."); return CA_E_ARG; }
+    if (!ecc_out) { set_error("ca_consistency_cols: ecc_out is NULL"); return CA_E_ARG; }
+    return host_allpairs(nullptr, cols, n, m, weights, ecc_out, sim_out);
+}
+int ca_sim_matrix(const int32_t* labels, int64_t n, int32_t m, double* sim_out) {
+    if (!sim_out) { set_error("ca_sim_matrix: sim_out is NULL"); return CA_E_ARG; }
+    return host_allpairs(labels, nullptr, n, m, nullptr, nullptr, sim_out);
+}
+int ca_sim_matrix_cols(const int32_t* const* cols, int64_t n, int32_t m, double* sim_out) {
+    if (!sim_out) { set_error("ca_sim_matrix_cols: sim_out is NULL"); return CA_E_ARG; }
+    return host_allpairs(nullptr, cols, n, m, nullptr, nullptr, sim_out);
+}
+
+int ca_agreement(const int32_t* reference, const int32_t* labels, int64_t n, int32_t m, double* agr_out) {
+    if (!reference || !labels || !agr_out || n < 0 || m < 1) { set_error("ca_agreement: bad argument"); return CA_E_ARG; }
+    CA_TRY(ensure_init());
+    if (n == 0) return CA_OK;
+    cudaStream_t s = ctx().stream;
+    ca_labels_t* h = nullptr;
+    CA_TRY(ca_labels_create(n, m + 1, &h));  // partitions 0..m-1 = the list, partition m = the reference
+    int rc = CA_OK;
+    static DevBuf d_out;
+    do {
+        cudaError_t e = cudaMemcpyAsync(h->L.d_raw, labels, (size_t)n * m * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->L.d_raw + (size_t)n * m, reference, (size_t)n * 4, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { set_error("host-to-device copy failed: %s", cudaGetErrorString(e)); rc = CA_E_CUDA; break; }
+        rc = d_out.ensure((size_t)std::max<int64_t>(n, 1) * 8);
+        if (rc) break;
+        e = cudaMemsetAsync(d_out.p, 0, (size_t)std::max<int64_t>(n, 1) * 8, s);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e)); rc = CA_E_CUDA; break; }
+        rc = run_allpairs(h->L, nullptr, 0, 1, d_out.as<double>(), nullptr, m, m);
+        if (rc) break;
+        if (n > 0) e = cudaMemcpyAsync(agr_out, d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("device-to-host copy failed: %s", cudaGetErrorString(e)); rc = CA_E_CUDA; }
+    } while (0);
+    ca_labels_destroy(h);
+    return rc;
+}
+
+// ---- legacy per-pair entry points ------------------------------------------------------------------------
+struct PairBufs {
+    DevBuf a, b, table, sa, sb, err, ecs, partial, out;
+};
+static PairBufs& pb() {
+    static PairBufs p;
+    return p;
+}
+
+static int pair_upload(const int32_t* a, const int32_t* b, int64_t n, cudaStream_t s) {
+    PairBufs& B = pb();
+    CA_TRY(B.a.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    CA_TRY(B.b.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    if (n > 0) {
+        CA_CUDA(cudaMemcpyAsync(B.a.p, a, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CA_CUDA(cudaMemcpyAsync(B.b.p, b, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    }
+    return CA_OK;
+}
+
+static int pair_tables(int64_t n, int32_t min_a, int32_t min_b, int32_t ka, int32_t kb, cudaStream_t s) {
+    PairBufs& B = pb();
+    CA_TRY(B.table.ensure((size_t)ka * kb * 4));
+    CA_TRY(B.sa.ensure((size_t)ka * 4));
+    CA_TRY(B.sb.ensure((size_t)kb * 4));
+    CA_TRY(B.err.ensure(4));
+    return pair_contingency(B.a.as<int32_t>(), B.b.as<int32_t>(), n, min_a, min_b, ka, kb, B.table.as<uint32_t>(),
+                            B.sa.as<uint32_t>(), B.sb.as<uint32_t>(), B.err.as<int32_t>(), s);
+}
+
+static int check_dims(int32_t min_a, int32_t max_a, int32_t min_b, int32_t max_b, int32_t* ka, int32_t* kb) {
+    int64_t ra = (int64_t)max_a - min_a + 1, rb = (int64_t)max_b - min_b + 1;
+    if (ra * rb > (1ll << 31)) {
+        set_error("contingency table %lld x %lld is too large", (long long)ra, (long long)rb);
+        return CA_E_UNSUPPORTED;
+    }
+    *ka = (int32_t)ra;
+    *kb = (int32_t)rb;
+    return CA_OK;
+}
+
+int ca_contingency(const int32_t* a, const int32_t* b, int64_t n, int32_t min_a, int32_t min_b, int32_t ka, int32_t kb,
+                   int32_t* table_out, int32_t* sizes_a, int32_t* sizes_b) {
+    if (!a || !b || !table_out || n < 0 || ka < 1 || kb < 1) { set_error("ca_contingency: bad argument"); return CA_E_ARG; }
+    if ((int64_t)ka * kb > (1ll << 31)) { set_error("contingency table %d x %d is too large", ka, kb); return CA_E_UNSUPPORTED; }
+    CA_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    PairBufs& B = pb();
+    CA_TRY(pair_upload(a, b, n, s));
+    CA_TRY(pair_tables(n, min_a, min_b, ka, kb, s));
+    int32_t err = 0;
+    CA_CUDA(cudaMemcpyAsync(&err, B.err.p, 4, cudaMemcpyDeviceToHost, s));
+    CA_CUDA(cudaMemcpyAsync(table_out, B.table.p, (size_t)ka * kb * 4, cudaMemcpyDeviceToHost, s));
+    if (sizes_a) CA_CUDA(cudaMemcpyAsync(sizes_a, B.sa.p, (size_t)ka * 4, cudaMemcpyDeviceToHost, s));
+    if (sizes_b) CA_CUDA(cudaMemcpyAsync(sizes_b, B.sb.p, (size_t)kb * 4, cudaMemcpyDeviceToHost, s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    if (err) { set_error("ca_contingency: a label lies outside [min, min+k)"); return CA_E_RANGE; }
+    return CA_OK;
+}
+
+int ca_ecs_pair(const int32_t* a, const int32_t* b, int64_t n, double* ecs_out, double* mean_out) {
+    if (!a || !b || (!ecs_out && !mean_out) || n < 0) { set_error("ca_ecs_pair: bad argument"); return CA_E_ARG; }
+    if (n == 0) { if (mean_out) *mean_out = 0.0 / 0.0; return CA_OK; }
+    CA_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    PairBufs& B = pb();
+    int32_t min_a, max_a, min_b, max_b, ka, kb;
+    CA_TRY(ca_label_range(a, n, &min_a, &max_a));
+    CA_TRY(ca_label_range(b, n, &min_b, &max_b));
+    CA_TRY(check_dims(min_a, max_a, min_b, max_b, &ka, &kb));
+    CA_TRY(pair_upload(a, b, n, s));
+    CA_TRY(pair_tables(n, min_a, min_b, ka, kb, s));
+    CA_TRY(B.ecs.ensure((size_t)n * 8));
+    CA_TRY(B.partial.ensure(4096 * 8));
+    CA_TRY(B.out.ensure(8));
+    int32_t nblocks = 0;
+    CA_TRY(pair_ecs_gather(B.a.as<int32_t>(), B.b.as<int32_t>(), n, min_a, min_b, ka, B.table.as<uint32_t>(), B.sa.as<uint32_t>(),
+                           B.sb.as<uint32_t>(), ecs_out ? B.ecs.as<double>() : nullptr, B.partial.as<double>(), &nblocks, s));
+    if (mean_out) {
+        CA_TRY(reduce_partials(B.partial.as<double>(), nblocks, 1.0 / (double)n, B.out.as<double>(), s));
+        CA_CUDA(cudaMemcpyAsync(mean_out, B.out.p, 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (ecs_out) CA_CUDA(cudaMemcpyAsync(ecs_out, B.ecs.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    return CA_OK;
+}
+
+int ca_ecs_pair_mean(const int32_t* a, const int32_t* b, int64_t n, double* mean_out) {
+    if (!a || !b || !mean_out || n < 0) { set_error("ca_ecs_pair_mean: bad argument"); return CA_E_ARG; }
+    if (n == 0) { *mean_out = 0.0 / 0.0; return CA_OK; }
+    CA_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    PairBufs& B = pb();
+    int32_t min_a, max_a, min_b, max_b, ka, kb;
+    CA_TRY(ca_label_range(a, n, &min_a, &max_a));
+    CA_TRY(ca_label_range(b, n, &min_b, &max_b));
+    CA_TRY(check_dims(min_a, max_a, min_b, max_b, &ka, &kb));
+    CA_TRY(pair_upload(a, b, n, s));
+    CA_TRY(pair_tables(n, min_a, min_b, ka, kb, s));
+    CA_TRY(B.partial.ensure(4096 * 8));
+    CA_TRY(B.out.ensure(8));
+    int32_t nblocks = 0;
+    CA_TRY(pair_mean_from_table(B.table.as<uint32_t>(), B.sa.as<uint32_t>(), B.sb.as<uint32_t>(), ka, kb, n, B.partial.as<double>(),
+                                &nblocks, s));
+    CA_TRY(reduce_partials(B.partial.as<double>(), nblocks, 1.0, B.out.as<double>(), s));
+    CA_CUDA(cudaMemcpyAsync(mean_out, B.out.p, 8, cudaMemcpyDeviceToHost, s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    return CA_OK;
+}
+
+int ca_merge_identical(const int32_t* labels, int64_t n, int32_t m, const double* freq_in, int32_t* keep_out, double* freq_out,
+                       int32_t* u_out);  // defined in ca_dedup.cu
+
+}  // extern "C"

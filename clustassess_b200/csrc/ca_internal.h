@@ -1,0 +1,150 @@
+// ca_internal.h -- shared declarations of the B200 ECS library (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/clustassess_b200.h"
+
+namespace ca {
+
+// ---- errors -----------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define CA_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ca::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return CA_E_CUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+#define CA_TRY(call)            \
+    do {                        \
+        int rc_ = (call);       \
+        if (rc_ != CA_OK) return rc_; \
+    } while (0)
+
+// ---- context ----------------------------------------------------------------------------------------
+struct Ctx {
+    bool inited = false;
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;        // max dynamic shared memory per block (opt-in)
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // the stream everything is launched on
+    cudaEvent_t ev[8] = {};
+    double prof[8] = {};
+    long launches = 0;  // kernels launched since the counter was last reset
+};
+Ctx& ctx();
+int ensure_init();
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
+// ---- row-block engine geometry ----------------------------------------------------------------------
+// A thread owns CPT consecutive positions of a partition's cluster-sorted cell order; a block of
+// RB_THREADS threads owns RB_CAP positions ("resident" items keep their labels in registers).
+constexpr int RB_CPT = 4;
+constexpr int RB_THREADS = 512;
+constexpr int RB_CAP = RB_CPT * RB_THREADS;  // 2048 positions per resident block
+constexpr int RB_JW = 8;                     // partitions per label tile: 8 x uint16 = one 16-byte load
+constexpr int RB_MAX_ROWS = 255;
+
+struct Item {       // one unit of work of the row-block kernel: rows [..] x cells [pos0, pos0+npos) of partition m
+    int32_t m;      // partition whose cluster-sorted order / table rows this block owns
+    int32_t pos0;   // first padded position (multiple of RB_CPT) in perm[m]
+    int32_t npos;   // padded positions (multiple of RB_CPT); > RB_CAP => single-cluster streaming item
+    int32_t nrows;  // table rows (clusters) in this block
+    int32_t jbeg;   // partner partitions j in [jbeg, jend)
+    int32_t jend;
+    int32_t sa;     // cluster size when nrows == 1 (else 0)
+    int32_t pad_;
+};
+
+// host planner (ca_plan.cpp)
+struct PlanOut {
+    std::vector<int32_t> cstart, crow;      // per cluster
+    std::vector<int32_t> pos0, npos, nrows, wide, sa;  // per item
+    int64_t total_pos = 0;
+};
+int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int32_t max_rows, PlanOut& out);
+
+// ---- prepared label set -----------------------------------------------------------------------------
+struct Labels {
+    int64_t n = 0;
+    int32_t m = 0;
+    int32_t* d_raw = nullptr;  // M x N int32 (partition-major)
+    bool ranked = false;    // min/max, ranks, compact sizes are valid
+    bool prepared = false;  // ... and the cell-major uint16 matrix
+    // filled by prepare():
+    std::vector<int32_t> h_min, h_max, h_k;
+    std::vector<int64_t> h_roff;  // offset of partition p's range in d_cnt / d_rank
+    bool identity = true;         // every partition's labels are already dense (rank == label - min)
+    int32_t kmax = 0, kp = 0, mpad = 0;
+    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_lab16;
+    std::vector<int32_t> h_sizes;  // [m][kp]
+};
+
+int prepare_ranks(Labels& L);
+int prepare_labels(Labels& L);
+
+// kernels' host launchers -----------------------------------------------------------------------------
+// ca_pack.cu
+int launch_fill_i32(int32_t* x, int64_t n, int32_t v, cudaStream_t s);
+int launch_minmax(const int32_t* raw, int64_t n, int32_t m, int32_t* d_min, int32_t* d_max, cudaStream_t s);
+int launch_count(const int32_t* raw, int64_t n, int32_t m, const int32_t* d_min, const int64_t* d_roff,
+                 const int32_t* h_range, int32_t max_range, uint32_t* d_cnt, cudaStream_t s);
+int launch_rank(const uint32_t* d_cnt, const int64_t* d_roff, const int32_t* d_min, const int32_t* d_max, int32_t m,
+                uint32_t* d_rank, int32_t* d_kcount, cudaStream_t s);
+int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_min,
+                 const int32_t* d_max, int32_t m, int32_t max_range, int32_t kp, int32_t* d_sizes, cudaStream_t s);
+int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t mpad, const int32_t* d_min,
+                             const uint32_t* d_rank, const int64_t* d_roff, uint16_t* d_lab16, cudaStream_t s);
+int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
+                const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
+                int64_t perm_stride, cudaStream_t s);
+
+// ca_rowblock.cu
+struct RowBlockParams {
+    const uint16_t* lab16;   // [n][mpad] compact labels, cell-major
+    const int32_t* perm;     // [m_slots][perm_stride] cluster-sorted cell ids, -1 = padding
+    const int32_t* slot_of;  // [m] partition -> perm slot (or -1)
+    const int32_t* sizes;    // [m][kp]
+    const uint16_t* crow;    // [m_slots][kp] row of a cluster inside its block
+    const double* w;         // [m] weights
+    const Item* items;
+    double* ecc;             // [n] accumulated with atomics (may be null)
+    double* sim;             // [m*m] accumulated with atomics (may be null)
+    int64_t perm_stride;
+    int32_t m, mpad, kp;
+    int32_t smem_bytes;      // dynamic shared memory available to sizes + tables
+    double inv_norm;
+};
+int launch_rowblock(const RowBlockParams& p, int32_t nitems, bool wide, cudaStream_t s, int* launches);
+int rowblock_smem_budget(int32_t kp, int32_t* max_rows_out);
+
+// ca_pair.cu
+int pair_contingency(const int32_t* d_a, const int32_t* d_b, int64_t n, int32_t min_a, int32_t min_b, int32_t ka,
+                     int32_t kb, uint32_t* d_table, uint32_t* d_sa, uint32_t* d_sb, int32_t* d_err, cudaStream_t s);
+int pair_ecs_gather(const int32_t* d_a, const int32_t* d_b, int64_t n, int32_t min_a, int32_t min_b, int32_t ka,
+                    const uint32_t* d_table, const uint32_t* d_sa, const uint32_t* d_sb, double* d_ecs,
+                    double* d_partial, int32_t* nblocks_out, cudaStream_t s);
+int pair_mean_from_table(const uint32_t* d_table, const uint32_t* d_sa, const uint32_t* d_sb, int32_t ka, int32_t kb,
+                         int64_t n, double* d_partial, int32_t* nblocks_out, cudaStream_t s);
+int reduce_partials(const double* d_partial, int32_t nblocks, double scale, double* d_out, cudaStream_t s);
+int launch_finish(double* ecc, int64_t n, double c0, double* sim, int32_t m, cudaStream_t s);
+
+// ca_dedup.cu
+int dedup_signatures(Labels& L, std::vector<uint64_t>& sig_lo, std::vector<uint64_t>& sig_hi, DevBuf& d_first, cudaStream_t s);
+int dedup_same_partition(Labels& L, const DevBuf& d_first, int32_t p, int32_t q, bool* same, cudaStream_t s);
+
+}  // namespace ca

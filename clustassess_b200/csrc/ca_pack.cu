@@ -1,0 +1,327 @@
+// ca_pack.cu -- label packing for the all-pairs ECS engine (sm_100a).
+//
+// Replaces the R-side label handling of the reference (labels stay in R vectors and are re-scanned
+// for min/max on EVERY pair: src/calculate_ecs.cpp:8,23; R/ECS.R:989) by one device pass per call:
+//   minmax   -> per-partition min / max                        (calculate_ecs.cpp:8,23 semantics)
+//   count    -> per-partition label histogram over [min, max]  (= cluster sizes, calculate_ecs.cpp:31)
+//   rank     -> dense rank of every used label (unused labels inside the range only produce all-zero
+//               table rows in the reference and never influence ECS, so the engine drops them)
+//   sizes    -> compact cluster sizes S[p][k]
+//   relabel_transpose -> cell-major uint16 label matrix lab16[n][mpad]
+//   sort     -> per-partition stable counting sort: perm[p] lists the cells grouped by cluster, every
+//               cluster at the padded start position chosen by the host planner (ca_plan.cpp)
+// All kernels are HBM-bound streaming passes over the M x N int32 input (coalesced loads), a few
+// percent of the row-block kernels' time.
+#include "ca_internal.h"
+
+namespace ca {
+
+static constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// per-partition min / max
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) minmax_kernel(const int32_t* __restrict__ raw, int64_t n, int32_t* __restrict__ d_min,
+                                                     int32_t* __restrict__ d_max) {
+    const int p = blockIdx.y;
+    const int32_t* x = raw + (int64_t)p * n;
+    int lo = INT32_MAX, hi = INT32_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int v = __ldg(x + i);
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(FULL, lo);
+    hi = __reduce_max_sync(FULL, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(d_min + p, lo);
+        atomicMax(d_max + p, hi);
+    }
+}
+
+__global__ void fill_i32_kernel(int32_t* x, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
+int launch_fill_i32(int32_t* x, int64_t n, int32_t v, cudaStream_t s) {
+    if (n <= 0) return CA_OK;
+    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, v);
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
+int launch_minmax(const int32_t* raw, int64_t n, int32_t m, int32_t* d_min, int32_t* d_max, cudaStream_t s) {
+    fill_i32_kernel<<<(m + 255) / 256, 256, 0, s>>>(d_min, m, INT32_MAX);
+    fill_i32_kernel<<<(m + 255) / 256, 256, 0, s>>>(d_max, m, INT32_MIN);
+    int64_t nb = (n + 256 * 16 - 1) / (256 * 16);
+    if (nb < 1) nb = 1;
+    if (nb > 4096) nb = 4096;
+    dim3 grid((unsigned)nb, (unsigned)m);
+    minmax_kernel<<<grid, 256, 0, s>>>(raw, n, d_min, d_max);
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches += 3;
+    return CA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-partition label histogram over [min, max]; shared-memory privatised when the range fits
+// ------------------------------------------------------------------------------------------------
+template <bool SMEM>
+__global__ void __launch_bounds__(512) count_kernel(const int32_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ d_min,
+                                                    const int64_t* __restrict__ d_roff, int32_t range_cap,
+                                                    uint32_t* __restrict__ d_cnt) {
+    extern __shared__ uint32_t sh[];
+    const int p = blockIdx.y;
+    const int32_t* x = raw + (int64_t)p * n;
+    const int mn = d_min[p];
+    uint32_t* g = d_cnt + d_roff[p];
+    const int range = (int)(d_roff[p + 1] - d_roff[p]);
+    const bool use_sh = SMEM && range <= range_cap;
+    if (use_sh) {
+        for (int i = threadIdx.x; i < range; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int v = __ldg(x + i) - mn;
+        if (use_sh)
+            atomicAdd(sh + v, 1u);
+        else
+            atomicAdd(g + v, 1u);
+    }
+    if (use_sh) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < range; i += blockDim.x) {
+            uint32_t c = sh[i];
+            if (c) atomicAdd(g + i, c);
+        }
+    }
+}
+
+int launch_count(const int32_t* raw, int64_t n, int32_t m, const int32_t* d_min, const int64_t* d_roff,
+                 const int32_t* /*h_range*/, int32_t max_range, uint32_t* d_cnt, cudaStream_t s) {
+    int64_t nb = (n + 512 * 32 - 1) / (512 * 32);
+    if (nb < 1) nb = 1;
+    if (nb > 1024) nb = 1024;
+    dim3 grid((unsigned)nb, (unsigned)m);
+    const int32_t cap = 12288;  // 48 KB of counters: no opt-in needed
+    if (max_range <= cap) {
+        count_kernel<true><<<grid, 512, (size_t)max_range * 4, s>>>(raw, n, d_min, d_roff, cap, d_cnt);
+    } else {
+        // mixed: partitions whose range fits use shared memory, the rest go straight to global atomics
+        count_kernel<true><<<grid, 512, (size_t)cap * 4, s>>>(raw, n, d_min, d_roff, cap, d_cnt);
+    }
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense rank of used labels: rank[v] = #{u < v : cnt[u] > 0}; one block per partition
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) rank_kernel(const uint32_t* __restrict__ d_cnt, const int64_t* __restrict__ d_roff,
+                                                    uint32_t* __restrict__ d_rank, int32_t* __restrict__ d_kcount) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    const int p = blockIdx.x;
+    const int64_t off = d_roff[p];
+    const int range = (int)(d_roff[p + 1] - off);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < range; base += blockDim.x) {
+        int v = base + threadIdx.x;
+        uint32_t f = (v < range && d_cnt[off + v] != 0) ? 1u : 0u;
+        unsigned bal = __ballot_sync(FULL, f);
+        uint32_t in_warp = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        uint32_t before = carry;
+        for (int w = 0; w < wid; w++) before += warp_tot[w];
+        if (v < range) d_rank[off + v] = before + in_warp;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += warp_tot[w];
+            carry += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) d_kcount[p] = (int32_t)carry;
+}
+
+int launch_rank(const uint32_t* d_cnt, const int64_t* d_roff, const int32_t*, const int32_t*, int32_t m, uint32_t* d_rank,
+                int32_t* d_kcount, cudaStream_t s) {
+    rank_kernel<<<m, 1024, 0, s>>>(d_cnt, d_roff, d_rank, d_kcount);
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
+__global__ void sizes_kernel(const uint32_t* __restrict__ d_cnt, const uint32_t* __restrict__ d_rank,
+                             const int64_t* __restrict__ d_roff, int32_t kp, int32_t* __restrict__ d_sizes) {
+    const int p = blockIdx.y;
+    const int64_t off = d_roff[p];
+    const int range = (int)(d_roff[p + 1] - off);
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < range; v += gridDim.x * blockDim.x) {
+        uint32_t c = d_cnt[off + v];
+        if (c) d_sizes[(int64_t)p * kp + d_rank[off + v]] = (int32_t)c;
+    }
+}
+
+int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d_roff, const int32_t*, const int32_t*,
+                 int32_t m, int32_t max_range, int32_t kp, int32_t* d_sizes, cudaStream_t s) {
+    int nb = (max_range + 255) / 256;
+    if (nb > 256) nb = 256;
+    if (nb < 1) nb = 1;
+    dim3 grid((unsigned)nb, (unsigned)m);
+    sizes_kernel<<<grid, 256, 0, s>>>(d_cnt, d_rank, d_roff, kp, d_sizes);
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// relabel + transpose: raw int32 [m][n] (partition-major)  ->  lab16 uint16 [n][mpad] (cell-major)
+// A block moves a 32-partition x 128-cell tile through shared memory: coalesced 4-byte reads along n,
+// 32-byte writes along the partition axis.
+// ------------------------------------------------------------------------------------------------
+constexpr int TP = 32, TC = 128;
+__global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* __restrict__ raw, int64_t n, int32_t m, int32_t mpad,
+                                                                const int32_t* __restrict__ d_min,
+                                                                const uint32_t* __restrict__ d_rank,
+                                                                const int64_t* __restrict__ d_roff,
+                                                                uint16_t* __restrict__ lab16) {
+    __shared__ uint16_t tile[TP][TC + 2];
+    const int64_t c0 = (int64_t)blockIdx.x * TC;
+    const int p0 = blockIdx.y * TP;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int pp = wid; pp < TP; pp += 8) {
+        const int p = p0 + pp;
+        if (p < m) {
+            const int32_t* x = raw + (int64_t)p * n;
+            const int mn = d_min[p];
+            const uint32_t* rk = d_rank ? d_rank + d_roff[p] : nullptr;
+#pragma unroll
+            for (int q = 0; q < TC / 32; q++) {
+                int64_t c = c0 + lane + 32 * q;
+                uint32_t v = 0;
+                if (c < n) {
+                    v = (uint32_t)(__ldg(x + c) - mn);
+                    if (rk) v = __ldg(rk + v);
+                }
+                tile[pp][lane + 32 * q] = (uint16_t)v;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < TC / 32; q++) tile[pp][lane + 32 * q] = 0;
+        }
+    }
+    __syncthreads();
+    const int cell = threadIdx.x >> 1, half = threadIdx.x & 1;
+    const int64_t c = c0 + cell;
+    if (c < n) {
+        uint32_t wds[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint32_t lo = tile[half * 16 + 2 * q][cell], hi = tile[half * 16 + 2 * q + 1][cell];
+            wds[q] = lo | (hi << 16);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(lab16 + c * mpad + p0 + half * 16);
+        dst[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        dst[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+    }
+}
+
+int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t mpad, const int32_t* d_min,
+                             const uint32_t* d_rank, const int64_t* d_roff, uint16_t* d_lab16, cudaStream_t s) {
+    if (n == 0) return CA_OK;
+    dim3 grid((unsigned)((n + TC - 1) / TC), (unsigned)(mpad / TP));
+    relabel_transpose_kernel<<<grid, 256, 0, s>>>(raw, n, m, mpad, d_min, d_rank, d_roff, d_lab16);
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stable counting sort of the cells of one partition by cluster: ONE WARP PER PARTITION.
+// The warp walks the cells in index order, 32 at a time; __match_any_sync groups equal labels inside
+// the 32, the group's first lane advances that cluster's cursor (shared memory) by the group size and
+// every lane writes its cell id at cursor + (its rank inside the group).  Cells of a cluster therefore
+// stay in ascending cell order, which keeps runs of equal partner labels together for the row-block
+// kernel's run compression.  500 partitions x 1M cells take ~1-2 ms: the chains are sequential per
+// partition but all partitions advance in parallel.
+// ------------------------------------------------------------------------------------------------
+template <bool SMEM_CURSOR>
+__global__ void __launch_bounds__(128) sort_kernel(const int32_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ d_min,
+                                                   const uint32_t* __restrict__ d_rank, const int64_t* __restrict__ d_roff,
+                                                   const int32_t* __restrict__ d_cstart, int32_t kp,
+                                                   const int32_t* __restrict__ d_parts, int32_t nparts,
+                                                   int32_t* __restrict__ d_perm, int64_t perm_stride,
+                                                   int32_t* __restrict__ d_cursor_scratch) {
+    extern __shared__ int32_t cur_sh[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + wid;
+    if (slot >= nparts) return;
+    const int p = d_parts[slot];
+    const int32_t* x = raw + (int64_t)p * n;
+    const int mn = d_min[p];
+    const uint32_t* rk = d_rank ? d_rank + d_roff[p] : nullptr;
+    const int32_t* cs = d_cstart + (int64_t)slot * kp;
+    int32_t* cur = SMEM_CURSOR ? cur_sh + (size_t)wid * kp : d_cursor_scratch + (int64_t)slot * kp;
+    for (int k = lane; k < kp; k += 32) cur[k] = cs[k];
+    __syncwarp();
+    int32_t* out = d_perm + (int64_t)slot * perm_stride;
+    constexpr int U = 4;
+    for (int64_t base = 0; base < n; base += 32 * U) {
+        uint32_t lab[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int64_t i = base + u * 32 + lane;
+            lab[u] = 0xffffffffu - (uint32_t)lane;  // unique key for out-of-range lanes
+            if (i < n) {
+                uint32_t v = (uint32_t)(__ldg(x + i) - mn);
+                lab[u] = rk ? __ldg(rk + v) : v;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int64_t i = base + u * 32 + lane;
+            if (base + u * 32 >= n) break;
+            const bool valid = i < n;
+            unsigned grp = __match_any_sync(FULL, lab[u]);
+            int leader = __ffs(grp) - 1;
+            int r = __popc(grp & ((1u << lane) - 1));
+            int32_t old = 0;
+            if (lane == leader && valid) {
+                old = cur[lab[u]];
+                cur[lab[u]] = old + __popc(grp);
+            }
+            if (!SMEM_CURSOR) __threadfence_block();
+            __syncwarp();
+            old = __shfl_sync(FULL, old, leader);
+            if (valid) out[old + r] = (int32_t)i;
+        }
+    }
+}
+
+int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
+                const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
+                int64_t perm_stride, cudaStream_t s) {
+    if (nparts == 0) return CA_OK;
+    CA_CUDA(cudaMemsetAsync(d_perm, 0xff, (size_t)nparts * (size_t)perm_stride * sizeof(int32_t), s));
+    size_t per_warp = (size_t)kp * 4;
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+    if (per_warp * wpb <= 200 * 1024) {
+        size_t smem = per_warp * wpb;
+        if (smem > 48 * 1024)
+            CA_CUDA(cudaFuncSetAttribute(sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sort_kernel<true><<<(nparts + wpb - 1) / wpb, wpb * 32, smem, s>>>(raw, n, d_min, d_rank, d_roff, d_cstart, kp, d_parts,
+                                                                           nparts, d_perm, perm_stride, nullptr);
+    } else {
+        static DevBuf scratch;  // cursors in global memory for very large cluster counts
+        CA_TRY(scratch.ensure((size_t)nparts * kp * 4));
+        sort_kernel<false><<<(nparts + 3) / 4, 128, 0, s>>>(raw, n, d_min, d_rank, d_roff, d_cstart, kp, d_parts, nparts, d_perm,
+                                                            perm_stride, scratch.as<int32_t>());
+    }
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
+}  // namespace ca

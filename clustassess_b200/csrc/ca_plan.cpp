@@ -1,0 +1,136 @@
+// ca_plan.cpp -- host-side row-block planner (pure C++, no CUDA).
+//
+// For one partition i with cluster sizes S[0..K) it decides where every cluster sits in the
+// cluster-sorted cell order perm_i and which clusters share one thread block of the row-block kernel:
+//   * every cluster's segment starts at a multiple of `align` (= cells per thread), so a thread never
+//     straddles two clusters; the tail of a segment is padding (perm = -1);
+//   * a cluster whose padded size exceeds `cap` becomes its own "streaming" item (one table row,
+//     cells processed in several sub-chunks; 32-bit counters if it has more than 65535 cells);
+//   * all other clusters are packed best-fit-decreasing into "resident" items of at most `cap`
+//     positions and at most `max_rows` table rows (their labels live in registers for a whole tile).
+// The reference has no counterpart: it re-scans both label vectors for every pair
+// (src/calculate_ecs.cpp:23-26); this planning is what lets one block own complete table rows.
+#include <algorithm>
+#include <map>
+#include <numeric>
+
+#include "ca_internal.h"
+
+namespace ca {
+
+int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int32_t max_rows, PlanOut& out) {
+    if (k < 0 || align <= 0 || cap < align || cap % align != 0 || max_rows < 1) {
+        set_error("plan_blocks: bad arguments (k=%d align=%d cap=%d max_rows=%d)", k, align, cap, max_rows);
+        return CA_E_ARG;
+    }
+    out.cstart.assign(k, 0);
+    out.crow.assign(k, 0);
+    out.pos0.clear();
+    out.npos.clear();
+    out.nrows.clear();
+    out.wide.clear();
+    out.sa.clear();
+    out.total_pos = 0;
+
+    std::vector<int32_t> order(k);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return sizes[a] > sizes[b]; });
+
+    auto padded = [&](int32_t s) { return (int64_t)((s + align - 1) / align) * align; };
+
+    struct Bin {
+        std::vector<int32_t> members;
+        int64_t used = 0;
+    };
+    std::vector<Bin> bins;
+    std::multimap<int64_t, int32_t> open;  // remaining capacity -> bin index (bins that can still take a row)
+    std::vector<int32_t> big;
+
+    for (int32_t idx = 0; idx < k; idx++) {
+        int32_t c = order[idx];
+        if (sizes[c] <= 0) {
+            set_error("plan_blocks: cluster %d has size %d (must be > 0)", c, sizes[c]);
+            return CA_E_ARG;
+        }
+        int64_t p = padded(sizes[c]);
+        if (p > cap) {
+            big.push_back(c);
+            continue;
+        }
+        auto it = open.lower_bound(p);  // best fit: smallest remaining capacity that still holds p
+        int32_t b;
+        if (it == open.end()) {
+            b = (int32_t)bins.size();
+            bins.emplace_back();
+        } else {
+            b = it->second;
+            open.erase(it);
+        }
+        bins[b].members.push_back(c);
+        bins[b].used += p;
+        int64_t rem = cap - bins[b].used;
+        if (rem >= align && (int32_t)bins[b].members.size() < max_rows) open.emplace(rem, b);
+    }
+
+    int64_t pos = 0;
+    auto push_item = [&](int64_t p0, int64_t np, int32_t nr, int32_t wide, int32_t sa) {
+        out.pos0.push_back((int32_t)p0);
+        out.npos.push_back((int32_t)np);
+        out.nrows.push_back(nr);
+        out.wide.push_back(wide);
+        out.sa.push_back(sa);
+    };
+    for (int32_t c : big) {  // streaming items first: they are the long ones
+        int64_t p = padded(sizes[c]);
+        out.cstart[c] = (int32_t)pos;
+        out.crow[c] = 0;
+        push_item(pos, p, 1, sizes[c] > 65535 ? 1 : 0, sizes[c]);
+        pos += p;
+    }
+    for (const Bin& b : bins) {
+        int64_t p0 = pos;
+        int32_t r = 0;
+        for (int32_t c : b.members) {
+            out.cstart[c] = (int32_t)pos;
+            out.crow[c] = r++;
+            pos += padded(sizes[c]);
+        }
+        push_item(p0, pos - p0, r, 0, r == 1 ? sizes[b.members[0]] : 0);
+    }
+    if (pos > 0x7fffff00LL) {
+        set_error("plan_blocks: %lld padded positions exceed the int32 position range", (long long)pos);
+        return CA_E_UNSUPPORTED;
+    }
+    out.total_pos = pos;
+    return CA_OK;
+}
+
+}  // namespace ca
+
+extern "C" int ca_plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int32_t max_rows,
+                              int32_t* cstart, int32_t* crow, int32_t* items, int32_t max_items, int64_t* npos_out) {
+    if (!sizes || !cstart || !crow || !items || !npos_out) {
+        ca::set_error("ca_plan_blocks: NULL argument");
+        return CA_E_ARG;
+    }
+    ca::PlanOut po;
+    int rc = ca::plan_blocks(sizes, k, align, cap, max_rows, po);
+    if (rc != CA_OK) return rc;
+    int32_t ni = (int32_t)po.pos0.size();
+    if (ni > max_items) {
+        ca::set_error("ca_plan_blocks: %d items exceed max_items=%d", ni, max_items);
+        return CA_E_ARG;
+    }
+    for (int32_t c = 0; c < k; c++) {
+        cstart[c] = po.cstart[c];
+        crow[c] = po.crow[c];
+    }
+    for (int32_t t = 0; t < ni; t++) {
+        items[4 * t + 0] = po.pos0[t];
+        items[4 * t + 1] = po.npos[t];
+        items[4 * t + 2] = po.nrows[t];
+        items[4 * t + 3] = po.wide[t];
+    }
+    *npos_out = po.total_pos;
+    return ni;
+}

@@ -1,0 +1,153 @@
+/*
+ * clustassess_b200.h -- C ABI of the B200-native element-centric-similarity (ECS) library.
+ *
+ * This is the drop-in boundary for ClustAssess's flat-disjoint ECS hot path.  The R package reaches its
+ * native code through .Call (reference: R/RcppExports.R:4-14 -> src/RcppExports.cpp:14-51, registration
+ * table src/RcppExports.cpp:129-145); a ~100-line C shim (r/clustassess_shim.c)
+ * forwards those .Call entries to the functions below.  Plain pointers and sizes only: no R, Rcpp or
+ * torch types cross this boundary.
+ *
+ * Conventions
+ *   - Every function returns CA_OK (0) or a negative CA_E_* code; ca_last_error() gives the message.
+ *     Nothing here throws, longjmps or calls back into the host language (reference error convention:
+ *     BEGIN_RCPP/END_RCPP at src/RcppExports.cpp:17,26 -- the shim raises Rf_error after we return).
+ *   - Labels are int32 (R INTSXP / factor codes; the shim truncates REALSXP like Rcpp's
+ *     input_parameter<IntegerVector>, src/RcppExports.cpp:20-21).  NA_integer_ (INT_MIN) is rejected with
+ *     CA_E_NA_LABEL (the reference has undefined behaviour there).
+ *   - A "label matrix" is partition-major M x N: partition p occupies labels[p*n .. p*n+n), which is
+ *     R's list-of-vectors layout.  The *_cols variants take M separate column pointers instead.
+ *   - Inputs are never written.  Outputs are caller-allocated; "host" pointers unless the name ends in
+ *     _dev.  There is NO CPU fallback: without a CUDA device every compute entry returns CA_E_NO_DEVICE.
+ *   - fp64 throughout; per-pair ECS is one IEEE division (bit-identical to the reference), set-level
+ *     results are within 1e-9 absolute of the reference (summation order differs).
+ */
+#ifndef CLUSTASSESS_B200_H
+#define CLUSTASSESS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CA_OK 0
+#define CA_E_NO_DEVICE (-1)   /* no usable CUDA device / ca_init failed                         */
+#define CA_E_CUDA (-2)        /* a CUDA runtime call failed (message has the CUDA error string)  */
+#define CA_E_ARG (-3)         /* bad argument (NULL pointer, negative size, m < 2 where required) */
+#define CA_E_NA_LABEL (-4)    /* a label equals INT_MIN (R's NA_integer_)                        */
+#define CA_E_RANGE (-5)       /* label outside [min, min+k) passed to ca_contingency              */
+#define CA_E_UNSUPPORTED (-6) /* label range or cluster count beyond the engine's limits          */
+#define CA_E_NOMEM (-7)       /* host or device allocation failed                                 */
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+
+/* Select the device(s) this process computes on.  devices==NULL or ndev<=0 -> device 0.  Idempotent.
+ * One process drives one GPU; multi-GPU jobs run one process per GPU and shard with rank/world below
+ * (reference analogue: the foreach %dopar% workers of R/ECS.R:953). */
+int ca_init(const int *devices, int ndev);
+void ca_shutdown(void);
+const char *ca_last_error(void);
+int ca_version(void);
+
+/* Launch all work on this CUDA stream (a cudaStream_t passed as void*).  NULL restores the library's
+ * own stream.  Lets a caller time the kernels with its own events. */
+int ca_set_stream(void *cuda_stream);
+
+/* ---- legacy per-pair entry points (replace the three Rcpp routines one for one) ------------------- */
+
+/* Host scan for min/max of a label vector (R computes min(mb) itself before calling myContTable,
+ * R/ECS.R:989).  */
+int ca_label_range(const int32_t *x, int64_t n, int32_t *min_out, int32_t *max_out);
+
+/* myContTable(a, b, min_a, min_b) -- src/calculate_ecs.cpp:7-19, .Call entry src/RcppExports.cpp:16.
+ * table_out: ka x kb int32, COLUMN-major like the R matrix it fills: T[i + j*ka] = #{n: a_n-min_a == i,
+ * b_n-min_b == j}, with ka = max(a)-min_a+1, kb = max(b)-min_b+1 (labels unused inside the range keep
+ * all-zero rows/cols, as in the reference).  sizes_a (ka) / sizes_b (kb) may be NULL; they receive the
+ * row / column sums (= cluster sizes, calculate_ecs.cpp:31). */
+int ca_contingency(const int32_t *a, const int32_t *b, int64_t n, int32_t min_a, int32_t min_b, int32_t ka,
+                   int32_t kb, int32_t *table_out, int32_t *sizes_a, int32_t *sizes_b);
+
+/* disjointECS(mb1, mb2) -- src/calculate_ecs.cpp:22-46, .Call entry src/RcppExports.cpp:30.
+ * ecs_out[n] = T[a_n][b_n] / max(|A(a_n)|, |B(b_n)|).  mean_out (may be NULL) receives mean(ecs_out),
+ * which is what element_sim_matrix / weighted_element_consistency take of it (R/ECS.R:954,1479). */
+int ca_ecs_pair(const int32_t *a, const int32_t *b, int64_t n, double *ecs_out, double *mean_out);
+
+/* disjointECSaverage(mb1, mb2) -- src/calculate_ecs.cpp:49-70, .Call entry src/RcppExports.cpp:42.
+ * sum T^2 / (n * max(S1, S2)) over non-empty cells; n*max is formed in fp64 (the reference's int*int
+ * overflows for n*max >= 2^31, and yields NaN when both ranges contain an unused label). */
+int ca_ecs_pair_mean(const int32_t *a, const int32_t *b, int64_t n, double *mean_out);
+
+/* ---- batched entry points (the all-pairs hot path) ----------------------------------------------- */
+
+/* weighted_element_consistency(list, weights, calculate_sim_matrix) -- R/ECS.R:1446-1500, and through it
+ * element_consistency / merge_partitions(ecs_thresh = 1) -- R/ECS.R:1350-1386, 1166-1226.
+ *   ecc_out[n] = [ sum_i w_i(w_i-1)/2 + sum_{i<j} w_i w_j ECS_ij[n] ] / [ W(W-1)/2 ],  W = sum w.
+ * weights == NULL -> all 1 (R/ECS.R:1466-1468).  sim_out (m x m, symmetric, unit diagonal; may be NULL)
+ * receives mean(ECS_ij) (R/ECS.R:1479-1482).  m < 2 -> CA_E_ARG (R stop(), R/ECS.R:1451). */
+int ca_consistency(const int32_t *labels, int64_t n, int32_t m, const double *weights, double *ecc_out,
+                   double *sim_out);
+int ca_consistency_cols(const int32_t *const *cols, int64_t n, int32_t m, const double *weights,
+                        double *ecc_out, double *sim_out);
+
+/* element_sim_matrix_flat_disjoint(mb_list) -- R/ECS.R:931-981 (matrix output): sim_out m x m,
+ * sim[i][j] = mean(ECS_ij), unit diagonal; m == 1 -> the 1x1 matrix 1 (R/ECS.R:938-940). */
+int ca_sim_matrix(const int32_t *labels, int64_t n, int32_t m, double *sim_out);
+int ca_sim_matrix_cols(const int32_t *const *cols, int64_t n, int32_t m, double *sim_out);
+
+/* element_agreement_flat_disjoint(reference, list) -- R/ECS.R:1625-1648:
+ * agr_out[n] = mean_p ECS(reference, labels[p])[n].   */
+int ca_agreement(const int32_t *reference, const int32_t *labels, int64_t n, int32_t m, double *agr_out);
+
+/* merge_identical_partitions(list) -- R/ECS.R:1021-1054 with are_identical_memberships R/ECS.R:984-1016:
+ * greedy first-match dedup.  keep_out[u] = index of the u-th kept partition, freq_out[u] = summed
+ * frequency (freq_in == NULL -> all 1), *u_out = number kept.  Reproduces the reference's quirk that a
+ * partition with an unused label inside its range is never identical to anything unless K == n.
+ *  */
+int ca_merge_identical(const int32_t *labels, int64_t n, int32_t m, const double *freq_in, int32_t *keep_out,
+                       double *freq_out, int32_t *u_out);
+
+/* ---- device-resident label sets (pipeline glue; also what bench.py times as "value") --------------- */
+
+typedef struct ca_labels ca_labels_t;
+
+int ca_labels_create(int64_t n, int32_t m, ca_labels_t **out); /* device M x N int32, uninitialised    */
+int ca_labels_upload(ca_labels_t *h, const int32_t *labels);   /* host -> device, whole matrix         */
+int ca_labels_upload_col(ca_labels_t *h, int32_t p, const int32_t *col);
+void *ca_labels_device_ptr(ca_labels_t *h);                    /* raw device matrix (int32 M x N)      */
+int ca_labels_invalidate(ca_labels_t *h);                      /* call after writing through the ptr   */
+int ca_labels_destroy(ca_labels_t *h);
+
+/* One rank's share of the all-pairs job on a device-resident label set.
+ *   rank/world : this process handles the partitions i with zigzag(i) == rank and all their pairs (i,j>i);
+ *                world == 1 -> everything.
+ *   ecc_dev    : device double[n]   (may be NULL)  += sum over owned i of (w_i/norm) sum_{j>i} w_j ECS_ij
+ *   sim_dev    : device double[m*m] (may be NULL)  += sum_n ECS_ij[n] at [i*m+j] for owned i, j>i
+ * Both buffers must be zeroed by the caller (or hold the values to accumulate onto).  After summing the
+ * buffers over ranks (one NCCL allreduce each), ca_consistency_finish_dev() adds the identical-pair
+ * constant, and mirrors / normalises the matrix. */
+int ca_consistency_partial_dev(ca_labels_t *h, const double *weights_host, int32_t rank, int32_t world,
+                               double *ecc_dev, double *sim_dev);
+int ca_consistency_finish_dev(int64_t n, int32_t m, const double *weights_host, double *ecc_dev,
+                              double *sim_dev);
+
+/* Stage timings (milliseconds, CUDA events on the library's stream) of the last batched call on this
+ * thread: [0] pack (min/max, cluster sizes, compaction)  [1] relabel + transpose to the cell-major uint16
+ * layout  [2] host planning (row blocks)  [3] per-partition stable counting sort  [4] row-block ECS
+ * kernels  [5] finish  [6] whole call  [7] number of row-block kernel launches.  Returns how many
+ * entries were written (<= cap). */
+int ca_get_profile(double *ms_out, int cap);
+
+/* ---- host-only test hook --------------------------------------------------------------------------- */
+
+/* The row-block planner, exposed so that CPU tests can check its invariants without a GPU.
+ * sizes[k] > 0 for k < K.  align = cells per thread, cap = cells per resident block, max_rows = table rows
+ * that fit in shared memory.  Outputs: cstart[k] (first padded position of cluster k), crow[k] (row of
+ * cluster k inside its block), items[4*t .. 4*t+3] = {pos0, npos, nrows, wide}.  Returns the number of
+ * items (<= max_items) or a negative error; *npos_out = padded positions in total. */
+int ca_plan_blocks(const int32_t *sizes, int32_t k, int32_t align, int32_t cap, int32_t max_rows,
+                   int32_t *cstart, int32_t *crow, int32_t *items, int32_t max_items, int64_t *npos_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLUSTASSESS_B200_H */

@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle / golden vectors.
+
+Bars: contingency tables and cluster sizes bit-exact (int32); per-pair ECS
+bit-exact (one IEEE fp64 division); ECC / weighted ECC / ECS matrix within 1e-9 absolute (fp64; only the
+summation order differs from the reference).  The reference's own property tests
+(tests/testthat/test-ECS.R) are restated on the GPU library further down.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from clustassess_b200 import _capi, ecs, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9  # fp64 absolute tolerance for set-level results (north_star)
+
+
+# ---- golden vectors generated from the unmodified reference C++ ------------------------------------------
+def test_golden_pairs(golden):
+    for k in range(int(golden["n_pairs"])):
+        a, b = golden[f"p{k}_a"], golden[f"p{k}_b"]
+        tab, sa, sb = ecs.contingency_table(a, b)
+        gt = golden[f"p{k}_table"]
+        assert np.array_equal(tab, gt), "table of golden pair %d" % k
+        assert np.array_equal(sa, gt.sum(1)) and np.array_equal(sb, gt.sum(0))
+        e = ecs.element_sim_elscore(a, b)
+        assert np.array_equal(e, golden[f"p{k}_ecs"]), "per-element ECS of golden pair %d must be bit-identical" % k
+        avg = float(golden[f"p{k}_avg"])
+        if np.isnan(avg):  # the reference's 0/0 quirk for labels unused in both ranges (see test_oracle.py)
+            avg = float(golden[f"p{k}_ecs"].mean())
+        assert abs(ecs.element_sim(a, b) - avg) < 1e-12
+
+
+def test_golden_set_level(golden):
+    L, w = golden["set_labels"], golden["set_weights"]
+    res = ecs.weighted_element_consistency(list(L), weights=w, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - golden["set_ecc_w"]).max() < TOL
+    assert np.abs(res["ecs_matrix"] - golden["set_sim"]).max() < TOL
+    assert np.abs(ecs.element_sim_matrix(list(L)) - golden["set_sim"]).max() < TOL
+    assert np.abs(ecs.weighted_element_consistency(list(L)) - golden["set_ecc_unw"]).max() < TOL
+    assert np.abs(ecs.element_consistency(list(L)) - golden["set_ecc_unw"]).max() < TOL
+
+
+def test_documented_known_answer(golden):
+    # merge_partitions(list(c(1,1,2), c(2,2,2), c("B","B","A")), 1)  -- docs/reference/merge_partitions.html:117-142
+    res = ecs.merge_partitions([[1, 1, 2], [2, 2, 2], ["B", "B", "A"]], 1)
+    assert [p["freq"] for p in res["partitions"]] == [2, 1]
+    assert list(res["partitions"][0]["mb"]) == [1, 1, 2] and list(res["partitions"][1]["mb"]) == [2, 2, 2]
+    assert np.abs(np.asarray(res["ecc"]) - golden["doc_ecc"]).max() < 5e-8  # the doc prints 7 digits
+    assert np.allclose(res["ecc"], [7 / 9, 7 / 9, 5 / 9], atol=1e-15)
+    assert abs(res["partitions"][0]["avg_agreement"] - 0.2777778) < 5e-8
+
+
+# ---- the reference's own tests (tests/testthat/test-ECS.R), restated ------------------------------------------
+def _lists(n_lists=100, k=10, n=100, seed=1234):
+    rng = np.random.default_rng(seed)
+    return [rng.integers(1, k + 1, size=n) for _ in range(n_lists)]
+
+
+def test_ecs_between_0_and_1():  # test-ECS.R:1-12
+    xs = _lists(200)
+    for x, y in zip(xs[::2], xs[1::2]):
+        e = ecs.element_sim_elscore(x, y)
+        assert 0 <= e.min() and e.max() <= 1
+
+
+def test_type_invariance():  # test-ECS.R:18-32
+    import pandas as pd
+
+    xs = _lists(20)
+    for x, y in zip(xs[::2], xs[1::2]):
+        e1 = ecs.element_sim_elscore(x, y)
+        e2 = ecs.element_sim_elscore(pd.Categorical(x), pd.Categorical(y))
+        e3 = ecs.element_sim_elscore(x.astype(str), y.astype(str))
+        e4 = ecs.element_sim_elscore(x.astype(np.float64), y.astype(np.float64))
+        assert np.array_equal(e1, e2) and np.array_equal(e1, e3) and np.array_equal(e1, e4)
+        assert np.array_equal(e1, oracle.corrected_l1_mb(x, y)) or np.abs(e1 - oracle.corrected_l1_mb(x, y)).max() < 1e-12
+
+
+def test_element_sim_is_mean_of_elscore():  # test-ECS.R:34-44
+    xs = _lists(40)
+    for x, y in zip(xs[::2], xs[1::2]):
+        assert abs(np.mean(ecs.element_sim_elscore(x, y)) - ecs.element_sim(x, y)) < 1e-12
+
+
+def test_ecc_is_average_of_pairwise_ecs():  # test-ECS.R:98-120
+    cl = _lists(100)
+    expected = ecs.element_consistency(cl)
+    acc = np.zeros(100)
+    for i in range(0, 100):
+        for j in range(i + 1, 100):
+            acc += 2 * oracle.disjoint_ecs(cl[i], cl[j])
+    assert np.abs(acc / (100 * 99) - expected).max() < TOL
+
+
+def test_ecs_matrix():  # test-ECS.R:122-140
+    cl = _lists(100)
+    mat = ecs.element_sim_matrix(cl)
+    assert np.array_equal(mat, mat.T) and np.all(np.diag(mat) == 1)
+    rng = np.random.default_rng(0)
+    for _ in range(60):
+        i, j = sorted(rng.choice(100, size=2, replace=False))
+        assert abs(mat[i, j] - ecs.element_sim_elscore(cl[i], cl[j]).mean()) < TOL
+    df = ecs.element_sim_matrix(cl[:5], output_type="data.frame")  # R/ECS.R:967-978
+    assert list(df["i.clustering"][:6]) == [1, 2, 3, 4, 5, 1] and list(df["j.clustering"][:6]) == [1, 1, 1, 1, 1, 2]
+    assert abs(df["element_sim"][5 * 1 + 3] - mat[3, 1]) < 1e-15
+
+
+def test_merge_partitions_properties():  # test-ECS.R:142-188
+    rng = np.random.default_rng(5)
+    base = [rng.integers(1, 4, size=60) for _ in range(6)]
+    cl = [base[i % 6] if i % 3 else (base[i % 6] % 3) * 7 + 2 for i in range(30)]  # many relabelled duplicates
+    for thresh in (1, 0.99, 0.5):
+        res = ecs.merge_partitions(cl, ecs_thresh=thresh, return_ecs_matrix=True)
+        parts = res["partitions"]
+        assert sum(p["freq"] for p in parts) == 30
+        for p in parts:
+            assert any(np.array_equal(p["mb"], c) for c in cl)
+        mbs = [p["mb"] for p in parts]
+        if len(mbs) > 1:
+            w = [p["freq"] for p in parts]
+            assert np.abs(res["ecc"] - ecs.weighted_element_consistency(mbs, weights=w)).max() < TOL
+            assert np.abs(res["ecs_matrix"] - ecs.element_sim_matrix(mbs)).max() < TOL
+        f = [p["freq"] for p in parts]
+        assert all(f[i] >= f[i + 1] for i in range(len(f) - 1))
+        res2 = ecs.merge_partitions(cl, ecs_thresh=thresh, order_logic="avg_agreement")
+        ag = [p["avg_agreement"] for p in res2["partitions"]]
+        assert all(ag[i] >= ag[i + 1] for i in range(len(ag) - 1))
+    keep, freq = oracle.merge_identical_partitions(np.stack(cl))
+    got = ecs.merge_identical_partitions([{"mb": c, "freq": 1} for c in cl])
+    assert [g["freq"] for g in got] == freq.tolist()
+    assert all(np.array_equal(g["mb"], cl[k]) for g, k in zip(got, keep))
+
+
+def test_dedup_reference_quirks():
+    # label gap inside the range: never identical, even to itself, unless range == n (R/ECS.R:994-1015)
+    cl = [[1, 3, 3, 3], [1, 3, 3, 3], [1, 2, 2, 2], [5, 4, 4, 4], [1, 3, 3, 3]]
+    keep, freq = oracle.merge_identical_partitions(np.array(cl))
+    got = ecs.merge_identical_partitions([{"mb": c, "freq": 1} for c in cl])
+    assert [g["freq"] for g in got] == freq.tolist() and len(got) == keep.size
+    cl = [[1, 1, 3], [1, 3, 3], [2, 2, 1]]  # range == n: the reference calls these identical
+    keep, freq = oracle.merge_identical_partitions(np.array(cl))
+    got = ecs.merge_identical_partitions([{"mb": c, "freq": 1} for c in cl])
+    assert [g["freq"] for g in got] == freq.tolist() and len(got) == keep.size
+    # ecc is invariant to all of this
+    cl = [[1, 3, 3, 3, 9], [1, 3, 3, 3, 9], [1, 2, 2, 2, 2], [5, 4, 4, 4, 4]]
+    assert np.abs(ecs.element_consistency(cl) - oracle.element_consistency(np.array(cl))).max() < TOL
+
+
+# ---- BASELINE.json configurations against the oracle ------------------------------------------------------------
+def test_config1_full():
+    L, _ = synth.config("C1")
+    assert np.abs(ecs.element_consistency(list(L)) - oracle.element_consistency(L)).max() < TOL
+    res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
+    ecc, sim = oracle.weighted_element_consistency(L, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+
+
+def test_config2_full():
+    (a, b), _ = synth.config("C2")
+    tab, sa, sb = ecs.contingency_table(a, b)
+    assert tab.shape == (20, 35) and np.array_equal(tab, oracle.cont_table(a, b))
+    assert np.array_equal(sa, np.bincount(a)[1:]) and np.array_equal(sb, np.bincount(b)[1:])
+    e = ecs.element_sim_elscore(a, b, alpha=0.9)
+    assert np.array_equal(e, oracle.disjoint_ecs(a, b))
+    assert abs(ecs.element_sim(a, b) - oracle.disjoint_ecs_average(a, b)) < 1e-12
+
+
+def test_config3_reduced_weighted():
+    L, w = synth.config("C3", m=12)
+    res = ecs.weighted_element_consistency(list(L), weights=w, calculate_sim_matrix=True)
+    ecc, sim = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+
+
+def test_config4_reduced_matrix():
+    L, _ = synth.config("C4", m=24)
+    assert np.abs(ecs.element_sim_matrix(list(L)) - oracle.element_sim_matrix(L)).max() < TOL
+
+
+@pytest.mark.parametrize("family", ["louvain", "uniform"])
+def test_config5_reduced(family):
+    L, _ = synth.config("C5", m=6, n=400_000, family=family)
+    res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
+    ecc, sim = oracle.weighted_element_consistency(L, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+    # the global-table contingency kernel (ka*kb beyond shared memory) is bit-exact too
+    tab, sa, sb = ecs.contingency_table(L[0], L[1])
+    assert np.array_equal(tab, oracle.cont_table(L[0], L[1]))
+    assert np.array_equal(ecs.element_sim_elscore(L[0], L[1]), oracle.disjoint_ecs(L[0], L[1]))
+
+
+def test_element_agreement():
+    L, _ = synth.config("C3", m=7, n=30_000)
+    got = ecs.element_agreement(L[0], list(L[1:]))
+    want = np.mean([oracle.corrected_l1_mb(L[0], L[p]) for p in range(1, 7)], axis=0)  # R/ECS.R:1639-1647
+    assert np.abs(got - want).max() < TOL
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 127, 2049, 4099])
+def test_ragged_sizes(n):
+    rng = np.random.default_rng(n)
+    L = rng.integers(-3, 6, size=(5, n)).astype(np.int32)
+    ecc, sim = oracle.weighted_element_consistency(L, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+    assert np.array_equal(ecs.element_sim_elscore(L[0], L[1]), oracle.disjoint_ecs(L[0], L[1]))
+
+
+def test_two_partitions_single_cluster_and_singletons():
+    n = 3000
+    one = np.ones(n, dtype=np.int32)
+    single = np.arange(n, dtype=np.int32) + 10
+    rng = np.random.default_rng(3)
+    mid = rng.integers(0, 40, size=n).astype(np.int32)
+    L = np.stack([one, single, mid, single[::-1].copy()])
+    ecc, sim = oracle.weighted_element_consistency(L, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+    two = ecs.weighted_element_consistency([one, mid])
+    assert np.abs(two - oracle.weighted_element_consistency(np.stack([one, mid]))).max() < TOL
+
+
+def test_label_gaps_negative_labels_and_weights():
+    rng = np.random.default_rng(11)
+    n = 5000
+    L = np.stack([rng.choice([-7, -2, 0, 5, 900], size=n), rng.choice([3, 4, 10_000], size=n),
+                  rng.integers(100, 140, size=n), rng.choice([1, 65_000], size=n)]).astype(np.int32)
+    w = np.array([3.0, 1.0, 2.0, 5.0])
+    ecc, sim = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), weights=w, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+    tab, _, _ = ecs.contingency_table(L[0], L[2])
+    assert np.array_equal(tab, oracle.cont_table(L[0], L[2]))  # empty rows/cols kept, like the reference
+
+
+def test_huge_cluster_wide_counters_and_streaming_items():
+    rng = np.random.default_rng(13)
+    n = 150_000  # two clusters of ~75k cells: beyond 16-bit counters, processed as streaming items
+    L = np.stack([rng.integers(0, 2, size=n), rng.integers(0, 3, size=n), rng.integers(0, 1500, size=n),
+                  (np.arange(n) < 70_000).astype(np.int64)]).astype(np.int32)
+    ecc, sim = oracle.weighted_element_consistency(L, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+
+
+def test_many_clusters_one_block_per_sm_configuration():
+    rng = np.random.default_rng(17)
+    n = 60_000
+    L = np.stack([rng.integers(0, 9000, size=n), rng.integers(0, 20, size=n), rng.integers(0, 6000, size=n)]).astype(np.int32)
+    ecc, sim = oracle.weighted_element_consistency(L, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+
+
+def test_identical_partitions_and_m_not_multiple_of_tile():
+    rng = np.random.default_rng(19)
+    base = rng.integers(0, 12, size=4000).astype(np.int32)
+    L = np.stack([base, base, (base + 5) % 12, rng.integers(0, 12, size=4000).astype(np.int32)] * 9 + [base])  # M = 37
+    assert np.abs(ecs.element_consistency(list(L)) - oracle.element_consistency(L)).max() < TOL
+    assert np.abs(ecs.weighted_element_consistency(list(L)) - oracle.weighted_element_consistency(L)).max() < TOL
+
+
+def test_errors_through_the_c_abi():
+    lib = _capi.lib()
+    a = np.array([1, 2, np.iinfo(np.int32).min], dtype=np.int32)
+    out = np.zeros(3)
+    assert lib.ca_ecs_pair(a, a, 3, out.ctypes.data, None) == -4  # CA_E_NA_LABEL
+    L = np.stack([a, a])
+    assert lib.ca_consistency(L.reshape(-1), 3, 2, None, out, None) == -4
+    assert lib.ca_consistency(L.reshape(-1), 3, 1, None, out, None) == _capi.CA_E_ARG
+    b = np.array([1, 2, 3], dtype=np.int32)
+    tab = np.zeros(4, dtype=np.int32)
+    assert lib.ca_contingency(b, b, 3, 1, 1, 2, 2, tab, None, None) == -5  # CA_E_RANGE: label 3 outside [1, 3)
+    with pytest.raises(_capi.ClustAssessError):
+        ecs.weighted_element_consistency([np.arange(70_000), np.arange(70_000)])  # > 65535 clusters
+
+
+def test_rank_sharding_sums_to_the_whole():
+    """ca_consistency_partial_dev over the ranks of a world of 3, accumulated into the same buffers, equals
+    the single-rank job (the allreduce is a plain sum)."""
+    import torch
+
+    L, w = synth.config("C3", m=11, n=20_000)
+    m, n = L.shape
+    ecc_ref, sim_ref = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+    dl = _capi.DeviceLabels(n, m).upload(L)
+    ecc = torch.zeros(n, dtype=torch.float64, device="cuda")
+    sim = torch.zeros(m * m, dtype=torch.float64, device="cuda")
+    for r in range(3):
+        dl.consistency_partial(w, r, 3, ecc.data_ptr(), sim.data_ptr())
+    _capi.consistency_finish(n, m, w, ecc.data_ptr(), sim.data_ptr())
+    torch.cuda.synchronize()
+    assert np.abs(ecc.cpu().numpy() - ecc_ref).max() < TOL
+    assert np.abs(sim.cpu().numpy().reshape(m, m) - sim_ref).max() < TOL
+    dl.close()

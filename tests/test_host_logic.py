@@ -1,0 +1,129 @@
+"""CPU tests of everything that does not need a GPU: the C-ABI library loads and exports every symbol
+include/clustassess_b200.h declares, the host-side planner keeps its invariants, argument errors are
+raised with the reference's messages, and compute calls FAIL LOUDLY without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from clustassess_b200 import _capi, ecs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "clustassess_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ca_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _capi.lib()
+    for name in declared:
+        assert hasattr(lib, name), "header declares %s but the library does not export it" % name
+    assert declared == set(_capi.SYMBOLS), (declared ^ set(_capi.SYMBOLS))
+    assert lib.ca_version() >= 100
+
+
+def _plan(sizes, align=4, cap=2048, max_rows=7):
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    k = sizes.size
+    cs = np.zeros(k, np.int32)
+    cr = np.zeros(k, np.int32)
+    items = np.zeros(4 * (k + 1), np.int32)
+    npos = C.c_int64()
+    ni = _capi.lib().ca_plan_blocks(sizes, k, align, cap, max_rows, cs, cr, items, k + 1, C.byref(npos))
+    assert ni >= 0, _capi.lib().ca_last_error()
+    return cs, cr, items[: 4 * ni].reshape(-1, 4), npos.value
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_planner_invariants(seed):
+    rng = np.random.default_rng(seed)
+    k = int(rng.integers(1, 400))
+    sizes = np.maximum(1, rng.lognormal(4.0, 1.6, size=k).astype(np.int64))
+    if seed == 3:
+        sizes[0] = 70000  # a cluster that needs 32-bit counters
+    align, cap, max_rows = 4, 2048, int(rng.integers(1, 12))
+    cs, cr, items, npos = _plan(sizes, align, cap, max_rows)
+    pad = (sizes + align - 1) // align * align
+    # segments are aligned, disjoint and cover [0, npos)
+    order = np.argsort(cs)
+    assert (cs % align == 0).all()
+    assert (cs[order][1:] == (cs + pad)[order][:-1]).all() and cs[order][0] == 0
+    assert npos == pad.sum()
+    # every cluster lies in exactly one item; rows are 0..nrows-1 inside it; limits hold
+    covered = 0
+    for pos0, np_, nrows, wide in items:
+        inside = np.where((cs >= pos0) & (cs < pos0 + np_))[0]
+        assert inside.size == nrows and pad[inside].sum() == np_
+        assert sorted(cr[inside].tolist()) == list(range(nrows))
+        assert nrows <= max_rows
+        if np_ > cap:
+            assert nrows == 1
+        assert bool(wide) == bool(sizes[inside].max() > 65535 and np_ > cap)
+        covered += nrows
+    assert covered == k
+    # best-fit-decreasing keeps resident blocks reasonably full
+    res = items[items[:, 1] <= cap]
+    small = pad[pad <= cap]
+    lower = max(-(-int(small.sum()) // cap), -(-small.size // max_rows))
+    assert res.shape[0] <= 2 * lower + 1
+
+
+def test_planner_rejects_bad_input():
+    cs = np.zeros(2, np.int32)
+    items = np.zeros(12, np.int32)
+    npos = C.c_int64()
+    bad = np.array([5, 0], dtype=np.int32)
+    assert _capi.lib().ca_plan_blocks(bad, 2, 4, 2048, 4, cs, cs.copy(), items, 3, C.byref(npos)) == _capi.CA_E_ARG
+    assert b"size" in _capi.lib().ca_last_error()
+
+
+def test_argument_errors_match_the_reference():
+    # R/ECS.R:177-178, 1374-1376, 1451-1452, 861-863
+    with pytest.raises(ValueError, match="do not have the same length"):
+        ecs.element_sim_elscore([1, 2, 3], [1, 2])
+    with pytest.raises(ValueError, match="do not have the same length"):
+        ecs.element_sim([1, 2, 3], [1, 2])
+    with pytest.raises(ValueError, match="At least two clusterings"):
+        ecs.element_consistency([[1, 2, 3]])
+    with pytest.raises(ValueError, match="At least two clusterings"):
+        ecs.weighted_element_consistency([[1, 2, 3]])
+    with pytest.raises(ValueError, match="output_type must be"):
+        ecs.element_sim_matrix([[1, 2], [2, 1]], output_type="list")
+    with pytest.raises(ValueError, match="ecs_thresh"):
+        ecs.merge_partitions([[1, 2], [2, 1]], ecs_thresh="a")
+    with pytest.raises(ValueError, match="order parameter"):
+        ecs.merge_partitions([[1, 2], [2, 1]], order_logic="size")
+    import pandas as pd
+
+    with pytest.raises(ValueError, match="Not all elements"):
+        ecs.element_sim_elscore(pd.Series([1, 2], index=["a", "b"]), pd.Series([1, 2], index=["a", "c"]))
+
+
+def test_label_coercion():
+    import pandas as pd
+
+    assert ecs._as_labels([1.9, -2.9, 3.0]).tolist() == [1, -2, 3]  # doubles truncate like Rcpp's int cast
+    assert ecs._as_labels(pd.Categorical(["b", "a", "b"])).tolist() == [2, 1, 2]
+    assert ecs._as_labels(["x", "y", "x"]).tolist() == [1, 2, 1]
+    with pytest.raises(ValueError, match="NA"):
+        ecs._as_labels([1.0, float("nan")])
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_a_device():
+    with pytest.raises(_capi.ClustAssessError, match="no CPU fallback"):
+        ecs.element_sim_elscore([1, 1, 2], [2, 2, 2])
+    with pytest.raises(_capi.ClustAssessError):
+        ecs.element_consistency([[1, 1, 2], [2, 2, 2]])
