@@ -18,7 +18,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-__all__ = ["louvain_like", "uniform_random", "config", "CONFIGS"]
+__all__ = ["louvain_like", "uniform_random", "config", "config_weights", "CONFIGS"]
 
 
 def _base(n, k0, seed):
@@ -138,9 +138,17 @@ def config(name, family="louvain", m=None, n=None, parts=None, threads=8):
         labels = uniform_random(c["m"], c["n"], c["k_lo"], c["k_hi"], c["seed"], parts=parts)
     else:
         raise ValueError("family must be 'louvain' or 'uniform'")
-    if name == "C3":
-        rng = np.random.Generator(np.random.PCG64([c["seed"], 1 << 21]))
-        weights = (1 + rng.poisson(1.0, size=c["m"])).astype(np.float64)
-        if parts is not None:
-            weights = weights[list(parts)]
+    weights = config_weights(name, c["m"])
+    if weights is not None and parts is not None:
+        weights = weights[list(parts)]
     return labels, weights
+
+
+def config_weights(name, m=None):
+    """Integer frequency weights 1 + Poisson(1) for C3 (mirrors `freq` of the unique partitions at one
+    resolution, R/stability-3-graph-clustering.R:339-341); None for the unweighted configurations."""
+    if name != "C3":
+        return None
+    c = CONFIGS[name]
+    rng = np.random.Generator(np.random.PCG64([c["seed"], 1 << 21]))
+    return (1 + rng.poisson(1.0, size=m or c["m"])).astype(np.float64)
