@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <numeric>
+#include <thread>
 
 #include "ca_internal.h"
 
@@ -156,6 +157,8 @@ int prepare_ranks(Labels& L) {
     CA_CUDA(cudaMemsetAsync(L.d_sizes.p, 0, (size_t)m * L.kp * 4, s));
     CA_TRY(launch_sizes(L.d_cnt.as<uint32_t>(), L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(), nullptr, nullptr, m,
                         (int32_t)max_range, L.kp, L.d_sizes.as<int32_t>(), s));
+    CA_TRY(L.d_invsizes.ensure((size_t)m * L.kp * 8));
+    CA_TRY(launch_invsizes(L.d_sizes.as<int32_t>(), (int64_t)m * L.kp, L.d_invsizes.as<double>(), s));
     L.h_sizes.assign((size_t)m * L.kp, 0);
     CA_CUDA(cudaMemcpyAsync(L.h_sizes.data(), L.d_sizes.p, (size_t)m * L.kp * 4, cudaMemcpyDeviceToHost, s));
     CA_CUDA(cudaStreamSynchronize(s));
@@ -234,35 +237,59 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     std::vector<int32_t> h_slot_of(m, -1);
     std::vector<int32_t> h_cstart((size_t)std::max(nparts, 1) * L.kp, 0);
     std::vector<uint16_t> h_crow((size_t)std::max(nparts, 1) * L.kp, 0);
-    std::vector<Item> items_narrow, items_wide;
+    std::vector<Item> items_k[3];  // 0 resident, 1 streaming (16-bit counters), 2 streaming (32-bit counters)
     int64_t perm_stride = 4;
-    PlanOut po;
-    for (int32_t sl = 0; sl < nparts; sl++) {
-        const int32_t p = parts[sl];
-        h_slot_of[p] = sl;
-        CA_TRY(plan_blocks(L.h_sizes.data() + (size_t)p * L.kp, L.h_k[p], RB_CPT, RB_CAP, max_rows, po));
-        perm_stride = std::max<int64_t>(perm_stride, (po.total_pos + 3) & ~3LL);
-        for (int32_t k = 0; k < L.h_k[p]; k++) {
-            h_cstart[(size_t)sl * L.kp + k] = po.cstart[k];
-            h_crow[(size_t)sl * L.kp + k] = (uint16_t)po.crow[k];
+    {   // plan every owned partition; partitions are independent, so the host threads share them
+        const int nthreads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, nparts}));
+        std::vector<std::vector<Item>> items_t[3];
+        for (auto& v : items_t) v.resize(nthreads);
+        std::vector<int64_t> stride_t(nthreads, 4);
+        std::vector<int> rc_t(nthreads, CA_OK);
+        for (int32_t sl = 0; sl < nparts; sl++) h_slot_of[parts[sl]] = sl;
+        auto work = [&](int tix) {
+            PlanOut po;
+            for (int32_t sl = tix; sl < nparts; sl += nthreads) {
+                const int32_t p = parts[sl];
+                int rc = plan_blocks(L.h_sizes.data() + (size_t)p * L.kp, L.h_k[p], RB_CPT, RB_CAP, max_rows, po);
+                if (rc != CA_OK) { rc_t[tix] = rc; return; }
+                stride_t[tix] = std::max<int64_t>(stride_t[tix], (po.total_pos + 3) & ~3LL);
+                for (int32_t k = 0; k < L.h_k[p]; k++) {
+                    h_cstart[(size_t)sl * L.kp + k] = po.cstart[k];
+                    h_crow[(size_t)sl * L.kp + k] = (uint16_t)po.crow[k];
+                }
+                for (size_t t = 0; t < po.pos0.size(); t++) {
+                    Item it;
+                    it.m = p;
+                    it.pos0 = po.pos0[t];
+                    it.npos = po.npos[t];
+                    it.nrows = po.nrows[t];
+                    it.jbeg = ref_only >= 0 ? 0 : p + 1;
+                    it.jend = ref_only >= 0 ? m_partners : m;
+                    it.sa = po.sa[t];
+                    it.pad_ = 0;
+                    items_t[it.npos <= RB_CAP ? 0 : (po.wide[t] ? 2 : 1)][tix].push_back(it);
+                }
+            }
+        };
+        if (nthreads == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
+            for (auto& t : th) t.join();
         }
-        for (size_t t = 0; t < po.pos0.size(); t++) {
-            Item it;
-            it.m = p;
-            it.pos0 = po.pos0[t];
-            it.npos = po.npos[t];
-            it.nrows = po.nrows[t];
-            it.jbeg = ref_only >= 0 ? 0 : p + 1;
-            it.jend = ref_only >= 0 ? m_partners : m;
-            it.sa = po.sa[t];
-            it.pad_ = 0;
-            (po.wide[t] ? items_wide : items_narrow).push_back(it);
+        for (int t = 0; t < nthreads; t++) {
+            if (rc_t[t] != CA_OK) {
+                set_error("row-block planning failed (code %d)", rc_t[t]);
+                return rc_t[t];
+            }
+            perm_stride = std::max(perm_stride, stride_t[t]);
+            for (int k = 0; k < 3; k++) items_k[k].insert(items_k[k].end(), items_t[k][t].begin(), items_t[k][t].end());
         }
     }
     auto cost = [](const Item& a) { return (int64_t)a.npos * (a.jend - a.jbeg); };
     auto by_cost = [&](const Item& a, const Item& b) { return cost(a) > cost(b); };
-    std::stable_sort(items_narrow.begin(), items_narrow.end(), by_cost);
-    std::stable_sort(items_wide.begin(), items_wide.end(), by_cost);
+    for (auto& v : items_k) std::stable_sort(v.begin(), v.end(), by_cost);
     std::vector<double> h_w(L.mpad + RB_JW, 0.0);
     double wsum = 0.0;
     const int32_t mw = ref_only >= 0 ? m_partners : m;
@@ -281,7 +308,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
 
     // ---- upload plan, sort ------------------------------------------------------------------------
     Workspace& W = ws();
-    const size_t nitems = items_narrow.size() + items_wide.size();
+    const size_t nitems = items_k[0].size() + items_k[1].size() + items_k[2].size();
     CA_TRY(W.perm.ensure((size_t)std::max(nparts, 1) * perm_stride * 4));
     CA_TRY(W.cstart.ensure(h_cstart.size() * 4));
     CA_TRY(W.crow.ensure(h_crow.size() * 2));
@@ -295,11 +322,13 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     CA_CUDA(cudaMemcpyAsync(W.slot_of.p, h_slot_of.data(), (size_t)m * 4, cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaMemcpyAsync(W.w.p, h_w.data(), h_w.size() * 8, cudaMemcpyHostToDevice, s));
     Item* d_items = W.items.as<Item>();
-    if (!items_narrow.empty())
-        CA_CUDA(cudaMemcpyAsync(d_items, items_narrow.data(), items_narrow.size() * sizeof(Item), cudaMemcpyHostToDevice, s));
-    if (!items_wide.empty())
-        CA_CUDA(cudaMemcpyAsync(d_items + items_narrow.size(), items_wide.data(), items_wide.size() * sizeof(Item),
-                                cudaMemcpyHostToDevice, s));
+    {
+        size_t off = 0;
+        for (auto& v : items_k) {
+            if (!v.empty()) CA_CUDA(cudaMemcpyAsync(d_items + off, v.data(), v.size() * sizeof(Item), cudaMemcpyHostToDevice, s));
+            off += v.size();
+        }
+    }
     CA_CUDA(cudaEventRecord(c.ev[3], s));
     CA_TRY(launch_sort(L.d_raw, n, L.d_min.as<int32_t>(), L.identity ? nullptr : L.d_rank.as<uint32_t>(),
                        L.d_roff.as<int64_t>(), W.cstart.as<int32_t>(), L.kp, W.parts.as<int32_t>(), nparts,
@@ -312,6 +341,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     P.perm = W.perm.as<int32_t>();
     P.slot_of = W.slot_of.as<int32_t>();
     P.sizes = L.d_sizes.as<int32_t>();
+    P.invsizes = L.d_invsizes.as<double>();
     P.crow = W.crow.as<uint16_t>();
     P.w = W.w.as<double>();
     P.items = d_items;
@@ -323,11 +353,13 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     P.kp = L.kp;
     P.smem_bytes = smem_bytes;
     P.inv_norm = inv_norm;
-    int launches = 0;
     if (d_ecc || d_sim) {
-        CA_TRY(launch_rowblock(P, (int32_t)items_narrow.size(), false, s, &launches));
-        P.items = d_items + items_narrow.size();
-        CA_TRY(launch_rowblock(P, (int32_t)items_wide.size(), true, s, &launches));
+        // the long streaming items first, then the resident blocks fill the machine behind them
+        const Item* base_k[3] = {d_items, d_items + items_k[0].size(), d_items + items_k[0].size() + items_k[1].size()};
+        for (int kind : {2, 1, 0}) {
+            P.items = base_k[kind];
+            CA_TRY(launch_rowblock(P, (int32_t)items_k[kind].size(), kind, s));
+        }
     }
     CA_CUDA(cudaEventRecord(c.ev[5], s));
     CA_CUDA(cudaStreamSynchronize(s));
@@ -341,7 +373,6 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     CA_CUDA(cudaEventElapsedTime(&ms, c.ev[4], c.ev[5]));
     c.prof[4] = ms;
     c.prof[7] = (double)c.launches;  // every kernel of this call (pack, transpose, sort, row-block)
-    (void)launches;
     c.prof[6] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     return CA_OK;
 }
@@ -483,7 +514,7 @@ int ca_labels_destroy(ca_labels_t* h) {
     Labels& L = h->L;
     if (L.d_raw) cudaFree(L.d_raw);
     L.d_min.release(); L.d_max.release(); L.d_cnt.release(); L.d_rank.release(); L.d_kcount.release();
-    L.d_roff.release(); L.d_sizes.release(); L.d_lab16.release();
+    L.d_roff.release(); L.d_sizes.release(); L.d_invsizes.release(); L.d_lab16.release();
     delete h;
     return CA_OK;
 }

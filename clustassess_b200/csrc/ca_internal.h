@@ -90,7 +90,7 @@ struct Labels {
     std::vector<int64_t> h_roff;  // offset of partition p's range in d_cnt / d_rank
     bool identity = true;         // every partition's labels are already dense (rank == label - min)
     int32_t kmax = 0, kp = 0, mpad = 0;
-    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_lab16;
+    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_invsizes, d_lab16;
     std::vector<int32_t> h_sizes;  // [m][kp]
 };
 
@@ -107,6 +107,7 @@ int launch_rank(const uint32_t* d_cnt, const int64_t* d_roff, const int32_t* d_m
                 uint32_t* d_rank, int32_t* d_kcount, cudaStream_t s);
 int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_min,
                  const int32_t* d_max, int32_t m, int32_t max_range, int32_t kp, int32_t* d_sizes, cudaStream_t s);
+int launch_invsizes(const int32_t* d_sizes, int64_t count, double* d_inv, cudaStream_t s);
 int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t mpad, const int32_t* d_min,
                              const uint32_t* d_rank, const int64_t* d_roff, uint16_t* d_lab16, cudaStream_t s);
 int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
@@ -119,6 +120,7 @@ struct RowBlockParams {
     const int32_t* perm;     // [m_slots][perm_stride] cluster-sorted cell ids, -1 = padding
     const int32_t* slot_of;  // [m] partition -> perm slot (or -1)
     const int32_t* sizes;    // [m][kp]
+    const double* invsizes;  // [m][kp] 1 / size (0 where the slot is unused)
     const uint16_t* crow;    // [m_slots][kp] row of a cluster inside its block
     const double* w;         // [m] weights
     const Item* items;
@@ -129,7 +131,8 @@ struct RowBlockParams {
     int32_t smem_bytes;      // dynamic shared memory available to sizes + tables
     double inv_norm;
 };
-int launch_rowblock(const RowBlockParams& p, int32_t nitems, bool wide, cudaStream_t s, int* launches);
+// kind: 0 = resident items, 1 = streaming items with 16-bit counters, 2 = streaming items with 32-bit counters
+int launch_rowblock(const RowBlockParams& p, int32_t nitems, int kind, cudaStream_t s);
 int rowblock_smem_budget(int32_t kp, int32_t* max_rows_out);
 
 // ca_pair.cu

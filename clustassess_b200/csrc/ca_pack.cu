@@ -12,6 +12,8 @@
 //               cluster at the padded start position chosen by the host planner (ca_plan.cpp)
 // All kernels are HBM-bound streaming passes over the M x N int32 input (coalesced loads), a few
 // percent of the row-block kernels' time.
+#include <algorithm>
+
 #include "ca_internal.h"
 
 namespace ca {
@@ -177,6 +179,21 @@ int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d
     return CA_OK;
 }
 
+__global__ void invsizes_kernel(const int32_t* __restrict__ sizes, int64_t count, double* __restrict__ inv) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        int32_t s = sizes[i];
+        inv[i] = s > 0 ? 1.0 / (double)s : 0.0;  // correctly rounded reciprocal, once per cluster
+    }
+}
+
+int launch_invsizes(const int32_t* d_sizes, int64_t count, double* d_inv, cudaStream_t s) {
+    if (count <= 0) return CA_OK;
+    invsizes_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_sizes, count, d_inv);
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // relabel + transpose: raw int32 [m][n] (partition-major)  ->  lab16 uint16 [n][mpad] (cell-major)
 // A block moves a 32-partition x 128-cell tile through shared memory: coalesced 4-byte reads along n,
@@ -239,51 +256,93 @@ int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t m
 }
 
 // ------------------------------------------------------------------------------------------------
-// stable counting sort of the cells of one partition by cluster: ONE WARP PER PARTITION.
-// The warp walks the cells in index order, 32 at a time; __match_any_sync groups equal labels inside
-// the 32, the group's first lane advances that cluster's cursor (shared memory) by the group size and
-// every lane writes its cell id at cursor + (its rank inside the group).  Cells of a cluster therefore
-// stay in ascending cell order, which keeps runs of equal partner labels together for the row-block
-// kernel's run compression.  500 partitions x 1M cells take ~1-2 ms: the chains are sequential per
-// partition but all partitions advance in parallel.
+// stable counting sort of the cells of every owned partition by cluster.
+// A partition's cells are cut into `nseg` contiguous segments; ONE WARP sorts one (partition, segment):
+//   seg_count_kernel : per (partition, segment) histogram of the labels
+//   seg_scan_kernel  : cursor[p][seg][k] = cstart[p][k] + #cells of cluster k in earlier segments
+//   sort_kernel      : the warp walks its segment in index order, 32 cells at a time; __match_any_sync groups
+//                      equal labels inside the 32, the group's first lane advances that cluster's cursor
+//                      (shared memory) by the group size and every lane writes its cell id at
+//                      cursor + (its rank inside the group).
+// Cells of a cluster therefore stay in ascending cell order (stable), which keeps runs of equal partner
+// labels together for the row-block kernel.  Each warp is a sequential chain, so the segment count is what
+// buys parallelism (thousands of chains in flight).
 // ------------------------------------------------------------------------------------------------
-template <bool SMEM_CURSOR>
-__global__ void __launch_bounds__(128) sort_kernel(const int32_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ d_min,
-                                                   const uint32_t* __restrict__ d_rank, const int64_t* __restrict__ d_roff,
-                                                   const int32_t* __restrict__ d_cstart, int32_t kp,
-                                                   const int32_t* __restrict__ d_parts, int32_t nparts,
-                                                   int32_t* __restrict__ d_perm, int64_t perm_stride,
-                                                   int32_t* __restrict__ d_cursor_scratch) {
-    extern __shared__ int32_t cur_sh[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int slot = blockIdx.x * (blockDim.x >> 5) + wid;
-    if (slot >= nparts) return;
+__device__ __forceinline__ uint32_t compact_of(const int32_t* x, int64_t i, int mn, const uint32_t* rk) {
+    uint32_t v = (uint32_t)(__ldg(x + i) - mn);
+    return rk ? __ldg(rk + v) : v;
+}
+
+__global__ void __launch_bounds__(256) seg_count_kernel(const int32_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ d_min,
+                                                        const uint32_t* __restrict__ d_rank, const int64_t* __restrict__ d_roff,
+                                                        int32_t kp, const int32_t* __restrict__ d_parts, int32_t nseg, int64_t seglen,
+                                                        int32_t* __restrict__ d_segcur) {
+    extern __shared__ int32_t cnt_sh[];
+    const int slot = blockIdx.y, seg = blockIdx.x;
     const int p = d_parts[slot];
     const int32_t* x = raw + (int64_t)p * n;
     const int mn = d_min[p];
     const uint32_t* rk = d_rank ? d_rank + d_roff[p] : nullptr;
-    const int32_t* cs = d_cstart + (int64_t)slot * kp;
-    int32_t* cur = SMEM_CURSOR ? cur_sh + (size_t)wid * kp : d_cursor_scratch + (int64_t)slot * kp;
-    for (int k = lane; k < kp; k += 32) cur[k] = cs[k];
-    __syncwarp();
+    int32_t* out = d_segcur + ((int64_t)slot * nseg + seg) * kp;
+    for (int k = threadIdx.x; k < kp; k += blockDim.x) cnt_sh[k] = 0;
+    __syncthreads();
+    const int64_t lo = (int64_t)seg * seglen, hi = min(n, lo + seglen);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(cnt_sh + compact_of(x, i, mn, rk), 1);
+    __syncthreads();
+    for (int k = threadIdx.x; k < kp; k += blockDim.x) out[k] = cnt_sh[k];
+}
+
+__global__ void seg_scan_kernel(const int32_t* __restrict__ d_cstart, int32_t kp, int32_t nparts, int32_t nseg,
+                                int32_t* __restrict__ d_segcur) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)nparts * kp) return;
+    const int slot = (int)(idx / kp), k = (int)(idx % kp);
+    int32_t run = d_cstart[idx];
+    for (int seg = 0; seg < nseg; seg++) {
+        int32_t* c = d_segcur + ((int64_t)slot * nseg + seg) * kp + k;
+        const int32_t t = *c;
+        *c = run;
+        run += t;
+    }
+}
+
+template <bool SMEM_CURSOR>
+__global__ void __launch_bounds__(128) sort_kernel(const int32_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ d_min,
+                                                   const uint32_t* __restrict__ d_rank, const int64_t* __restrict__ d_roff,
+                                                   int32_t kp, const int32_t* __restrict__ d_parts, int32_t nparts, int32_t nseg,
+                                                   int64_t seglen, int32_t* __restrict__ d_perm, int64_t perm_stride,
+                                                   int32_t* __restrict__ d_segcur) {
+    extern __shared__ int32_t cur_sh[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t job = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
+    if (job >= (int64_t)nparts * nseg) return;
+    const int slot = (int)(job / nseg), seg = (int)(job % nseg);
+    const int p = d_parts[slot];
+    const int32_t* x = raw + (int64_t)p * n;
+    const int mn = d_min[p];
+    const uint32_t* rk = d_rank ? d_rank + d_roff[p] : nullptr;
+    int32_t* gcur = d_segcur + ((int64_t)slot * nseg + seg) * kp;
+    int32_t* cur = SMEM_CURSOR ? cur_sh + (size_t)wid * kp : gcur;
+    if (SMEM_CURSOR) {
+        for (int k = lane; k < kp; k += 32) cur[k] = gcur[k];
+        __syncwarp();
+    }
     int32_t* out = d_perm + (int64_t)slot * perm_stride;
+    const int64_t lo = (int64_t)seg * seglen, hi = min(n, lo + seglen);
     constexpr int U = 4;
-    for (int64_t base = 0; base < n; base += 32 * U) {
+    for (int64_t base = lo; base < hi; base += 32 * U) {
         uint32_t lab[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             int64_t i = base + u * 32 + lane;
             lab[u] = 0xffffffffu - (uint32_t)lane;  // unique key for out-of-range lanes
-            if (i < n) {
-                uint32_t v = (uint32_t)(__ldg(x + i) - mn);
-                lab[u] = rk ? __ldg(rk + v) : v;
-            }
+            if (i < hi) lab[u] = compact_of(x, i, mn, rk);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             int64_t i = base + u * 32 + lane;
-            if (base + u * 32 >= n) break;
-            const bool valid = i < n;
+            if (base + u * 32 >= hi) break;
+            const bool valid = i < hi;
             unsigned grp = __match_any_sync(FULL, lab[u]);
             int leader = __ffs(grp) - 1;
             int r = __popc(grp & ((1u << lane) - 1));
@@ -305,20 +364,42 @@ int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint3
                 int64_t perm_stride, cudaStream_t s) {
     if (nparts == 0) return CA_OK;
     CA_CUDA(cudaMemsetAsync(d_perm, 0xff, (size_t)nparts * (size_t)perm_stride * sizeof(int32_t), s));
-    size_t per_warp = (size_t)kp * 4;
-    int wpb = 4;
-    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
-    if (per_warp * wpb <= 200 * 1024) {
-        size_t smem = per_warp * wpb;
+    static DevBuf segcur;
+    const size_t per_warp = (size_t)kp * 4;
+    const bool smem_ok = per_warp <= 200 * 1024;
+    // segments: enough chains to fill the machine, each at least 16k cells long; the shared-memory count
+    // kernel needs the label table in shared memory too, so very large cluster counts stay at one segment
+    int32_t nseg = 1;
+    if (smem_ok) {
+        int64_t want = (int64_t)ctx().sm_count * 24 / nparts + 1;
+        int64_t cap = n / 16384 + 1;
+        nseg = (int32_t)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, cap), 64));
+    }
+    const int64_t seglen = ((n + nseg - 1) / nseg + 127) & ~127LL;
+    CA_TRY(segcur.ensure((size_t)nparts * nseg * kp * 4));
+    if (nseg > 1) {
+        if (per_warp > 48 * 1024)
+            CA_CUDA(cudaFuncSetAttribute(seg_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_warp));
+        seg_count_kernel<<<dim3((unsigned)nseg, (unsigned)nparts), 256, per_warp, s>>>(raw, n, d_min, d_rank, d_roff, kp, d_parts, nseg,
+                                                                                      seglen, segcur.as<int32_t>());
+        const int64_t tot = (int64_t)nparts * kp;
+        seg_scan_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_cstart, kp, nparts, nseg, segcur.as<int32_t>());
+        ca::ctx().launches += 2;
+    } else {
+        CA_CUDA(cudaMemcpyAsync(segcur.p, d_cstart, (size_t)nparts * kp * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    const int64_t jobs = (int64_t)nparts * nseg;
+    if (smem_ok) {
+        int wpb = 4;
+        while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+        const size_t smem = per_warp * wpb;
         if (smem > 48 * 1024)
             CA_CUDA(cudaFuncSetAttribute(sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sort_kernel<true><<<(nparts + wpb - 1) / wpb, wpb * 32, smem, s>>>(raw, n, d_min, d_rank, d_roff, d_cstart, kp, d_parts,
-                                                                           nparts, d_perm, perm_stride, nullptr);
-    } else {
-        static DevBuf scratch;  // cursors in global memory for very large cluster counts
-        CA_TRY(scratch.ensure((size_t)nparts * kp * 4));
-        sort_kernel<false><<<(nparts + 3) / 4, 128, 0, s>>>(raw, n, d_min, d_rank, d_roff, d_cstart, kp, d_parts, nparts, d_perm,
-                                                            perm_stride, scratch.as<int32_t>());
+        sort_kernel<true><<<(unsigned)((jobs + wpb - 1) / wpb), wpb * 32, smem, s>>>(raw, n, d_min, d_rank, d_roff, kp, d_parts, nparts,
+                                                                                    nseg, seglen, d_perm, perm_stride, segcur.as<int32_t>());
+    } else {  // cursors stay in global memory for very large cluster counts
+        sort_kernel<false><<<(unsigned)((jobs + 3) / 4), 128, 0, s>>>(raw, n, d_min, d_rank, d_roff, kp, d_parts, nparts, nseg, seglen,
+                                                                      d_perm, perm_stride, segcur.as<int32_t>());
     }
     CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
     return CA_OK;

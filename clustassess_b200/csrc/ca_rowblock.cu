@@ -7,21 +7,29 @@
 // Design (B200-first, not a port).  For a partition i the cells are stably sorted by their cluster in i
 // (perm_i, ca_pack.cu) so a thread block owns a contiguous run of cells that covers COMPLETE clusters
 // of i -- i.e. complete ROWS of every contingency table T_ij.  The rows of one block are small enough
-// (<= ~100 KB as 16-bit counters) to live in shared memory, so for each partner partition j the block
+// (16-bit counters) to live in shared memory, so for each partner partition j the block
 //   (1) zeroes its rows and stages S_j (cluster sizes of j) in shared memory,
-//   (2) histograms the partner labels of its cells into its rows (shared-memory atomics,
-//       thread-local run compression + warp aggregation, so correlated labelings cost ~1 atomic/warp),
-//   (3) gathers T[a][b] / max(S_i[a], S_j[b]) per cell -- one IEEE fp64 division, as
-//       calculate_ecs.cpp:35 -- and accumulates w_j * ECS into a per-cell register,
+//   (2) histograms the partner labels of its cells into its rows: a thread owns 4 consecutive cells,
+//       counts how many share the label of its first cell, threads with the same leading key are
+//       aggregated across the warp (ballot / shfl / redux, two rounds), so a run of equal labels costs
+//       ONE shared atomic per warp; only the cells that differ ("exceptions") add individually,
+//   (3) gathers ECS = T[a][b] / max(S_i[a], S_j[b])  (calculate_ecs.cpp:35) once per thread for the
+//       leading key; the exceptions of the whole warp are compacted into a dense list (ballot + popc) and
+//       evaluated one per lane; everything is accumulated in per-cell registers,
 // and only after ALL partners writes (w_i/norm) * acc to ecc with one fp64 atomic per cell.
-// Labels are read from a cell-major uint16 matrix lab16[n][mpad]: one 16-byte load per cell fetches the
-// labels of 8 partner partitions, so HBM traffic is ~2 B per (pair, cell) instead of the 16 B of a
+// Labels come from a cell-major uint16 matrix lab16[n][mpad]: one 16-byte load per cell fetches the labels
+// of 8 partner partitions (kept in a per-thread shared-memory scratch tile so that the partner loop is a
+// rolled loop with running addresses), so HBM traffic is ~2 B per (pair, cell) instead of the 16 B of a
 // pair-at-a-time stream, and no table ever leaves the SM.
 //
 // Work item = (partition i, a set of complete clusters of i).  "Resident" items (<= RB_CAP positions)
-// keep cell ids, labels and accumulators in registers; clusters larger than RB_CAP are "streaming"
-// items (one table row, cells re-read per phase, ecc accumulated per tile).  Up to JT partners are
+// keep their accumulators in registers for the whole job; clusters larger than RB_CAP are "streaming"
+// items (one table row, cells processed in sub-chunks, ecc accumulated per phase).  Up to JT partners are
 // processed per phase (JT tables side by side in shared memory) to amortise the block barriers.
+//
+// The division T / max(Sa, Sb) is evaluated as T * r with r = 1/max from rcp.approx.f64 refined by two
+// Newton steps (relative error ~1e-16): the batched path only has to meet 1e-9 absolute; the per-pair entry
+// points (ca_pair.cu) keep the single IEEE division and are bit-identical to the reference.
 #include "ca_internal.h"
 
 namespace ca {
@@ -29,81 +37,153 @@ namespace ca {
 static constexpr unsigned FULL = 0xffffffffu;
 static constexpr int CPT = RB_CPT;
 static constexpr int THREADS = RB_THREADS;
-static constexpr int SMEM_HDR = 128;  // bytes reserved in front of sizes/tables (sim accumulators)
+static constexpr int NWARPS = THREADS / 32;
+static_assert(CPT == 4, "the packed-label code below is written for 4 cells per thread");
 
+// shared-memory map (byte offsets from the dynamic shared base)
+static constexpr int STAGE_REC = 64;                          // exception records per warp and pass
+static constexpr int SM_SIMACC = 0;                           // RB_JW doubles
+static constexpr int SM_STAGE = 128;                          // per warp STAGE_REC x 8 B records / results
+static constexpr int SM_LAB = SM_STAGE + NWARPS * STAGE_REC * 8;   // [RB_JW][THREADS] x 8 B: 4 packed labels per thread
+static constexpr int SM_DYN = SM_LAB + RB_JW * THREADS * 8;   // [JT][kp] uint32 sizes of the partners, then [JT][nrows*kp] counters
+
+// ---- 32-bit shared-space accessors ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void lds_v2(uint32_t a, uint32_t& x, uint32_t& y) {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void red_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_add_f64(uint32_t a, double v) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+// counter of table entry `key` (table base tb, bytes): two 16-bit counters per word unless WIDE
 template <bool WIDE>
-__device__ __forceinline__ void tbl_add(uint32_t* T, int key, int v) {
+__device__ __forceinline__ void tbl_add(uint32_t tb, uint32_t key, uint32_t v) {
     if (WIDE)
-        atomicAdd(T + key, (uint32_t)v);
-    else  // two 16-bit counters per word; a block never counts past 65535 (planner guarantees it)
-        atomicAdd(T + (key >> 1), (uint32_t)v << ((key & 1) << 4));
+        red_add(tb + key * 4u, v);
+    else  // a block never counts past 65535 (the planner guarantees it), so halves cannot carry
+        red_add(tb + ((key * 2u) & ~3u), v << ((key & 1u) << 4));
 }
 template <bool WIDE>
-__device__ __forceinline__ uint32_t tbl_get(const uint32_t* T, int key) {
-    if (WIDE) return T[key];
-    return (uint32_t) reinterpret_cast<const uint16_t*>(T)[key];
+__device__ __forceinline__ uint32_t tbl_get(uint32_t tb, uint32_t key) {
+    return WIDE ? lds_u32(tb + key * 4u) : lds_u16(tb + key * 2u);
 }
 
-__device__ __forceinline__ int lab_of(const uint4& v, int jj) {
-    const uint32_t w = (jj >> 1) == 0 ? v.x : (jj >> 1) == 1 ? v.y : (jj >> 1) == 2 ? v.z : v.w;
-    return (jj & 1) ? (int)(w >> 16) : (int)(w & 0xffffu);
+// T / max(sa, sb): reciprocal seed + two Newton steps, then one multiply
+__device__ __forceinline__ double ecs_of(uint32_t count, uint32_t sa, uint32_t sb) {
+    const double mx = (double)max(sa, sb);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
+    r = fma(fma(-mx, r, 1.0), r, r);
+    r = fma(fma(-mx, r, 1.0), r, r);
+    return (double)count * r;
 }
 
-// (2) histogram of one partner partition for this thread's CPT cells.  key = row*kp + b, -1 = padding.
+struct Acc {           // per-thread accumulators: acc(cell c) = base + corr[c]
+    double base;       // sum_j w_j * ECS of the thread's leading key
+    double corr[CPT];  // corrections for the partners where cell c differed from the leading key
+};
+
+// (2) histogram of one partner for this thread's 4 cells (p01, p23 = packed labels; padding cells mirror cell 0).
+// Measured on B200 (tools/microbench.cu): a shared ATOMS instruction costs ~11 SM-cycles whether 1 or 32 lanes
+// are active and whether or not they hit the same word.  So the cheapest histogram issues as FEW atomic
+// instructions as possible, each as full as possible: one per-thread add of (leading key, #cells that share it)
+// -- 32 lanes, mostly the same address, which is free -- plus the warp's exceptions compacted into dense
+// 32-lane batches through a small per-warp staging buffer.
 template <bool WIDE>
-__device__ __forceinline__ void hist_step(uint32_t* T, const int (&key)[CPT], int lane) {
-    const int k0 = key[0];
-    int cnt0 = 0;
-#pragma unroll
-    for (int c = 0; c < CPT; c++) cnt0 += (key[c] == k0) ? 1 : 0;
-    bool pending = k0 >= 0;
-    // warp aggregation of the threads' leading keys: up to two rounds of "first pending lane broadcasts
-    // its key, matching lanes hand it their counts" (covers a warp that straddles two clusters / runs)
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        const unsigned pm = __ballot_sync(FULL, pending);
-        if (pm == 0) break;
-        const int leader = __ffs(pm) - 1;
-        const int kl = __shfl_sync(FULL, k0, leader);
-        const bool mt = pending && (k0 == kl);
-        const int tot = __reduce_add_sync(FULL, mt ? cnt0 : 0);
-        if (lane == leader) tbl_add<WIDE>(T, kl, tot);
-        pending = pending && !mt;
+__device__ __forceinline__ void hist_step(uint32_t tb, uint32_t stage, uint32_t p01, uint32_t p23, uint32_t rowbase, int nvalid,
+                                          int lane) {
+    const uint32_t kk = __byte_perm(p01, 0, 0x1010);  // leading label in both halves
+    const uint32_t d01 = p01 ^ kk, d23 = p23 ^ kk;    // non-zero halves = cells that differ from it
+    const bool x1 = (d01 >> 16) != 0, x2 = (d23 & 0xffffu) != 0, x3 = (d23 >> 16) != 0;
+    const int cnt0 = nvalid - (int)x1 - (int)x2 - (int)x3;
+    if (cnt0 > 0) tbl_add<WIDE>(tb, rowbase + (p01 & 0xffffu), (uint32_t)cnt0);
+    const unsigned m1 = __ballot_sync(FULL, x1), m2 = __ballot_sync(FULL, x2), m3 = __ballot_sync(FULL, x3);
+    if ((m1 | m2 | m3) != 0) {
+        const unsigned lt = (1u << lane) - 1u;
+        const int n1 = __popc(m1), n2 = __popc(m2);
+        const int i1 = __popc(m1 & lt), i2 = n1 + __popc(m2 & lt), i3 = n1 + n2 + __popc(m3 & lt);
+        const int ne = n1 + n2 + __popc(m3);  // <= 96 = 2 * STAGE_REC * (8 / 4) records of 4 bytes
+        if (x1) sts_u32(stage + i1 * 4u, rowbase + (p01 >> 16));
+        if (x2) sts_u32(stage + i2 * 4u, rowbase + (p23 & 0xffffu));
+        if (x3) sts_u32(stage + i3 * 4u, rowbase + (p23 >> 16));
+        __syncwarp();
+        for (int h = lane; h < ne; h += 32) tbl_add<WIDE>(tb, lds_u32(stage + h * 4u), 1u);
+        __syncwarp();
     }
-    if (pending) tbl_add<WIDE>(T, k0, cnt0);
-#pragma unroll
-    for (int c = 1; c < CPT; c++)
-        if (key[c] >= 0 && key[c] != k0) tbl_add<WIDE>(T, key[c], 1);
 }
 
-// (3) per-element ECS of one partner partition: e = T[a][b] / max(S_i[a], S_j[b])  (calculate_ecs.cpp:35,39-43)
-template <bool WIDE>
-__device__ __forceinline__ double gather_step(const uint32_t* T, const uint32_t* szj, const int (&key)[CPT], int rowbase,
-                                              uint32_t sa, double wj, double (&acc)[CPT]) {
-    const int k0 = key[0];
-    double e0 = 0.0, es = 0.0;
-    if (k0 >= 0) {
-        const uint32_t t = tbl_get<WIDE>(T, k0);
-        const uint32_t mx = max(sa, szj[k0 - rowbase]);
-        e0 = (double)t / (double)mx;
+// (3) per-element ECS of one partner.  Returns this lane's share of sum_cells ECS (for the ECS matrix).
+template <bool WIDE, bool WANT_SIM>
+__device__ __forceinline__ double gather_step(uint32_t tb, uint32_t szb, uint32_t stage, uint32_t p01, uint32_t p23,
+                                              uint32_t rowbase, uint32_t sa, int nvalid, double wj, int lane, Acc& acc) {
+    const uint32_t kk = __byte_perm(p01, 0, 0x1010);
+    const uint32_t d01 = p01 ^ kk, d23 = p23 ^ kk;
+    const bool x1 = (d01 >> 16) != 0, x2 = (d23 & 0xffffu) != 0, x3 = (d23 >> 16) != 0;
+    const uint32_t b0 = p01 & 0xffffu;
+    double we0 = 0.0, es = 0.0;
+    if (nvalid > 0) {
+        const double e0 = ecs_of(tbl_get<WIDE>(tb, rowbase + b0), sa, lds_u32(szb + b0 * 4u));
+        we0 = e0 * wj;
+        acc.base += we0;
+        if (WANT_SIM) es = e0 * (double)(nvalid - (int)x1 - (int)x2 - (int)x3);
     }
-#pragma unroll
-    for (int c = 0; c < CPT; c++) {
-        if (key[c] >= 0) {
-            double e = e0;
-            if (key[c] != k0) {
-                const uint32_t t = tbl_get<WIDE>(T, key[c]);
-                const uint32_t mx = max(sa, szj[key[c] - rowbase]);
-                e = (double)t / (double)mx;
+    const unsigned m1 = __ballot_sync(FULL, x1), m2 = __ballot_sync(FULL, x2), m3 = __ballot_sync(FULL, x3);
+    if ((m1 | m2 | m3) != 0) {
+        // compact the warp's exceptions into a dense list: one lane evaluates one exception
+        const unsigned lt = (1u << lane) - 1u;
+        const int n1 = __popc(m1), n2 = __popc(m2);
+        const int i1 = __popc(m1 & lt), i2 = n1 + __popc(m2 & lt), i3 = n1 + n2 + __popc(m3 & lt);
+        const int ne = n1 + n2 + __popc(m3);
+        for (int q0 = 0; q0 < ne; q0 += STAGE_REC) {  // one pass unless a warp has > STAGE_REC exceptions
+            const bool o1 = x1 && (unsigned)(i1 - q0) < (unsigned)STAGE_REC;
+            const bool o2 = x2 && (unsigned)(i2 - q0) < (unsigned)STAGE_REC;
+            const bool o3 = x3 && (unsigned)(i3 - q0) < (unsigned)STAGE_REC;
+            // record = { key | label << 16 , S_i[row] }; key < 65536 because the table lives in shared memory
+            if (o1) sts_v2(stage + (i1 - q0) * 8u, (rowbase + (p01 >> 16)) | (p01 & 0xffff0000u), sa);
+            if (o2) sts_v2(stage + (i2 - q0) * 8u, (rowbase + (p23 & 0xffffu)) | (p23 << 16), sa);
+            if (o3) sts_v2(stage + (i3 - q0) * 8u, (rowbase + (p23 >> 16)) | (p23 & 0xffff0000u), sa);
+            __syncwarp();
+            const int nq = min(ne - q0, STAGE_REC);
+            for (int h = lane; h < nq; h += 32) {
+                uint32_t rec, rsa;
+                lds_v2(stage + h * 8u, rec, rsa);
+                const double e = ecs_of(tbl_get<WIDE>(tb, rec & 0xffffu), rsa, lds_u32(szb + (rec >> 16) * 4u));
+                if (WANT_SIM) es += e;
+                sts_f64(stage + h * 8u, e * wj);
             }
-            acc[c] = fma(wj, e, acc[c]);
-            es += e;
+            __syncwarp();
+            if (o1) acc.corr[1] += lds_f64(stage + (i1 - q0) * 8u) - we0;
+            if (o2) acc.corr[2] += lds_f64(stage + (i2 - q0) * 8u) - we0;
+            if (o3) acc.corr[3] += lds_f64(stage + (i3 - q0) * 8u) - we0;
+            __syncwarp();
         }
     }
     return es;
 }
 
-template <bool WIDE, bool WANT_ECC, bool WANT_SIM>
+template <bool WIDE, bool RESIDENT, bool WANT_ECC, bool WANT_SIM>
 __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Item it = P.items[blockIdx.x];
@@ -114,176 +194,196 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
     const int kp = P.kp, nrows = it.nrows;
     constexpr int CW = WIDE ? 4 : 2;
     const int per_j = kp * (4 + CW * nrows);
-    int JT = (P.smem_bytes - SMEM_HDR) / per_j;
+    int JT = (P.smem_bytes - SM_DYN) / per_j;
     JT = JT > RB_JW ? RB_JW : JT;
-    double* simacc = reinterpret_cast<double*>(smem);                              // [RB_JW]
-    uint32_t* sz = reinterpret_cast<uint32_t*>(smem + SMEM_HDR);                   // [JT][kp]
-    uint32_t* tbl = reinterpret_cast<uint32_t*>(smem + SMEM_HDR + (size_t)JT * kp * 4);  // [JT][nrows*kp] counters
-    const int tbl_words_j = nrows * kp * CW / 4;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t s_stage = sbase + SM_STAGE + (tid >> 5) * (STAGE_REC * 8);
+    const uint32_t s_lab = sbase + SM_LAB + tid * 8u;             // + jj * THREADS * 8
+    const uint32_t s_sz = sbase + SM_DYN;                         // [JT][kp] uint32
+    const uint32_t s_tbl = s_sz + (uint32_t)JT * kp * 4u;         // [JT][nrows*kp] counters
+    const uint32_t tbl_bytes_j = (uint32_t)nrows * kp * CW;
     constexpr int CHUNK = THREADS * CPT;
-    const int nsub = (it.npos + CHUNK - 1) / CHUNK;
-    const bool resident = nsub == 1;
+    const int nsub = RESIDENT ? 1 : (it.npos + CHUNK - 1) / CHUNK;
     const int slot = P.slot_of[m];
     const int32_t* perm = P.perm + (int64_t)slot * P.perm_stride + it.pos0;
     const int mpad = P.mpad;
     const double wscale = P.w[m] * P.inv_norm;
 
-    int cell[CPT];
-    uint4 lab[CPT];
-    double acc[CPT];
-    int rowbase = 0;
-    uint32_t sa = (uint32_t)it.sa;
+    int4 cell = make_int4(-1, -1, -1, -1);
+    int nvalid = 0;
+    uint32_t rowbase = 0, sa = (uint32_t)it.sa;
+    Acc acc;
+    acc.base = 0.0;
 #pragma unroll
-    for (int c = 0; c < CPT; c++) {
-        cell[c] = -1;
-        acc[c] = 0.0;
-        lab[c] = make_uint4(0, 0, 0, 0);
-    }
+    for (int c = 0; c < CPT; c++) acc.corr[c] = 0.0;
 
     auto load_cells = [&](int s) {
         const int p = s * CHUNK + tid * CPT;
-        if (p < it.npos) {
-            const int4 v = __ldg(reinterpret_cast<const int4*>(perm + p));
-            cell[0] = v.x; cell[1] = v.y; cell[2] = v.z; cell[3] = v.w;
-        } else {
-            cell[0] = cell[1] = cell[2] = cell[3] = -1;
+        cell = make_int4(-1, -1, -1, -1);
+        if (p < it.npos) cell = __ldg(reinterpret_cast<const int4*>(perm + p));
+        nvalid = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);
+    };
+    // Fetch this thread's 4 x 8 labels of the tile [j0, j0+8) and park them, partner-major, in its private
+    // slice of the shared scratch tile: s_lab + jj*THREADS*8 holds {cell0|cell1<<16, cell2|cell3<<16}.
+    // Padding cells mirror cell 0 (never an exception); idle threads store zeros.  No barrier is needed:
+    // a thread only ever reads back what it wrote itself.
+    auto load_labels = [&](int j0) {
+        uint4 l0 = make_uint4(0, 0, 0, 0), l1, l2, l3;
+        if (cell.x >= 0) l0 = __ldg(reinterpret_cast<const uint4*>(P.lab16 + (int64_t)cell.x * mpad + j0));
+        l1 = l2 = l3 = l0;
+        if (cell.y >= 0) l1 = __ldg(reinterpret_cast<const uint4*>(P.lab16 + (int64_t)cell.y * mpad + j0));
+        if (cell.z >= 0) l2 = __ldg(reinterpret_cast<const uint4*>(P.lab16 + (int64_t)cell.z * mpad + j0));
+        if (cell.w >= 0) l3 = __ldg(reinterpret_cast<const uint4*>(P.lab16 + (int64_t)cell.w * mpad + j0));
+        const uint32_t w0[4] = {l0.x, l0.y, l0.z, l0.w}, w1[4] = {l1.x, l1.y, l1.z, l1.w};
+        const uint32_t w2[4] = {l2.x, l2.y, l2.z, l2.w}, w3[4] = {l3.x, l3.y, l3.z, l3.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            sts_v2(s_lab + (2 * q) * (THREADS * 8), __byte_perm(w0[q], w1[q], 0x5410), __byte_perm(w2[q], w3[q], 0x5410));
+            sts_v2(s_lab + (2 * q + 1) * (THREADS * 8), __byte_perm(w0[q], w1[q], 0x7632), __byte_perm(w2[q], w3[q], 0x7632));
         }
     };
-    auto load_labels = [&](int j0) {
-#pragma unroll
-        for (int c = 0; c < CPT; c++)
-            if (cell[c] >= 0) lab[c] = __ldg(reinterpret_cast<const uint4*>(P.lab16 + (int64_t)cell[c] * mpad + j0));
+    auto prefetch_labels = [&](int j0) {
+        if (cell.x >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lab16 + (int64_t)cell.x * mpad + j0));
+        if (cell.y >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lab16 + (int64_t)cell.y * mpad + j0));
+        if (cell.z >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lab16 + (int64_t)cell.z * mpad + j0));
+        if (cell.w >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lab16 + (int64_t)cell.w * mpad + j0));
+    };
+    auto flush = [&]() {
+        if (cell.x >= 0) atomicAdd(P.ecc + cell.x, acc.base * wscale);
+        if (cell.y >= 0) atomicAdd(P.ecc + cell.y, (acc.base + acc.corr[1]) * wscale);
+        if (cell.z >= 0) atomicAdd(P.ecc + cell.z, (acc.base + acc.corr[2]) * wscale);
+        if (cell.w >= 0) atomicAdd(P.ecc + cell.w, (acc.base + acc.corr[3]) * wscale);
     };
 
-    if (resident) {
+    if (RESIDENT) {
         load_cells(0);
-        if (nrows > 1 && cell[0] >= 0) {
-            const int a = (int)__ldg(P.lab16 + (int64_t)cell[0] * mpad + m);
-            rowbase = (int)__ldg(P.crow + (int64_t)slot * kp + a) * kp;
+        if (nrows > 1 && cell.x >= 0) {
+            const int a = (int)__ldg(P.lab16 + (int64_t)cell.x * mpad + m);
+            rowbase = (uint32_t)__ldg(P.crow + (int64_t)slot * kp + a) * (uint32_t)kp;
             sa = (uint32_t)__ldg(P.sizes + (int64_t)m * kp + a);
         }
     }
 
-    for (int j0 = jbeg & ~(RB_JW - 1); j0 < jend; j0 += RB_JW) {
-        if (resident) load_labels(j0);
-        for (int g0 = 0; g0 < RB_JW; g0 += JT) {
-            const int glo = max(g0, jbeg - j0), ghi = min(min(g0 + JT, RB_JW), jend - j0);
-            if (glo >= ghi) continue;
+    const int jfirst = jbeg & ~(RB_JW - 1);
+    for (int j0 = jfirst; j0 < jend; j0 += RB_JW) {
+        if (RESIDENT) {
+            load_labels(j0);
+            if (j0 + RB_JW < jend) prefetch_labels(j0 + RB_JW);
+        }
+        const int tlo = max(0, jbeg - j0), thi = min(RB_JW, jend - j0);  // partners [tlo, thi) of this tile are wanted
+        for (int g0 = tlo; g0 < thi; g0 += JT) {
+            const int ng = min(JT, thi - g0);  // partners of this phase: j0+g0 .. j0+g0+ng-1
             __syncthreads();  // every thread is done gathering from the previous phase's tables
             {   // (1) zero this phase's tables, stage the partners' cluster sizes
-                uint4* t4 = reinterpret_cast<uint4*>(tbl);
-                const int nq = (ghi - g0) * tbl_words_j / 4;
-                for (int i = tid; i < nq; i += THREADS) t4[i] = make_uint4(0, 0, 0, 0);
-                const int kq = kp / 4;
-                for (int jl = glo - g0; jl < ghi - g0; jl++) {
+                const uint32_t nz = (uint32_t)ng * tbl_bytes_j;
+                for (uint32_t o = (uint32_t)tid * 16u; o < nz; o += THREADS * 16u) sts_v4(s_tbl + o, 0u, 0u, 0u, 0u);
+                const int kq = kp / 4;  // 16-byte chunks of a row of kp uint32
+                for (int jl = 0; jl < ng; jl++) {
                     const uint4* src = reinterpret_cast<const uint4*>(P.sizes + (int64_t)(j0 + g0 + jl) * kp);
-                    uint4* dst = reinterpret_cast<uint4*>(sz + (size_t)jl * kp);
-                    for (int i = tid; i < kq; i += THREADS) dst[i] = __ldg(src + i);
+                    for (int i = tid; i < kq; i += THREADS) {
+                        const uint4 v = __ldg(src + i);
+                        sts_v4(s_sz + (uint32_t)(jl * kp + i * 4) * 4u, v.x, v.y, v.z, v.w);
+                    }
                 }
-                if (WANT_SIM && tid < RB_JW) simacc[tid] = 0.0;
+                if (WANT_SIM && tid < RB_JW) sts_f64(sbase + SM_SIMACC + tid * 8u, 0.0);
             }
             __syncthreads();
             // (2) histogram
             for (int s = 0; s < nsub; s++) {
-                if (!resident) {
+                if (!RESIDENT) {
                     load_cells(s);
                     load_labels(j0);
                 }
-#pragma unroll
-                for (int jj = 0; jj < RB_JW; jj++) {
-                    if (jj >= glo && jj < ghi) {
-                        int key[CPT];
-#pragma unroll
-                        for (int c = 0; c < CPT; c++) key[c] = cell[c] >= 0 ? rowbase + lab_of(lab[c], jj) : -1;
-                        hist_step<WIDE>(tbl + (size_t)(jj - g0) * tbl_words_j, key, lane);
-                    }
+                uint32_t tb = s_tbl, la = s_lab + (uint32_t)g0 * (THREADS * 8);
+                for (int jl = 0; jl < ng; jl++, tb += tbl_bytes_j, la += THREADS * 8) {
+                    uint32_t p01, p23;
+                    lds_v2(la, p01, p23);
+                    hist_step<WIDE>(tb, s_stage, p01, p23, rowbase, nvalid, lane);
                 }
             }
             __syncthreads();
             // (3) gather + accumulate
             for (int s = 0; s < nsub; s++) {
-                if (!resident) {
+                if (!RESIDENT) {
                     load_cells(s);
                     load_labels(j0);
+                    acc.base = 0.0;
 #pragma unroll
-                    for (int c = 0; c < CPT; c++) acc[c] = 0.0;
+                    for (int c = 0; c < CPT; c++) acc.corr[c] = 0.0;
                 }
+                uint32_t tb = s_tbl, szb = s_sz, la = s_lab + (uint32_t)g0 * (THREADS * 8);
+                for (int jl = 0; jl < ng; jl++, tb += tbl_bytes_j, szb += (uint32_t)kp * 4u, la += THREADS * 8) {
+                    uint32_t p01, p23;
+                    lds_v2(la, p01, p23);
+                    const double wj = __ldg(P.w + j0 + g0 + jl);
+                    double es = gather_step<WIDE, WANT_SIM>(tb, szb, s_stage, p01, p23, rowbase, sa, nvalid, wj, lane, acc);
+                    if (WANT_SIM) {
 #pragma unroll
-                for (int jj = 0; jj < RB_JW; jj++) {
-                    if (jj >= glo && jj < ghi) {
-                        int key[CPT];
-#pragma unroll
-                        for (int c = 0; c < CPT; c++) key[c] = cell[c] >= 0 ? rowbase + lab_of(lab[c], jj) : -1;
-                        const double wj = __ldg(P.w + j0 + jj);
-                        double es = gather_step<WIDE>(tbl + (size_t)(jj - g0) * tbl_words_j, sz + (size_t)(jj - g0) * kp, key,
-                                                      rowbase, sa, wj, acc);
-                        if (WANT_SIM) {
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
-                            if (lane == 0 && es != 0.0) atomicAdd(simacc + jj, es);
-                        }
+                        for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
+                        if (lane == 0 && es != 0.0) red_add_f64(sbase + SM_SIMACC + jl * 8u, es);
                     }
                 }
-                if (!resident && WANT_ECC) {
-#pragma unroll
-                    for (int c = 0; c < CPT; c++)
-                        if (cell[c] >= 0) atomicAdd(P.ecc + cell[c], acc[c] * wscale);
-                }
+                if (!RESIDENT && WANT_ECC) flush();
             }
             if (WANT_SIM) {
                 __syncthreads();
-                if (tid >= glo && tid < ghi && simacc[tid] != 0.0)
-                    atomicAdd(P.sim + (int64_t)m * P.m + (j0 + tid), simacc[tid]);
+                if (tid < ng) {
+                    const double v = lds_f64(sbase + SM_SIMACC + tid * 8u);
+                    if (v != 0.0) atomicAdd(P.sim + (int64_t)m * P.m + (j0 + g0 + tid), v);
+                }
             }
         }
     }
-    if (resident && WANT_ECC) {
-#pragma unroll
-        for (int c = 0; c < CPT; c++)
-            if (cell[c] >= 0) atomicAdd(P.ecc + cell[c], acc[c] * wscale);
-    }
+    if (RESIDENT && WANT_ECC) flush();
 }
 
-// Shared memory available to one block for sizes + tables, and the number of table rows a resident
-// block may own so that at least one partner fits (JT >= 1).  Two blocks per SM when the tables allow.
+// Shared memory available to one block, and the number of table rows a resident block may own so that
+// at least one partner fits (JT >= 1).  Two blocks per SM when the tables allow it.
 int rowblock_smem_budget(int32_t kp, int32_t* max_rows_out) {
     Ctx& c = ctx();
     size_t optin = c.smem_optin ? c.smem_optin : 227 * 1024;
     int budget = (int)((optin + 1024) / 2 - 1024 - 512);  // two resident blocks per SM
-    int rows = ((budget - SMEM_HDR) / kp - 4) / 2;
+    int rows = ((budget - SM_DYN) / kp - 4) / 2;
     if (rows < 4) {  // large cluster counts: one block per SM
         budget = (int)optin - 512;
-        rows = ((budget - SMEM_HDR) / kp - 4) / 2;
+        rows = ((budget - SM_DYN) / kp - 4) / 2;
     }
     if (rows > RB_MAX_ROWS) rows = RB_MAX_ROWS;
+    if (rows > 65536 / kp) rows = 65536 / kp > 0 ? 65536 / kp : 1;  // exception records carry 16-bit table keys
     // do not reserve more shared memory than 8 partners x max_rows rows can use
-    long long need = SMEM_HDR + (long long)RB_JW * kp * (4 + 4 * (long long)rows);
+    long long need = SM_DYN + (long long)RB_JW * kp * (4 + 4 * (long long)(rows > 0 ? rows : 1));
     if (need < budget) budget = (int)((need + 15) & ~15LL);
     if (max_rows_out) *max_rows_out = rows;
     return budget;
 }
 
-template <bool WIDE, bool E, bool S>
+template <bool WIDE, bool R, bool E, bool S>
 static int launch_one(const RowBlockParams& p, int32_t nitems, cudaStream_t s) {
-    auto kern = rowblock_kernel<WIDE, E, S>;
+    auto kern = rowblock_kernel<WIDE, R, E, S>;
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
     kern<<<(unsigned)nitems, THREADS, (size_t)p.smem_bytes, s>>>(p);
-    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    CA_CUDA(cudaGetLastError());
+    ca::ctx().launches++;
     return CA_OK;
 }
 
-int launch_rowblock(const RowBlockParams& p, int32_t nitems, bool wide, cudaStream_t s, int* launches) {
+// kind: 0 = resident items (16-bit counters), 1 = streaming items (16-bit), 2 = streaming items (32-bit)
+int launch_rowblock(const RowBlockParams& p, int32_t nitems, int kind, cudaStream_t s) {
     if (nitems <= 0) return CA_OK;
     const bool e = p.ecc != nullptr, sm = p.sim != nullptr;
-    if (launches) (*launches)++;
-    if (wide) {
-        if (e && sm) return launch_one<true, true, true>(p, nitems, s);
-        if (e) return launch_one<true, true, false>(p, nitems, s);
-        return launch_one<true, false, true>(p, nitems, s);
+    if (kind == 0) {
+        if (e && sm) return launch_one<false, true, true, true>(p, nitems, s);
+        if (e) return launch_one<false, true, true, false>(p, nitems, s);
+        return launch_one<false, true, false, true>(p, nitems, s);
     }
-    if (e && sm) return launch_one<false, true, true>(p, nitems, s);
-    if (e) return launch_one<false, true, false>(p, nitems, s);
-    return launch_one<false, false, true>(p, nitems, s);
+    if (kind == 1) {
+        if (e && sm) return launch_one<false, false, true, true>(p, nitems, s);
+        if (e) return launch_one<false, false, true, false>(p, nitems, s);
+        return launch_one<false, false, false, true>(p, nitems, s);
+    }
+    if (e && sm) return launch_one<true, false, true, true>(p, nitems, s);
+    if (e) return launch_one<true, false, true, false>(p, nitems, s);
+    return launch_one<true, false, false, true>(p, nitems, s);
 }
 
 }  // namespace ca
