@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclustassess_b200.so")
+LIB_PATH = os.environ.get("CLUSTASSESS_B200_LIB") or os.path.join(_HERE, "libclustassess_b200.so")
 
 CA_OK = 0
 CA_E_ARG = -3

@@ -2,6 +2,7 @@
 // See include/clustassess_b200.h for the contract and the reference lines every entry replaces.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -353,6 +354,10 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     P.kp = L.kp;
     P.smem_bytes = smem_bytes;
     P.inv_norm = inv_norm;
+    P.dbg = 0;
+#ifdef CA_ABLATE
+    if (const char* e = getenv("CA_ABLATE")) P.dbg = atoi(e);
+#endif
     if (d_ecc || d_sim) {
         // the long streaming items first, then the resident blocks fill the machine behind them
         const Item* base_k[3] = {d_items, d_items + items_k[0].size(), d_items + items_k[0].size() + items_k[1].size()};

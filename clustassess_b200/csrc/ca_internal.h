@@ -130,6 +130,7 @@ struct RowBlockParams {
     int32_t m, mpad, kp;
     int32_t smem_bytes;      // dynamic shared memory available to sizes + tables
     double inv_norm;
+    int32_t dbg;             // ablation switches, honoured only by the -DCA_ABLATE profiling build (tools/ablate.py)
 };
 // kind: 0 = resident items, 1 = streaming items with 16-bit counters, 2 = streaming items with 32-bit counters
 int launch_rowblock(const RowBlockParams& p, int32_t nitems, int kind, cudaStream_t s);

@@ -106,32 +106,53 @@ struct Acc {           // per-thread accumulators: acc(cell c) = base + corr[c]
 };
 
 // (2) histogram of one partner for this thread's 4 cells (p01, p23 = packed labels; padding cells mirror cell 0).
-// Measured on B200 (tools/microbench.cu): a shared ATOMS instruction costs ~11 SM-cycles whether 1 or 32 lanes
-// are active and whether or not they hit the same word.  So the cheapest histogram issues as FEW atomic
-// instructions as possible, each as full as possible: one per-thread add of (leading key, #cells that share it)
-// -- 32 lanes, mostly the same address, which is free -- plus the warp's exceptions compacted into dense
-// 32-lane batches through a small per-warp staging buffer.
+// Cost model measured on B200 (tools/microbench.cu, profiles/): a shared ATOMS instruction costs ~11 SM-cycles
+// of the LSU pipe however few lanes are active, and lanes that hit the SAME word serialise into one wavefront
+// each.  So a warp issues ONE atomic instruction per partner whose lanes hold DISTINCT keys:
+//   - the threads' leading keys are aggregated (ballot / shfl / redux, two rounds: a warp rarely spans more
+//     than two runs) into one (key, count) record per run,
+//   - cells that differ from their thread's leading key become (key, 1) records,
+//   - all records are compacted into a dense list (ballot + popc -> per-warp staging buffer) and applied 32
+//     per atomic instruction.
 template <bool WIDE>
 __device__ __forceinline__ void hist_step(uint32_t tb, uint32_t stage, uint32_t p01, uint32_t p23, uint32_t rowbase, int nvalid,
                                           int lane) {
     const uint32_t kk = __byte_perm(p01, 0, 0x1010);  // leading label in both halves
     const uint32_t d01 = p01 ^ kk, d23 = p23 ^ kk;    // non-zero halves = cells that differ from it
     const bool x1 = (d01 >> 16) != 0, x2 = (d23 & 0xffffu) != 0, x3 = (d23 >> 16) != 0;
+    const uint32_t k0 = rowbase + (p01 & 0xffffu);
     const int cnt0 = nvalid - (int)x1 - (int)x2 - (int)x3;
-    if (cnt0 > 0) tbl_add<WIDE>(tb, rowbase + (p01 & 0xffffu), (uint32_t)cnt0);
-    const unsigned m1 = __ballot_sync(FULL, x1), m2 = __ballot_sync(FULL, x2), m3 = __ballot_sync(FULL, x3);
-    if ((m1 | m2 | m3) != 0) {
-        const unsigned lt = (1u << lane) - 1u;
-        const int n1 = __popc(m1), n2 = __popc(m2);
-        const int i1 = __popc(m1 & lt), i2 = n1 + __popc(m2 & lt), i3 = n1 + n2 + __popc(m3 & lt);
-        const int ne = n1 + n2 + __popc(m3);  // <= 96 = 2 * STAGE_REC * (8 / 4) records of 4 bytes
-        if (x1) sts_u32(stage + i1 * 4u, rowbase + (p01 >> 16));
-        if (x2) sts_u32(stage + i2 * 4u, rowbase + (p23 & 0xffffu));
-        if (x3) sts_u32(stage + i3 * 4u, rowbase + (p23 >> 16));
-        __syncwarp();
-        for (int h = lane; h < ne; h += 32) tbl_add<WIDE>(tb, lds_u32(stage + h * 4u), 1u);
-        __syncwarp();
+    bool pending = cnt0 > 0;
+    uint32_t rec0 = k0 | ((uint32_t)cnt0 << 16);  // record = key | count << 16 (key < 65536: the table is in smem)
+    bool x0 = pending;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const unsigned pm = __ballot_sync(FULL, pending);
+        if (pm == 0) break;
+        const int leader = __ffs(pm) - 1;
+        const uint32_t kl = __shfl_sync(FULL, k0, leader);
+        const bool mt = pending && (k0 == kl);
+        const int tot = __reduce_add_sync(FULL, mt ? cnt0 : 0);
+        if (mt) {
+            x0 = lane == leader;  // only the run's first thread keeps a record
+            rec0 = k0 | ((uint32_t)tot << 16);
+        }
+        pending = pending && !mt;
     }
+    const unsigned m0 = __ballot_sync(FULL, x0), m1 = __ballot_sync(FULL, x1), m2 = __ballot_sync(FULL, x2),
+                   m3 = __ballot_sync(FULL, x3);
+    const unsigned lt = (1u << lane) - 1u;
+    const int n0 = __popc(m0), n1 = n0 + __popc(m1), n2 = n1 + __popc(m2), ne = n2 + __popc(m3);  // ne <= 128
+    if (x0) sts_u32(stage + (uint32_t)__popc(m0 & lt) * 4u, rec0);
+    if (x1) sts_u32(stage + (uint32_t)(n0 + __popc(m1 & lt)) * 4u, (rowbase + (p01 >> 16)) | 0x10000u);
+    if (x2) sts_u32(stage + (uint32_t)(n1 + __popc(m2 & lt)) * 4u, (rowbase + (p23 & 0xffffu)) | 0x10000u);
+    if (x3) sts_u32(stage + (uint32_t)(n2 + __popc(m3 & lt)) * 4u, (rowbase + (p23 >> 16)) | 0x10000u);
+    __syncwarp();
+    for (int h = lane; h < ne; h += 32) {
+        const uint32_t rec = lds_u32(stage + h * 4u);
+        tbl_add<WIDE>(tb, rec & 0xffffu, rec >> 16);
+    }
+    __syncwarp();
 }
 
 // (3) per-element ECS of one partner.  Returns this lane's share of sum_cells ECS (for the ECS matrix).
@@ -196,6 +217,9 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
     const int per_j = kp * (4 + CW * nrows);
     int JT = (P.smem_bytes - SM_DYN) / per_j;
     JT = JT > RB_JW ? RB_JW : JT;
+#ifdef CA_ABLATE
+    if (P.dbg >> 8) JT = min(JT, P.dbg >> 8);  // force a smaller partner group
+#endif
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t s_stage = sbase + SM_STAGE + (tid >> 5) * (STAGE_REC * 8);
     const uint32_t s_lab = sbase + SM_LAB + tid * 8u;             // + jj * THREADS * 8
@@ -208,6 +232,11 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
     const int32_t* perm = P.perm + (int64_t)slot * P.perm_stride + it.pos0;
     const int mpad = P.mpad;
     const double wscale = P.w[m] * P.inv_norm;
+#ifdef CA_ABLATE
+    const int dbg = P.dbg;
+#else
+    constexpr int dbg = 0;
+#endif
 
     int4 cell = make_int4(-1, -1, -1, -1);
     int nvalid = 0;
@@ -242,12 +271,6 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
             sts_v2(s_lab + (2 * q + 1) * (THREADS * 8), __byte_perm(w0[q], w1[q], 0x7632), __byte_perm(w2[q], w3[q], 0x7632));
         }
     };
-    auto prefetch_labels = [&](int j0) {
-        if (cell.x >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lab16 + (int64_t)cell.x * mpad + j0));
-        if (cell.y >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lab16 + (int64_t)cell.y * mpad + j0));
-        if (cell.z >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lab16 + (int64_t)cell.z * mpad + j0));
-        if (cell.w >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lab16 + (int64_t)cell.w * mpad + j0));
-    };
     auto flush = [&]() {
         if (cell.x >= 0) atomicAdd(P.ecc + cell.x, acc.base * wscale);
         if (cell.y >= 0) atomicAdd(P.ecc + cell.y, (acc.base + acc.corr[1]) * wscale);
@@ -266,15 +289,14 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
 
     const int jfirst = jbeg & ~(RB_JW - 1);
     for (int j0 = jfirst; j0 < jend; j0 += RB_JW) {
-        if (RESIDENT) {
+        if (RESIDENT && !(dbg & 8)) {
             load_labels(j0);
-            if (j0 + RB_JW < jend) prefetch_labels(j0 + RB_JW);
         }
         const int tlo = max(0, jbeg - j0), thi = min(RB_JW, jend - j0);  // partners [tlo, thi) of this tile are wanted
         for (int g0 = tlo; g0 < thi; g0 += JT) {
             const int ng = min(JT, thi - g0);  // partners of this phase: j0+g0 .. j0+g0+ng-1
             __syncthreads();  // every thread is done gathering from the previous phase's tables
-            {   // (1) zero this phase's tables, stage the partners' cluster sizes
+            if (!(dbg & 4)) {   // (1) zero this phase's tables, stage the partners' cluster sizes
                 const uint32_t nz = (uint32_t)ng * tbl_bytes_j;
                 for (uint32_t o = (uint32_t)tid * 16u; o < nz; o += THREADS * 16u) sts_v4(s_tbl + o, 0u, 0u, 0u, 0u);
                 const int kq = kp / 4;  // 16-byte chunks of a row of kp uint32
@@ -289,7 +311,7 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
             }
             __syncthreads();
             // (2) histogram
-            for (int s = 0; s < nsub; s++) {
+            for (int s = 0; s < ((dbg & 1) ? 0 : nsub); s++) {
                 if (!RESIDENT) {
                     load_cells(s);
                     load_labels(j0);
@@ -303,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
             }
             __syncthreads();
             // (3) gather + accumulate
-            for (int s = 0; s < nsub; s++) {
+            for (int s = 0; s < ((dbg & 2) ? 0 : nsub); s++) {
                 if (!RESIDENT) {
                     load_cells(s);
                     load_labels(j0);
