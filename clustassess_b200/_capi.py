@@ -43,6 +43,7 @@ SYMBOLS = {
     "ca_labels_device_ptr": (C.c_void_p, [C.c_void_p]),
     "ca_labels_invalidate": (C.c_int, [C.c_void_p]),
     "ca_labels_destroy": (C.c_int, [C.c_void_p]),
+    "ca_shard_owner": (C.c_int, [C.c_int32, C.c_int32]),
     "ca_consistency_partial_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ca_consistency_finish_dev": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ca_get_profile": (C.c_int, [_F64, C.c_int]),

@@ -410,6 +410,7 @@ Labels& labels_of(ca_labels_t* h) { return h->L; }
 extern "C" {
 
 int ca_version(void) { return 100; }
+int ca_shard_owner(int32_t i, int32_t world) { return world > 0 && i >= 0 ? owner_of(i, world) : -1; }
 const char* ca_last_error(void) { return g_err; }
 
 int ca_init(const int* devices, int ndev) {

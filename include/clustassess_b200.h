@@ -125,6 +125,7 @@ int ca_labels_destroy(ca_labels_t *h);
  * Both buffers must be zeroed by the caller (or hold the values to accumulate onto).  After summing the
  * buffers over ranks (one NCCL allreduce each), ca_consistency_finish_dev() adds the identical-pair
  * constant, and mirrors / normalises the matrix. */
+int ca_shard_owner(int32_t i, int32_t world); /* rank that owns partition i and its pairs (i, j > i) */
 int ca_consistency_partial_dev(ca_labels_t *h, const double *weights_host, int32_t rank, int32_t world,
                                double *ecc_dev, double *sim_dev);
 int ca_consistency_finish_dev(int64_t n, int32_t m, const double *weights_host, double *ecc_dev,

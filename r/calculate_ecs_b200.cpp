@@ -1,0 +1,129 @@
+// r/calculate_ecs_b200.cpp -- drop-in replacement for ClustAssess's src/calculate_ecs.cpp (route A of
+// INTEGRATION.md).  Same three exported routines, same signatures, same return types -- so
+// Rcpp::compileAttributes() regenerates R/RcppExports.R:4-14 and the registration table of
+// src/RcppExports.cpp:129-145 unchanged -- but the bodies forward to the B200 library's C ABI
+// (include/clustassess_b200.h) instead of computing on the CPU.  Four batched routines are added for the
+// set-level R functions.  Link with  PKG_LIBS = -L$(CLUSTASSESS_B200_HOME) -lclustassess_b200  in src/Makevars.
+//
+// NOT compiled in this repository (the build container has neither R nor Rcpp); the Python twin of this
+// file, clustassess_b200/_capi.py, drives exactly the same entry points in the tests.
+#include <Rcpp.h>
+#include "clustassess_b200.h"
+
+using namespace Rcpp;
+
+static inline void ca_check(int rc) {
+    // The C ABI never throws and never calls R; turn its error code into an R condition here, after every
+    // C++ frame of the library has unwound (END_RCPP converts the exception, src/RcppExports.cpp:26).
+    if (rc != CA_OK) stop("%s", ca_last_error());
+}
+
+// [[Rcpp::export]]
+IntegerMatrix myContTable(IntegerVector &a, IntegerVector &b, int minim_mb1, int minim_mb2) {
+    int lo, hi_a, hi_b;
+    ca_check(ca_label_range(a.begin(), a.size(), &lo, &hi_a));
+    ca_check(ca_label_range(b.begin(), b.size(), &lo, &hi_b));
+    const int ka = hi_a - minim_mb1 + 1, kb = hi_b - minim_mb2 + 1;
+    IntegerMatrix result(ka, kb);  // column-major, exactly what ca_contingency fills
+    ca_check(ca_contingency(a.begin(), b.begin(), a.size(), minim_mb1, minim_mb2, ka, kb, result.begin(), NULL, NULL));
+    return result;
+}
+
+// [[Rcpp::export]]
+NumericVector disjointECS(IntegerVector mb1, IntegerVector mb2) {
+    if (mb1.size() != mb2.size()) stop("clustering1 and clustering2 do not have the same length.");
+    NumericVector ecsScore(mb1.size());
+    ca_check(ca_ecs_pair(mb1.begin(), mb2.begin(), mb1.size(), ecsScore.begin(), NULL));
+    return ecsScore;
+}
+
+// [[Rcpp::export]]
+double disjointECSaverage(IntegerVector mb1, IntegerVector mb2) {
+    if (mb1.size() != mb2.size()) stop("clustering1 and clustering2 do not have the same length.");
+    double avg = NA_REAL;
+    ca_check(ca_ecs_pair_mean(mb1.begin(), mb2.begin(), mb1.size(), &avg));
+    return avg;
+}
+
+// ---- batched routines: one upload, all pairs on the GPU -------------------------------------------------
+static std::vector<const int32_t *> column_pointers(List mb_list, std::vector<IntegerVector> &keep, R_xlen_t &n) {
+    // as<IntegerVector> coerces numeric (truncating) and factor (codes) inputs exactly like the reference's
+    // input_parameter<IntegerVector> (src/RcppExports.cpp:34-35); integer vectors are NOT copied.
+    const int m = mb_list.size();
+    keep.reserve(m);
+    std::vector<const int32_t *> cols(m);
+    n = -1;
+    for (int p = 0; p < m; p++) {
+        keep.push_back(as<IntegerVector>(mb_list[p]));
+        if (n < 0) n = keep[p].size();
+        if (keep[p].size() != n) stop("The partitions do not have the same length");
+        cols[p] = keep[p].begin();
+    }
+    return cols;
+}
+
+// [[Rcpp::export]]
+List ecsConsistency(List mb_list, Nullable<NumericVector> weights, bool calculate_sim_matrix) {
+    const int m = mb_list.size();
+    if (m <= 1) stop("At least two clusterings are required to calculate the consistency.");
+    std::vector<IntegerVector> keep;
+    R_xlen_t n;
+    std::vector<const int32_t *> cols = column_pointers(mb_list, keep, n);
+    NumericVector ecc(n);
+    NumericMatrix sim(calculate_sim_matrix ? m : 0, calculate_sim_matrix ? m : 0);
+    const double *w = NULL;
+    NumericVector wv;
+    if (weights.isNotNull()) {
+        wv = NumericVector(weights);
+        if (wv.size() != m) stop("weights must have one entry per clustering");
+        w = wv.begin();
+    }
+    ca_check(ca_consistency_cols(cols.data(), n, m, w, ecc.begin(), calculate_sim_matrix ? sim.begin() : NULL));
+    return List::create(Named("ecc") = ecc, Named("ecs_matrix") = sim);
+}
+
+// [[Rcpp::export]]
+NumericMatrix ecsSimMatrix(List mb_list) {
+    const int m = mb_list.size();
+    std::vector<IntegerVector> keep;
+    R_xlen_t n;
+    std::vector<const int32_t *> cols = column_pointers(mb_list, keep, n);
+    NumericMatrix sim(m, m);  // symmetric, so R's column-major layout needs no transposition
+    ca_check(ca_sim_matrix_cols(cols.data(), n, m, sim.begin()));
+    return sim;
+}
+
+// [[Rcpp::export]]
+NumericVector ecsAgreement(IntegerVector reference, List mb_list) {
+    const int m = mb_list.size();
+    std::vector<IntegerVector> keep;
+    R_xlen_t n;
+    std::vector<const int32_t *> cols = column_pointers(mb_list, keep, n);
+    if (reference.size() != n) stop("The partitions do not have the same length");
+    IntegerMatrix packed(n, m);  // ca_agreement takes one partition-major matrix
+    for (int p = 0; p < m; p++) std::copy(cols[p], cols[p] + n, packed.begin() + (R_xlen_t)p * n);
+    NumericVector out(n);
+    ca_check(ca_agreement(reference.begin(), packed.begin(), n, m, out.begin()));
+    return out;
+}
+
+// [[Rcpp::export]]
+List ecsMergeIdentical(List mb_list, NumericVector freq) {
+    const int m = mb_list.size();
+    std::vector<IntegerVector> keep;
+    R_xlen_t n;
+    std::vector<const int32_t *> cols = column_pointers(mb_list, keep, n);
+    IntegerMatrix packed(n, m);
+    for (int p = 0; p < m; p++) std::copy(cols[p], cols[p] + n, packed.begin() + (R_xlen_t)p * n);
+    IntegerVector kept(m);
+    NumericVector fout(m);
+    int u = 0;
+    ca_check(ca_merge_identical(packed.begin(), n, m, freq.begin(), kept.begin(), fout.begin(), &u));
+    IntegerVector kept1(u);
+    NumericVector f1(u);
+    for (int t = 0; t < u; t++) {
+        kept1[t] = kept[t] + 1;  // 1-based for R
+        f1[t] = fout[t];
+    }
+    return List::create(Named("keep") = kept1, Named("freq") = f1);
+}
