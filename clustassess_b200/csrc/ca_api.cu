@@ -343,6 +343,14 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     P.slot_of = W.slot_of.as<int32_t>();
     P.sizes = L.d_sizes.as<int32_t>();
     P.invsizes = L.d_invsizes.as<double>();
+    {
+        static DevBuf zeros;
+        if (!zeros.p) {
+            CA_TRY(zeros.ensure(256 * 1024));
+            CA_CUDA(cudaMemsetAsync(zeros.p, 0, 256 * 1024, s));
+        }
+        P.zeros = zeros.p;
+    }
     P.crow = W.crow.as<uint16_t>();
     P.w = W.w.as<double>();
     P.items = d_items;

@@ -121,6 +121,7 @@ struct RowBlockParams {
     const int32_t* slot_of;  // [m] partition -> perm slot (or -1)
     const int32_t* sizes;    // [m][kp]
     const double* invsizes;  // [m][kp] 1 / size (0 where the slot is unused)
+    const void* zeros;       // >= 256 KB of zero bytes: source of the bulk copy that clears the tables
     const uint16_t* crow;    // [m_slots][kp] row of a cluster inside its block
     const double* w;         // [m] weights
     const Item* items;

@@ -43,6 +43,7 @@ static_assert(CPT == 4, "the packed-label code below is written for 4 cells per 
 // shared-memory map (byte offsets from the dynamic shared base)
 static constexpr int STAGE_REC = 64;                          // exception records per warp and pass
 static constexpr int SM_SIMACC = 0;                           // RB_JW doubles
+static constexpr int SM_MBAR = 64;                            // two mbarriers: [0] tables zeroed, [1] sizes staged
 static constexpr int SM_STAGE = 128;                          // per warp STAGE_REC x 8 B records / results
 static constexpr int SM_LAB = SM_STAGE + NWARPS * STAGE_REC * 8;   // [RB_JW][THREADS] x 8 B: 4 packed labels per thread
 static constexpr int SM_DYN = SM_LAB + RB_JW * THREADS * 8;   // [JT][kp] uint32 sizes of the partners, then [JT][nrows*kp] counters
@@ -76,6 +77,32 @@ __device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint3
 }
 __device__ __forceinline__ void red_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_add_f64(uint32_t a, double v) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -------------------------------
+// One thread stages the partners' cluster sizes and zero-fills the tables (copying from a zero buffer in global
+// memory) without spending LSU instructions or registers; the block waits on the barrier's phase parity.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();  // a lost copy must fail loudly, never hang the GPU
+    }
+}
 
 // counter of table entry `key` (table base tb, bytes): two 16-bit counters per word unless WIDE
 template <bool WIDE>
@@ -287,6 +314,13 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
         }
     }
 
+    const uint32_t bar_z = sbase + SM_MBAR, bar_s = sbase + SM_MBAR + 8;
+    if (tid == 0) {
+        mbar_init(bar_z, 1);
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t par = 0;  // phase parity of both barriers
     const int jfirst = jbeg & ~(RB_JW - 1);
     for (int j0 = jfirst; j0 < jend; j0 += RB_JW) {
         if (RESIDENT && !(dbg & 8)) {
@@ -296,20 +330,18 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
         for (int g0 = tlo; g0 < thi; g0 += JT) {
             const int ng = min(JT, thi - g0);  // partners of this phase: j0+g0 .. j0+g0+ng-1
             __syncthreads();  // every thread is done gathering from the previous phase's tables
-            if (!(dbg & 4)) {   // (1) zero this phase's tables, stage the partners' cluster sizes
-                const uint32_t nz = (uint32_t)ng * tbl_bytes_j;
-                for (uint32_t o = (uint32_t)tid * 16u; o < nz; o += THREADS * 16u) sts_v4(s_tbl + o, 0u, 0u, 0u, 0u);
-                const int kq = kp / 4;  // 16-byte chunks of a row of kp uint32
-                for (int jl = 0; jl < ng; jl++) {
-                    const uint4* src = reinterpret_cast<const uint4*>(P.sizes + (int64_t)(j0 + g0 + jl) * kp);
-                    for (int i = tid; i < kq; i += THREADS) {
-                        const uint4 v = __ldg(src + i);
-                        sts_v4(s_sz + (uint32_t)(jl * kp + i * 4) * 4u, v.x, v.y, v.z, v.w);
-                    }
+            if (!(dbg & 4)) {   // (1) zero this phase's tables and stage the partners' cluster sizes: two bulk copies
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order the block's generic reads before the async writes
+                    const uint32_t nz = (uint32_t)ng * tbl_bytes_j, nsz = (uint32_t)ng * kp * 4u;
+                    mbar_expect_tx(bar_z, nz);
+                    bulk_g2s(s_tbl, P.zeros, nz, bar_z);
+                    mbar_expect_tx(bar_s, nsz);
+                    bulk_g2s(s_sz, P.sizes + (int64_t)(j0 + g0) * kp, nsz, bar_s);
                 }
                 if (WANT_SIM && tid < RB_JW) sts_f64(sbase + SM_SIMACC + tid * 8u, 0.0);
+                mbar_wait(bar_z, par);
             }
-            __syncthreads();
             // (2) histogram
             for (int s = 0; s < ((dbg & 1) ? 0 : nsub); s++) {
                 if (!RESIDENT) {
@@ -324,6 +356,8 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
                 }
             }
             __syncthreads();
+            if (!(dbg & 4)) mbar_wait(bar_s, par);
+            par ^= 1u;
             // (3) gather + accumulate
             for (int s = 0; s < ((dbg & 2) ? 0 : nsub); s++) {
                 if (!RESIDENT) {
