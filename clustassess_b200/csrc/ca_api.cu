@@ -238,11 +238,14 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     std::vector<int32_t> h_slot_of(m, -1);
     std::vector<int32_t> h_cstart((size_t)std::max(nparts, 1) * L.kp, 0);
     std::vector<uint16_t> h_crow((size_t)std::max(nparts, 1) * L.kp, 0);
-    std::vector<Item> items_k[3];  // 0 resident, 1 streaming (16-bit counters), 2 streaming (32-bit counters)
+    // 0 resident (phase-synchronous), 1 streaming (16-bit counters), 2 streaming (32-bit counters), 3 resident (pipelined)
+    constexpr int NK = 4;
+    std::vector<Item> items_k[NK];
+    const bool use_pipe = getenv("CA_NO_PIPELINE") == nullptr;
     int64_t perm_stride = 4;
     {   // plan every owned partition; partitions are independent, so the host threads share them
         const int nthreads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, nparts}));
-        std::vector<std::vector<Item>> items_t[3];
+        std::vector<std::vector<Item>> items_t[NK];
         for (auto& v : items_t) v.resize(nthreads);
         std::vector<int64_t> stride_t(nthreads, 4);
         std::vector<int> rc_t(nthreads, CA_OK);
@@ -268,7 +271,9 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                     it.jend = ref_only >= 0 ? m_partners : m;
                     it.sa = po.sa[t];
                     it.pad_ = 0;
-                    items_t[it.npos <= RB_CAP ? 0 : (po.wide[t] ? 2 : 1)][tix].push_back(it);
+                    int kind = it.npos <= RB_CAP ? 0 : (po.wide[t] ? 2 : 1);
+                    if (kind == 0 && use_pipe && rowblock_pipe_buffers(L.kp, it.nrows, smem_bytes) >= 3) kind = 3;
+                    items_t[kind][tix].push_back(it);
                 }
             }
         };
@@ -285,7 +290,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                 return rc_t[t];
             }
             perm_stride = std::max(perm_stride, stride_t[t]);
-            for (int k = 0; k < 3; k++) items_k[k].insert(items_k[k].end(), items_t[k][t].begin(), items_t[k][t].end());
+            for (int k = 0; k < NK; k++) items_k[k].insert(items_k[k].end(), items_t[k][t].begin(), items_t[k][t].end());
         }
     }
     auto cost = [](const Item& a) { return (int64_t)a.npos * (a.jend - a.jbeg); };
@@ -309,7 +314,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
 
     // ---- upload plan, sort ------------------------------------------------------------------------
     Workspace& W = ws();
-    const size_t nitems = items_k[0].size() + items_k[1].size() + items_k[2].size();
+    size_t nitems = 0;
+    for (auto& v : items_k) nitems += v.size();
     CA_TRY(W.perm.ensure((size_t)std::max(nparts, 1) * perm_stride * 4));
     CA_TRY(W.cstart.ensure(h_cstart.size() * 4));
     CA_TRY(W.crow.ensure(h_crow.size() * 2));
@@ -363,19 +369,53 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     P.smem_bytes = smem_bytes;
     P.inv_norm = inv_norm;
     P.dbg = 0;
+    P.timeline = nullptr;
 #ifdef CA_ABLATE
     if (const char* e = getenv("CA_ABLATE")) P.dbg = atoi(e);
+    static DevBuf tl;
+    const size_t tl_bytes = 256 * 16 * 10 * sizeof(long long);
+    if (getenv("CA_TIMELINE")) {
+        CA_TRY(tl.ensure(tl_bytes));
+        CA_CUDA(cudaMemsetAsync(tl.p, 0, tl_bytes, s));
+        P.timeline = tl.as<long long>();
+    }
 #endif
     if (d_ecc || d_sim) {
         // the long streaming items first, then the resident blocks fill the machine behind them
-        const Item* base_k[3] = {d_items, d_items + items_k[0].size(), d_items + items_k[0].size() + items_k[1].size()};
-        for (int kind : {2, 1, 0}) {
+        const Item* base_k[NK];
+        {
+            size_t off = 0;
+            for (int k = 0; k < NK; k++) {
+                base_k[k] = d_items + off;
+                off += items_k[k].size();
+            }
+        }
+        for (int kind : {2, 1, 3, 0}) {
             P.items = base_k[kind];
             CA_TRY(launch_rowblock(P, (int32_t)items_k[kind].size(), kind, s));
         }
     }
     CA_CUDA(cudaEventRecord(c.ev[5], s));
     CA_CUDA(cudaStreamSynchronize(s));
+#ifdef CA_ABLATE
+    if (P.timeline) {  // average section cycles per warp over the first 256 pipelined blocks
+        std::vector<long long> h(256 * 16 * 10);
+        CA_CUDA(cudaMemcpy(h.data(), P.timeline, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        double sum[10] = {0}, nw = 0, gsum = 0;
+        for (size_t w = 0; w < 256 * 16; w++) {
+            if (h[w * 10 + 7] == 0) continue;
+            nw++;
+            gsum += (double)h[w * 10 + 8];
+            for (int k = 0; k < 10; k++) sum[k] += (double)h[w * 10 + k];
+        }
+        if (nw > 0) {
+            const char* nm[8] = {"labels", "wait_zero", "hist", "refill", "wait_hist", "wait_sizes", "gather", "total"};
+            fprintf(stderr, "[timeline] %d warps, avg partners %.1f, ring %.1f; cycles per warp-partner:", (int)nw, gsum / nw, sum[9] / nw);
+            for (int k = 0; k < 8; k++) fprintf(stderr, " %s=%.0f", nm[k], sum[k] / gsum);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     float ms;
     CA_CUDA(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
     c.prof[0] = ms;

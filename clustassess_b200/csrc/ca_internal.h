@@ -131,11 +131,13 @@ struct RowBlockParams {
     int32_t m, mpad, kp;
     int32_t smem_bytes;      // dynamic shared memory available to sizes + tables
     double inv_norm;
+    long long* timeline;     // per-warp section cycle counters (-DCA_ABLATE build with CA_TIMELINE=1 only), else null
     int32_t dbg;             // ablation switches, honoured only by the -DCA_ABLATE profiling build (tools/ablate.py)
 };
 // kind: 0 = resident items, 1 = streaming items with 16-bit counters, 2 = streaming items with 32-bit counters
 int launch_rowblock(const RowBlockParams& p, int32_t nitems, int kind, cudaStream_t s);
 int rowblock_smem_budget(int32_t kp, int32_t* max_rows_out);
+int rowblock_pipe_buffers(int32_t kp, int32_t nrows, int32_t smem_bytes);  // ring buffers the pipelined kernel gets (>= 3 to use it)
 
 // ca_pair.cu
 int pair_contingency(const int32_t* d_a, const int32_t* d_b, int64_t n, int32_t min_a, int32_t min_b, int32_t ka,

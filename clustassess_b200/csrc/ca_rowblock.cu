@@ -183,16 +183,20 @@ __device__ __forceinline__ void hist_step(uint32_t tb, uint32_t stage, uint32_t 
 }
 
 // (3) per-element ECS of one partner.  Returns this lane's share of sum_cells ECS (for the ECS matrix).
-template <bool WIDE, bool WANT_SIM>
+// Partner cluster sizes come from shared memory (szb, staged per phase) or, with GSZ, straight from the global
+// sizes row szg (L2-resident, 4 MB in all): the leading key's size sb0 is then fetched by the caller BEFORE it
+// waits for the table, so only the exceptions' lookups sit in the dependent chain.
+template <bool WIDE, bool WANT_SIM, bool GSZ = false>
 __device__ __forceinline__ double gather_step(uint32_t tb, uint32_t szb, uint32_t stage, uint32_t p01, uint32_t p23,
-                                              uint32_t rowbase, uint32_t sa, int nvalid, double wj, int lane, Acc& acc) {
+                                              uint32_t rowbase, uint32_t sa, int nvalid, double wj, int lane, Acc& acc,
+                                              const int32_t* __restrict__ szg = nullptr, uint32_t sb0 = 0) {
     const uint32_t kk = __byte_perm(p01, 0, 0x1010);
     const uint32_t d01 = p01 ^ kk, d23 = p23 ^ kk;
     const bool x1 = (d01 >> 16) != 0, x2 = (d23 & 0xffffu) != 0, x3 = (d23 >> 16) != 0;
     const uint32_t b0 = p01 & 0xffffu;
     double we0 = 0.0, es = 0.0;
     if (nvalid > 0) {
-        const double e0 = ecs_of(tbl_get<WIDE>(tb, rowbase + b0), sa, lds_u32(szb + b0 * 4u));
+        const double e0 = ecs_of(tbl_get<WIDE>(tb, rowbase + b0), sa, GSZ ? sb0 : lds_u32(szb + b0 * 4u));
         we0 = e0 * wj;
         acc.base += we0;
         if (WANT_SIM) es = e0 * (double)(nvalid - (int)x1 - (int)x2 - (int)x3);
@@ -217,7 +221,8 @@ __device__ __forceinline__ double gather_step(uint32_t tb, uint32_t szb, uint32_
             for (int h = lane; h < nq; h += 32) {
                 uint32_t rec, rsa;
                 lds_v2(stage + h * 8u, rec, rsa);
-                const double e = ecs_of(tbl_get<WIDE>(tb, rec & 0xffffu), rsa, lds_u32(szb + (rec >> 16) * 4u));
+                const uint32_t rsb = GSZ ? (uint32_t)__ldg(szg + (rec >> 16)) : lds_u32(szb + (rec >> 16) * 4u);
+                const double e = ecs_of(tbl_get<WIDE>(tb, rec & 0xffffu), rsa, rsb);
                 if (WANT_SIM) es += e;
                 sts_f64(stage + h * 8u, e * wj);
             }
@@ -393,6 +398,209 @@ __global__ void __launch_bounds__(THREADS, 2) rowblock_kernel(const RowBlockPara
     if (RESIDENT && WANT_ECC) flush();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined resident kernel.  Measured on the full config-5 job, the phase-synchronous kernel above spends
+// ~60 % of its time stalled at the two block barriers of every phase (warp skew + staging latency): its time
+// is A + B/JT with JT (partners per phase) capped at ~3 by shared memory.  Here the same shared memory is a
+// RING of NB >= 3 buffers, one partner each, and all hand-offs are mbarriers, so no warp ever waits for the
+// slowest warp of the SAME step:
+//     iteration g (every warp):  hist(partner g) -> arrive H[g]        ... table of g is being built
+//                                wait H[g-1] (all warps)               ... finished one half-iteration ago
+//                                gather(partner g-1) -> arrive G[g-1]
+//     the LAST warp to finish gather(g-1) (a shared release counter tells it) refills that buffer at once for
+//     partner g-1+NB with a TMA bulk copy from a zero buffer, completing on Z.
+// Nobody ever waits for a refill to be ISSUED, every dependency has at least half an iteration of slack, and the
+// TMA latency has a whole iteration.  Partner cluster sizes are NOT staged: the leading key's size is fetched
+// from the L2-resident sizes matrix before the H wait, the exceptions' sizes by their handler lanes -- which frees
+// a third of the ring's shared memory for more buffers.
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int PM_SIMACC = 0;                            // RB_JW doubles, one per ring buffer
+static constexpr int PM_MBAR = 64;                             // 3 x RB_JW mbarriers (Z, S, H per buffer) + RB_JW release counters
+static constexpr int PM_STAGE = PM_MBAR + 4 * RB_JW * 8;
+static constexpr int PM_LAB = PM_STAGE + NWARPS * STAGE_REC * 8;
+static constexpr int PM_DYN = PM_LAB + RB_JW * THREADS * 8;    // ring: NB x nrows*kp 16-bit counters
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+int rowblock_pipe_buffers(int32_t kp, int32_t nrows, int32_t smem_bytes) {
+    const int per_j = kp * 2 * nrows;
+    const int nb = (smem_bytes - PM_DYN) / per_j;
+    return nb > RB_JW ? RB_JW : nb;
+}
+
+template <bool WANT_ECC, bool WANT_SIM>
+__global__ void __launch_bounds__(THREADS, 2) rowblock_pipe_kernel(const RowBlockParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Item it = P.items[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int m = it.m;
+    const int jbeg = it.jbeg, G = it.jend - it.jbeg;
+    if (G <= 0) return;
+    const int kp = P.kp, nrows = it.nrows;
+    const uint32_t per_j = (uint32_t)kp * 2u * nrows;  // one table per ring buffer
+    int NB = (P.smem_bytes - PM_DYN) / (int)per_j;
+    NB = NB > RB_JW ? RB_JW : NB;  // >= 3 guaranteed by the host
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t s_stage = sbase + PM_STAGE + (tid >> 5) * (STAGE_REC * 8);
+    const uint32_t s_lab = sbase + PM_LAB + tid * 8u;
+    const uint32_t s_ring = sbase + PM_DYN;                       // buffer b: table at s_ring + b*per_j
+    const uint32_t bar0 = sbase + PM_MBAR;                        // Z[b] = bar0+b*8, H[b] = +128, release counter = +192
+    const int slot = P.slot_of[m];
+    const int32_t* perm = P.perm + (int64_t)slot * P.perm_stride + it.pos0;
+    const int mpad = P.mpad;
+    const double wscale = P.w[m] * P.inv_norm;
+
+    if (tid == 0) {
+        for (int b = 0; b < RB_JW; b++) {
+            mbar_init(bar0 + b * 8, 1);
+            mbar_init(bar0 + 128 + b * 8, NWARPS);
+            sts_u32(bar0 + 192 + b * 8, 0u);  // release counter of buffer b
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (WANT_SIM && tid < RB_JW) sts_f64(sbase + PM_SIMACC + tid * 8u, 0.0);
+
+    int4 cell = make_int4(-1, -1, -1, -1);
+    {
+        const int p = tid * CPT;
+        if (p < it.npos) cell = __ldg(reinterpret_cast<const int4*>(perm + p));
+    }
+    const int nvalid = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);
+    uint32_t rowbase = 0, sa = (uint32_t)it.sa;
+    if (nrows > 1 && cell.x >= 0) {
+        const int a = (int)__ldg(P.lab16 + (int64_t)cell.x * mpad + m);
+        rowbase = (uint32_t)__ldg(P.crow + (int64_t)slot * kp + a) * (uint32_t)kp;
+        sa = (uint32_t)__ldg(P.sizes + (int64_t)m * kp + a);
+    }
+    Acc acc;
+    acc.base = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPT; c++) acc.corr[c] = 0.0;
+
+    // A cell's 32-byte DRAM sector holds the labels of TWO consecutive 8-partner tiles.  The even tile's load asks
+    // L2 to keep the sector (evict_last) so that the odd tile, one tile period later, still finds it; the odd
+    // tile's load releases it (evict_first).  Otherwise every sector is fetched from DRAM twice.
+    uint64_t pol_keep, pol_drop;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
+    auto ldg_hint = [&](const uint16_t* ptr, uint64_t pol) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(ptr), "l"(pol));
+        return v;
+    };
+    auto load_labels = [&](int j0) {  // as in the phase-synchronous kernel: thread-private slice of the scratch tile
+        const uint64_t pol = (j0 & RB_JW) ? pol_drop : pol_keep;
+        uint4 l0 = make_uint4(0, 0, 0, 0), l1, l2, l3;
+        if (cell.x >= 0) l0 = ldg_hint(P.lab16 + (int64_t)cell.x * mpad + j0, pol);
+        l1 = l2 = l3 = l0;
+        if (cell.y >= 0) l1 = ldg_hint(P.lab16 + (int64_t)cell.y * mpad + j0, pol);
+        if (cell.z >= 0) l2 = ldg_hint(P.lab16 + (int64_t)cell.z * mpad + j0, pol);
+        if (cell.w >= 0) l3 = ldg_hint(P.lab16 + (int64_t)cell.w * mpad + j0, pol);
+        const uint32_t w0[4] = {l0.x, l0.y, l0.z, l0.w}, w1[4] = {l1.x, l1.y, l1.z, l1.w};
+        const uint32_t w2[4] = {l2.x, l2.y, l2.z, l2.w}, w3[4] = {l3.x, l3.y, l3.z, l3.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            sts_v2(s_lab + (2 * q) * (THREADS * 8), __byte_perm(w0[q], w1[q], 0x5410), __byte_perm(w2[q], w3[q], 0x5410));
+            sts_v2(s_lab + (2 * q + 1) * (THREADS * 8), __byte_perm(w0[q], w1[q], 0x7632), __byte_perm(w2[q], w3[q], 0x7632));
+        }
+    };
+    // refill ring buffer of partner gz (one thread): flush + clear its ECS-matrix accumulator, zero-fill the table
+    auto refill = [&](int gz) {
+        const int b = gz % NB;
+        if (WANT_SIM && gz >= NB) {
+            const double v = lds_f64(sbase + PM_SIMACC + b * 8u);
+            if (v != 0.0) atomicAdd(P.sim + (int64_t)m * P.m + (jbeg + gz - NB), v);
+            sts_f64(sbase + PM_SIMACC + b * 8u, 0.0);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the block's generic reads before the async writes
+        mbar_expect_tx(bar0 + b * 8, per_j);
+        bulk_g2s(s_ring + (uint32_t)b * per_j, P.zeros, per_j, bar0 + b * 8);
+    };
+
+    __syncthreads();  // barriers initialised, accumulators cleared
+    if (tid == 0)
+        for (int gz = 0; gz < NB && gz < G; gz++) refill(gz);
+
+    const int jfirst = jbeg & ~(RB_JW - 1);
+    uint32_t q01 = 0, q23 = 0;  // labels of the previous partner (gathered one iteration after their histogram)
+#ifdef CA_ABLATE
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), tstart = t0;
+#define CA_TICK(k) { long long t1_ = clock64(); tk[k] += t1_ - t0; t0 = t1_; }
+#else
+#define CA_TICK(k)
+#endif
+    for (int g = 0; g <= G; g++) {
+        uint32_t p01 = 0, p23 = 0;
+        if (g < G) {
+            const int j = jbeg + g, jj = (j - jfirst) & (RB_JW - 1);
+            if (jj == 0 || g == 0) load_labels(j & ~(RB_JW - 1));
+            const int b = g % NB;
+            lds_v2(s_lab + (uint32_t)jj * (THREADS * 8), p01, p23);
+            CA_TICK(0)
+            mbar_wait(bar0 + b * 8, (uint32_t)((g / NB) & 1));  // table zero-filled
+            CA_TICK(1)
+            hist_step<false>(s_ring + (uint32_t)b * per_j, s_stage, p01, p23, rowbase, nvalid, lane);
+            if (lane == 0) mbar_arrive(bar0 + 128 + b * 8);      // (hist_step ends with __syncwarp)
+            CA_TICK(2)
+        }
+        CA_TICK(3)
+        if (g >= 1) {
+            const int b = (g - 1) % NB;
+            const int32_t* szg = P.sizes + (int64_t)(jbeg + g - 1) * kp;  // partner g-1's cluster sizes (global, L2)
+            const uint32_t sb0 = nvalid > 0 ? (uint32_t)__ldg(szg + (q01 & 0xffffu)) : 0u;  // in flight during the wait
+            const double wj = __ldg(P.w + jbeg + g - 1);
+            mbar_wait(bar0 + 128 + b * 8, (uint32_t)(((g - 1) / NB) & 1));  // every warp has added partner g-1 to the table
+            CA_TICK(4)
+            double es = gather_step<false, WANT_SIM, true>(s_ring + (uint32_t)b * per_j, 0u, s_stage, q01, q23, rowbase, sa, nvalid, wj,
+                                                           lane, acc, szg, sb0);
+            if (WANT_SIM) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
+                if (lane == 0 && es != 0.0) red_add_f64(sbase + PM_SIMACC + b * 8u, es);
+            }
+            __syncwarp();
+            if (lane == 0) {  // release the buffer; the last warp to do so refills it for partner g-1+NB right away
+                uint32_t old;
+                asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(bar0 + 192 + b * 8) : "memory");
+                if (old == NWARPS - 1) {
+                    sts_u32(bar0 + 192 + b * 8, 0u);
+                    if (g - 1 + NB < G) refill(g - 1 + NB);
+                }
+            }
+            CA_TICK(6)
+        }
+        q01 = p01;
+        q23 = p23;
+    }
+#ifdef CA_ABLATE
+    if (P.timeline && lane == 0 && blockIdx.x < 256) {
+        long long* o = P.timeline + ((size_t)blockIdx.x * NWARPS + (tid >> 5)) * 10;
+        for (int k = 0; k < 7; k++) o[k] = tk[k];
+        o[7] = clock64() - tstart;
+        o[8] = G;
+        o[9] = NB;
+    }
+#endif
+    if (WANT_SIM) {  // the last min(NB, G) partners still sit in their accumulators
+        __syncthreads();
+        if (tid < NB && tid < G) {
+            const int gl = G - 1 - ((G - 1 - tid) % NB + NB) % NB;  // last partner that used buffer tid
+            const double v = lds_f64(sbase + PM_SIMACC + tid * 8u);
+            if (gl >= 0 && v != 0.0) atomicAdd(P.sim + (int64_t)m * P.m + (jbeg + gl), v);
+        }
+    }
+    if (WANT_ECC) {
+        if (cell.x >= 0) atomicAdd(P.ecc + cell.x, acc.base * wscale);
+        if (cell.y >= 0) atomicAdd(P.ecc + cell.y, (acc.base + acc.corr[1]) * wscale);
+        if (cell.z >= 0) atomicAdd(P.ecc + cell.z, (acc.base + acc.corr[2]) * wscale);
+        if (cell.w >= 0) atomicAdd(P.ecc + cell.w, (acc.base + acc.corr[3]) * wscale);
+    }
+}
+
 // Shared memory available to one block, and the number of table rows a resident block may own so that
 // at least one partner fits (JT >= 1).  Two blocks per SM when the tables allow it.
 int rowblock_smem_budget(int32_t kp, int32_t* max_rows_out) {
@@ -423,7 +631,18 @@ static int launch_one(const RowBlockParams& p, int32_t nitems, cudaStream_t s) {
     return CA_OK;
 }
 
-// kind: 0 = resident items (16-bit counters), 1 = streaming items (16-bit), 2 = streaming items (32-bit)
+template <bool E, bool S>
+static int launch_pipe(const RowBlockParams& p, int32_t nitems, cudaStream_t s) {
+    auto kern = rowblock_pipe_kernel<E, S>;
+    CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    kern<<<(unsigned)nitems, THREADS, (size_t)p.smem_bytes, s>>>(p);
+    CA_CUDA(cudaGetLastError());
+    ca::ctx().launches++;
+    return CA_OK;
+}
+
+// kind: 0 = resident items (16-bit counters), 1 = streaming items (16-bit), 2 = streaming items (32-bit),
+//       3 = resident items through the pipelined kernel
 int launch_rowblock(const RowBlockParams& p, int32_t nitems, int kind, cudaStream_t s) {
     if (nitems <= 0) return CA_OK;
     const bool e = p.ecc != nullptr, sm = p.sim != nullptr;
@@ -431,6 +650,11 @@ int launch_rowblock(const RowBlockParams& p, int32_t nitems, int kind, cudaStrea
         if (e && sm) return launch_one<false, true, true, true>(p, nitems, s);
         if (e) return launch_one<false, true, true, false>(p, nitems, s);
         return launch_one<false, true, false, true>(p, nitems, s);
+    }
+    if (kind == 3) {
+        if (e && sm) return launch_pipe<true, true>(p, nitems, s);
+        if (e) return launch_pipe<true, false>(p, nitems, s);
+        return launch_pipe<false, true>(p, nitems, s);
     }
     if (kind == 1) {
         if (e && sm) return launch_one<false, false, true, true>(p, nitems, s);
