@@ -163,6 +163,24 @@ int prepare_ranks(Labels& L) {
     L.h_sizes.assign((size_t)m * L.kp, 0);
     CA_CUDA(cudaMemcpyAsync(L.h_sizes.data(), L.d_sizes.p, (size_t)m * L.kp * 4, cudaMemcpyDeviceToHost, s));
     CA_CUDA(cudaStreamSynchronize(s));
+    {   // tile engine: cluster sizes as uint16 (0xFFFF = look the size up) and K_j | flags per partition
+        std::vector<uint16_t> h16((size_t)m * L.kp);
+        std::vector<int32_t> hk(L.mpad, 0);
+        for (int32_t p = 0; p < m; p++) {
+            bool big = false;
+            for (int32_t k = 0; k < L.kp; k++) {
+                const int32_t v = L.h_sizes[(size_t)p * L.kp + k];
+                big = big || v >= 65535;
+                h16[(size_t)p * L.kp + k] = (uint16_t)std::min(v, 65535);
+            }
+            hk[p] = L.h_k[p] | (big ? (1 << 30) : 0);
+        }
+        CA_TRY(L.d_sizes16.ensure(h16.size() * 2));
+        CA_TRY(L.d_kinfo.ensure(hk.size() * 4));
+        CA_CUDA(cudaMemcpyAsync(L.d_sizes16.p, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice, s));
+        CA_CUDA(cudaMemcpyAsync(L.d_kinfo.p, hk.data(), hk.size() * 4, cudaMemcpyHostToDevice, s));
+        CA_CUDA(cudaStreamSynchronize(s));
+    }
     L.ranked = true;
     return CA_OK;
 }
@@ -222,7 +240,9 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     // ---- host planning ----------------------------------------------------------------------------
     auto t_plan0 = std::chrono::steady_clock::now();
     int32_t max_rows = 0;
-    const int smem_bytes = rowblock_smem_budget(L.kp, &max_rows);
+    const bool tile_engine = getenv("CA_ENGINE_V1") == nullptr;  // CA_ENGINE_V1=1 selects the first-generation row-block kernels
+    const int smem_bytes = tile_engine ? tile_smem_budget(L.kmax, &max_rows) : rowblock_smem_budget(L.kp, &max_rows);
+    const int32_t blk_cpt = tile_engine ? TL_CPT : RB_CPT, blk_cap = tile_engine ? TL_CAP : RB_CAP;
     if (max_rows < 1) {
         set_error("%d clusters per partition need more shared memory per table row than one SM has", L.kmax);
         return CA_E_UNSUPPORTED;
@@ -254,7 +274,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
             PlanOut po;
             for (int32_t sl = tix; sl < nparts; sl += nthreads) {
                 const int32_t p = parts[sl];
-                int rc = plan_blocks(L.h_sizes.data() + (size_t)p * L.kp, L.h_k[p], RB_CPT, RB_CAP, max_rows, po);
+                int rc = plan_blocks(L.h_sizes.data() + (size_t)p * L.kp, L.h_k[p], blk_cpt, blk_cap, max_rows, po);
                 if (rc != CA_OK) { rc_t[tix] = rc; return; }
                 stride_t[tix] = std::max<int64_t>(stride_t[tix], (po.total_pos + 3) & ~3LL);
                 for (int32_t k = 0; k < L.h_k[p]; k++) {
@@ -270,9 +290,10 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                     it.jbeg = ref_only >= 0 ? 0 : p + 1;
                     it.jend = ref_only >= 0 ? m_partners : m;
                     it.sa = po.sa[t];
-                    it.pad_ = 0;
+                    it.pad_ = tile_engine ? po.wide[t] : 0;
                     int kind = it.npos <= RB_CAP ? 0 : (po.wide[t] ? 2 : 1);
-                    if (kind == 0 && use_pipe && rowblock_pipe_buffers(L.kp, it.nrows, smem_bytes) >= 3) kind = 3;
+                    if (tile_engine) kind = 0;  // one kernel serves every kind of item
+                    if (!tile_engine && kind == 0 && use_pipe && rowblock_pipe_buffers(L.kp, it.nrows, smem_bytes) >= 3) kind = 3;
                     items_t[kind][tix].push_back(it);
                 }
             }
@@ -380,7 +401,28 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         P.timeline = tl.as<long long>();
     }
 #endif
-    if (d_ecc || d_sim) {
+    if (tile_engine) {
+        TileParams T;
+        T.lab16 = P.lab16;
+        T.perm = P.perm;
+        T.slot_of = P.slot_of;
+        T.sizes = P.sizes;
+        T.sizes16 = L.d_sizes16.as<uint16_t>();
+        T.kinfo = L.d_kinfo.as<int32_t>();
+        T.zeros = P.zeros;
+        T.crow = P.crow;
+        T.w = P.w;
+        T.items = d_items;
+        T.ecc = d_ecc;
+        T.sim = d_sim;
+        T.perm_stride = perm_stride;
+        T.m = m;
+        T.mpad = L.mpad;
+        T.kp = L.kp;
+        T.smem_bytes = smem_bytes;
+        T.inv_norm = inv_norm;
+        CA_TRY(launch_tile(T, (int32_t)items_k[0].size(), s));  // items sorted by cost, longest first
+    } else if (d_ecc || d_sim) {
         // the long streaming items first, then the resident blocks fill the machine behind them
         const Item* base_k[NK];
         {
@@ -569,6 +611,7 @@ int ca_labels_destroy(ca_labels_t* h) {
     if (L.d_raw) cudaFree(L.d_raw);
     L.d_min.release(); L.d_max.release(); L.d_cnt.release(); L.d_rank.release(); L.d_kcount.release();
     L.d_roff.release(); L.d_sizes.release(); L.d_invsizes.release(); L.d_lab16.release();
+    L.d_sizes16.release(); L.d_kinfo.release();
     delete h;
     return CA_OK;
 }

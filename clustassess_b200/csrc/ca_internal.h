@@ -67,7 +67,7 @@ struct Item {       // one unit of work of the row-block kernel: rows [..] x cel
     int32_t jbeg;   // partner partitions j in [jbeg, jend)
     int32_t jend;
     int32_t sa;     // cluster size when nrows == 1 (else 0)
-    int32_t pad_;
+    int32_t pad_;   // tile engine: 1 = streaming item with more than 65535 cells (32-bit counters)
 };
 
 // host planner (ca_plan.cpp)
@@ -90,7 +90,7 @@ struct Labels {
     std::vector<int64_t> h_roff;  // offset of partition p's range in d_cnt / d_rank
     bool identity = true;         // every partition's labels are already dense (rank == label - min)
     int32_t kmax = 0, kp = 0, mpad = 0;
-    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_invsizes, d_lab16;
+    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_invsizes, d_lab16, d_sizes16, d_kinfo;
     std::vector<int32_t> h_sizes;  // [m][kp]
 };
 
@@ -138,6 +138,32 @@ struct RowBlockParams {
 int launch_rowblock(const RowBlockParams& p, int32_t nitems, int kind, cudaStream_t s);
 int rowblock_smem_budget(int32_t kp, int32_t* max_rows_out);
 int rowblock_pipe_buffers(int32_t kp, int32_t nrows, int32_t smem_bytes);  // ring buffers the pipelined kernel gets (>= 3 to use it)
+
+// ca_tile.cu -- second-generation engine: 1024 threads x 4 cells, 8-partner phases, lanes mapped to partners
+constexpr int TL_CPT = 4;
+constexpr int TL_THREADS = 1024;
+constexpr int TL_CAP = TL_CPT * TL_THREADS;  // 4096 positions per resident block
+constexpr int TL_MAX_ROWS = 1024;
+struct TileParams {
+    const uint16_t* lab16;    // [n][mpad] compact labels, cell-major
+    const int32_t* perm;      // [m_slots][perm_stride] cluster-sorted cell ids, -1 = padding
+    const int32_t* slot_of;   // [m] partition -> perm slot (or -1)
+    const int32_t* sizes;     // [m][kp] cluster sizes
+    const uint16_t* sizes16;  // [m][kp] min(size, 65535)
+    const int32_t* kinfo;     // [mpad] K_j | (1 << 30 if partition j has a cluster with >= 65535 cells), 0 beyond m
+    const void* zeros;        // >= 256 KB of zero bytes: source of the bulk copy that clears the tables
+    const uint16_t* crow;     // [m_slots][kp] row of a cluster inside its block
+    const double* w;          // [mpad + 8] weights
+    const Item* items;
+    double* ecc;              // [n] accumulated with atomics (may be null)
+    double* sim;              // [m*m] accumulated with atomics (may be null)
+    int64_t perm_stride;
+    int32_t m, mpad, kp;
+    int32_t smem_bytes;       // dynamic shared memory per block
+    double inv_norm;
+};
+int launch_tile(const TileParams& p, int32_t nitems, cudaStream_t s);
+int tile_smem_budget(int32_t kmax, int32_t* max_rows_out);
 
 // ca_pair.cu
 int pair_contingency(const int32_t* d_a, const int32_t* d_b, int64_t n, int32_t min_a, int32_t min_b, int32_t ka,
