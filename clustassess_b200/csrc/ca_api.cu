@@ -163,21 +163,21 @@ int prepare_ranks(Labels& L) {
     L.h_sizes.assign((size_t)m * L.kp, 0);
     CA_CUDA(cudaMemcpyAsync(L.h_sizes.data(), L.d_sizes.p, (size_t)m * L.kp * 4, cudaMemcpyDeviceToHost, s));
     CA_CUDA(cudaStreamSynchronize(s));
-    {   // tile engine: cluster sizes as uint16 (0xFFFF = look the size up) and K_j | flags per partition
-        std::vector<uint16_t> h16((size_t)m * L.kp);
+    {   // tile engine: initial table entries min(size, 65535) << 16 (0xFFFF = look the size up) and K_j | flags per partition
+        std::vector<uint32_t> h16((size_t)m * L.kp);
         std::vector<int32_t> hk(L.mpad, 0);
         for (int32_t p = 0; p < m; p++) {
             bool big = false;
             for (int32_t k = 0; k < L.kp; k++) {
                 const int32_t v = L.h_sizes[(size_t)p * L.kp + k];
                 big = big || v >= 65535;
-                h16[(size_t)p * L.kp + k] = (uint16_t)std::min(v, 65535);
+                h16[(size_t)p * L.kp + k] = (uint32_t)std::min(v, 65535) << 16;
             }
             hk[p] = L.h_k[p] | (big ? (1 << 30) : 0);
         }
-        CA_TRY(L.d_sizes16.ensure(h16.size() * 2));
+        CA_TRY(L.d_spack.ensure(h16.size() * 4));
         CA_TRY(L.d_kinfo.ensure(hk.size() * 4));
-        CA_CUDA(cudaMemcpyAsync(L.d_sizes16.p, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice, s));
+        CA_CUDA(cudaMemcpyAsync(L.d_spack.p, h16.data(), h16.size() * 4, cudaMemcpyHostToDevice, s));
         CA_CUDA(cudaMemcpyAsync(L.d_kinfo.p, hk.data(), hk.size() * 4, cudaMemcpyHostToDevice, s));
         CA_CUDA(cudaStreamSynchronize(s));
     }
@@ -407,7 +407,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         T.perm = P.perm;
         T.slot_of = P.slot_of;
         T.sizes = P.sizes;
-        T.sizes16 = L.d_sizes16.as<uint16_t>();
+        T.spack = L.d_spack.as<uint32_t>();
         T.kinfo = L.d_kinfo.as<int32_t>();
         T.zeros = P.zeros;
         T.crow = P.crow;
@@ -611,7 +611,7 @@ int ca_labels_destroy(ca_labels_t* h) {
     if (L.d_raw) cudaFree(L.d_raw);
     L.d_min.release(); L.d_max.release(); L.d_cnt.release(); L.d_rank.release(); L.d_kcount.release();
     L.d_roff.release(); L.d_sizes.release(); L.d_invsizes.release(); L.d_lab16.release();
-    L.d_sizes16.release(); L.d_kinfo.release();
+    L.d_spack.release(); L.d_kinfo.release();
     delete h;
     return CA_OK;
 }

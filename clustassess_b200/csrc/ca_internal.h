@@ -90,7 +90,7 @@ struct Labels {
     std::vector<int64_t> h_roff;  // offset of partition p's range in d_cnt / d_rank
     bool identity = true;         // every partition's labels are already dense (rank == label - min)
     int32_t kmax = 0, kp = 0, mpad = 0;
-    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_invsizes, d_lab16, d_sizes16, d_kinfo;
+    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_invsizes, d_lab16, d_spack, d_kinfo;
     std::vector<int32_t> h_sizes;  // [m][kp]
 };
 
@@ -149,7 +149,7 @@ struct TileParams {
     const int32_t* perm;      // [m_slots][perm_stride] cluster-sorted cell ids, -1 = padding
     const int32_t* slot_of;   // [m] partition -> perm slot (or -1)
     const int32_t* sizes;     // [m][kp] cluster sizes
-    const uint16_t* sizes16;  // [m][kp] min(size, 65535)
+    const uint32_t* spack;    // [m][kp] min(size, 65535) << 16: the initial value of a table entry (size : count = 0)
     const int32_t* kinfo;     // [mpad] K_j | (1 << 30 if partition j has a cluster with >= 65535 cells), 0 beyond m
     const void* zeros;        // >= 256 KB of zero bytes: source of the bulk copy that clears the tables
     const uint16_t* crow;     // [m_slots][kp] row of a cluster inside its block

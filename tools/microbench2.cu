@@ -27,28 +27,34 @@ __device__ uint32_t make_addr(int pattern, int lane, int k, uint32_t seed) {
     }
 }
 
-template <int OP>  // 0 = red.shared.add, 1 = ld.shared.u32, 2 = ld.shared.u16, 3 = atom.shared.add (returns)
+template <int OP>  // 0 = red.shared.add 1 (SASS ATOMS.POPC.INC), 1 = ld.shared.u32, 2 = ld.shared.u16, 3 = atom.shared.add (returns),
+                   // 4 = red.shared.add of a register value (1 or 0x10000: two 16-bit counters per word)
 __global__ void __launch_bounds__(THREADS, 1) k_probe(uint32_t* out, int pattern, int active) {
     extern __shared__ uint32_t sh[];
-    for (int i = threadIdx.x; i < WORDS; i += blockDim.x) sh[i] = i;
+    for (int i = threadIdx.x; i < WORDS; i += blockDim.x) sh[i] = i & 0xffff;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     uint32_t a[8];
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(sh);
     for (int k = 0; k < 8; k++) a[k] = base + 4u * make_addr(pattern, lane, k, blockIdx.x * THREADS + threadIdx.x);
     uint32_t acc = 0;
+    const uint32_t val = (threadIdx.x * 2654435761u >> 13 & 1u) ? 0x10000u : 1u;
     if (lane < active) {
         for (int i = 0; i < ITERS; i++) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 if (OP == 0) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a[k]), "r"(1u) : "memory");
-                if (OP == 1) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a[k])); acc += v; }
-                if (OP == 2) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a[k])); acc += v; }
+                // the loaded value feeds the next address (table values are < 2^31, so the address never changes,
+                // but the compiler cannot know): 8 independent chains per thread x 32 warps keep the pipe full
+                if (OP == 1) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a[k]) : "memory"); a[k] ^= (v >> 31) << 2; }
+                if (OP == 2) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a[k]) : "memory"); a[k] ^= ((uint32_t)v >> 16) << 2; }
+                if (OP == 4) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a[k]), "r"(val) : "memory");
                 if (OP == 3) { uint32_t v; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(v) : "r"(a[k]), "r"(1u) : "memory"); acc += v; }
             }
         }
     }
     __syncthreads();
+    for (int k = 0; k < 8; k++) acc += a[k];
     for (int i = threadIdx.x; i < WORDS; i += blockDim.x) acc += sh[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
@@ -77,17 +83,19 @@ int main() {
     CK(cudaFuncSetAttribute(k_probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WORDS * 4));
     CK(cudaFuncSetAttribute(k_probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WORDS * 4));
     CK(cudaFuncSetAttribute(k_probe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WORDS * 4));
+    CK(cudaFuncSetAttribute(k_probe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WORDS * 4));
     const double warp_instr = (double)grid * (THREADS / 32) * ITERS * 8;
     auto cyc = [&](float ms) { return ms * 1e-3 * ghz * 1e9 * sms / warp_instr; };
     const char* pname[7] = {"conflict-free", "random words", "one word/warp", "8 tables x 4 same", "8 tables x 4 rand", "2 words/warp", "4 words/warp"};
-    const char* oname[4] = {"red.add", "lds.u32", "lds.u16", "atom.add"};
-    for (int op = 0; op < 4; op++)
+    const char* oname[5] = {"red.inc", "lds.u32", "lds.u16", "atom.add", "red.add"};
+    for (int op = 0; op < 5; op++)
         for (int pat = 0; pat < 7; pat++) {
             float ms = 0;
             if (op == 0) ms = time_it([&] { k_probe<0><<<grid, THREADS, WORDS * 4>>>(out, pat, 32); });
             if (op == 1) ms = time_it([&] { k_probe<1><<<grid, THREADS, WORDS * 4>>>(out, pat, 32); });
             if (op == 2) ms = time_it([&] { k_probe<2><<<grid, THREADS, WORDS * 4>>>(out, pat, 32); });
             if (op == 3) ms = time_it([&] { k_probe<3><<<grid, THREADS, WORDS * 4>>>(out, pat, 32); });
+            if (op == 4) ms = time_it([&] { k_probe<4><<<grid, THREADS, WORDS * 4>>>(out, pat, 32); });
             printf("%-9s %-18s : %6.2f\n", oname[op], pname[pat], cyc(ms));
         }
     for (int act : {1, 4, 8, 16}) {
