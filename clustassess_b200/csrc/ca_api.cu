@@ -158,8 +158,6 @@ int prepare_ranks(Labels& L) {
     CA_CUDA(cudaMemsetAsync(L.d_sizes.p, 0, (size_t)m * L.kp * 4, s));
     CA_TRY(launch_sizes(L.d_cnt.as<uint32_t>(), L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(), nullptr, nullptr, m,
                         (int32_t)max_range, L.kp, L.d_sizes.as<int32_t>(), s));
-    CA_TRY(L.d_invsizes.ensure((size_t)m * L.kp * 8));
-    CA_TRY(launch_invsizes(L.d_sizes.as<int32_t>(), (int64_t)m * L.kp, L.d_invsizes.as<double>(), s));
     L.h_sizes.assign((size_t)m * L.kp, 0);
     CA_CUDA(cudaMemcpyAsync(L.h_sizes.data(), L.d_sizes.p, (size_t)m * L.kp * 4, cudaMemcpyDeviceToHost, s));
     CA_CUDA(cudaStreamSynchronize(s));
@@ -210,7 +208,7 @@ static inline int owner_of(int32_t i, int32_t world) {
 }
 
 struct Workspace {
-    DevBuf perm, cstart, crow, items, parts, slot_of, w;
+    DevBuf perm, cstart, crow, items, parts, w, wu_prefix, qinfo;
 };
 static Workspace& ws() {
     static Workspace w;
@@ -240,9 +238,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     // ---- host planning ----------------------------------------------------------------------------
     auto t_plan0 = std::chrono::steady_clock::now();
     int32_t max_rows = 0;
-    const bool tile_engine = getenv("CA_ENGINE_V1") == nullptr;  // CA_ENGINE_V1=1 selects the first-generation row-block kernels
-    const int smem_bytes = tile_engine ? tile_smem_budget(L.kmax, &max_rows) : rowblock_smem_budget(L.kp, &max_rows);
-    const int32_t blk_cpt = tile_engine ? TL_CPT : RB_CPT, blk_cap = tile_engine ? TL_CAP : RB_CAP;
+    const int smem_bytes = tile_smem_budget(L.kmax, &max_rows);
     if (max_rows < 1) {
         set_error("%d clusters per partition need more shared memory per table row than one SM has", L.kmax);
         return CA_E_UNSUPPORTED;
@@ -255,26 +251,20 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
             if (owner_of(i, world) == rank) parts.push_back(i);
     }
     const int32_t nparts = (int32_t)parts.size();
-    std::vector<int32_t> h_slot_of(m, -1);
     std::vector<int32_t> h_cstart((size_t)std::max(nparts, 1) * L.kp, 0);
     std::vector<uint16_t> h_crow((size_t)std::max(nparts, 1) * L.kp, 0);
-    // 0 resident (phase-synchronous), 1 streaming (16-bit counters), 2 streaming (32-bit counters), 3 resident (pipelined)
-    constexpr int NK = 4;
-    std::vector<Item> items_k[NK];
-    const bool use_pipe = getenv("CA_NO_PIPELINE") == nullptr;
+    std::vector<Item> items;
     int64_t perm_stride = 4;
     {   // plan every owned partition; partitions are independent, so the host threads share them
         const int nthreads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, nparts}));
-        std::vector<std::vector<Item>> items_t[NK];
-        for (auto& v : items_t) v.resize(nthreads);
+        std::vector<std::vector<Item>> items_t(nthreads);
         std::vector<int64_t> stride_t(nthreads, 4);
         std::vector<int> rc_t(nthreads, CA_OK);
-        for (int32_t sl = 0; sl < nparts; sl++) h_slot_of[parts[sl]] = sl;
         auto work = [&](int tix) {
             PlanOut po;
             for (int32_t sl = tix; sl < nparts; sl += nthreads) {
                 const int32_t p = parts[sl];
-                int rc = plan_blocks(L.h_sizes.data() + (size_t)p * L.kp, L.h_k[p], blk_cpt, blk_cap, max_rows, po);
+                int rc = plan_blocks(L.h_sizes.data() + (size_t)p * L.kp, L.h_k[p], TL_CPT, TL_CAP, max_rows, po);
                 if (rc != CA_OK) { rc_t[tix] = rc; return; }
                 stride_t[tix] = std::max<int64_t>(stride_t[tix], (po.total_pos + 3) & ~3LL);
                 for (int32_t k = 0; k < L.h_k[p]; k++) {
@@ -286,15 +276,12 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                     it.m = p;
                     it.pos0 = po.pos0[t];
                     it.npos = po.npos[t];
-                    it.nrows = po.nrows[t];
+                    it.nrows = po.nrows[t] | (po.wide[t] ? (1 << 30) : 0);  // bit 30: 32-bit counters
                     it.jbeg = ref_only >= 0 ? 0 : p + 1;
                     it.jend = ref_only >= 0 ? m_partners : m;
                     it.sa = po.sa[t];
-                    it.pad_ = tile_engine ? po.wide[t] : 0;
-                    int kind = it.npos <= RB_CAP ? 0 : (po.wide[t] ? 2 : 1);
-                    if (tile_engine) kind = 0;  // one kernel serves every kind of item
-                    if (!tile_engine && kind == 0 && use_pipe && rowblock_pipe_buffers(L.kp, it.nrows, smem_bytes) >= 3) kind = 3;
-                    items_t[kind][tix].push_back(it);
+                    it.pad_ = sl;  // perm slot
+                    items_t[tix].push_back(it);
                 }
             }
         };
@@ -311,13 +298,34 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                 return rc_t[t];
             }
             perm_stride = std::max(perm_stride, stride_t[t]);
-            for (int k = 0; k < NK; k++) items_k[k].insert(items_k[k].end(), items_t[k][t].begin(), items_t[k][t].end());
+            items.insert(items.end(), items_t[t].begin(), items_t[t].end());
         }
     }
-    auto cost = [](const Item& a) { return (int64_t)a.npos * (a.jend - a.jbeg); };
-    auto by_cost = [&](const Item& a, const Item& b) { return cost(a) > cost(b); };
-    for (auto& v : items_k) std::stable_sort(v.begin(), v.end(), by_cost);
-    std::vector<double> h_w(L.mpad + RB_JW, 0.0);
+    // Work unit = (item, super-tile of TL_SUPER partners), numbered super-tile-major.  With the items sorted by
+    // their first partner (the long streaming items first among equals), the items that reach into super-tile s
+    // are a prefix of the list, so a work-unit number decodes with one prefix array.
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+        if (a.jbeg != b.jbeg) return a.jbeg < b.jbeg;
+        return a.npos > b.npos;
+    });
+    std::vector<int32_t> h_wu_prefix(1, 0);
+    {
+        int32_t jmax = 0;
+        for (const Item& it : items) jmax = std::max(jmax, it.jend);
+        const int32_t nsuper = (jmax + TL_SUPER - 1) / TL_SUPER;
+        size_t k = 0;
+        int64_t tot = 0;
+        for (int32_t sp = 0; sp < nsuper; sp++) {
+            while (k < items.size() && items[k].jbeg < (sp + 1) * TL_SUPER) k++;
+            tot += (int64_t)k;
+            if (tot > 0x7fffff00LL) {
+                set_error("too many work units (%lld)", (long long)tot);
+                return CA_E_UNSUPPORTED;
+            }
+            h_wu_prefix.push_back((int32_t)tot);
+        }
+    }
+    std::vector<double> h_w(L.mpad + 8, 0.0);
     double wsum = 0.0;
     const int32_t mw = ref_only >= 0 ? m_partners : m;
     for (int32_t p = 0; p < mw; p++) {
@@ -335,129 +343,61 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
 
     // ---- upload plan, sort ------------------------------------------------------------------------
     Workspace& W = ws();
-    size_t nitems = 0;
-    for (auto& v : items_k) nitems += v.size();
+    CA_TRY(W.wu_prefix.ensure(h_wu_prefix.size() * 4));
+    CA_TRY(W.qinfo.ensure((size_t)std::max(nparts, 1) * perm_stride * 2));
     CA_TRY(W.perm.ensure((size_t)std::max(nparts, 1) * perm_stride * 4));
     CA_TRY(W.cstart.ensure(h_cstart.size() * 4));
     CA_TRY(W.crow.ensure(h_crow.size() * 2));
-    CA_TRY(W.items.ensure(std::max<size_t>(nitems, 1) * sizeof(Item)));
+    CA_TRY(W.items.ensure(std::max<size_t>(items.size(), 1) * sizeof(Item)));
     CA_TRY(W.parts.ensure((size_t)std::max(nparts, 1) * 4));
-    CA_TRY(W.slot_of.ensure((size_t)m * 4));
     CA_TRY(W.w.ensure(h_w.size() * 8));
+    CA_CUDA(cudaMemcpyAsync(W.wu_prefix.p, h_wu_prefix.data(), h_wu_prefix.size() * 4, cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaMemcpyAsync(W.cstart.p, h_cstart.data(), h_cstart.size() * 4, cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaMemcpyAsync(W.crow.p, h_crow.data(), h_crow.size() * 2, cudaMemcpyHostToDevice, s));
     if (nparts) CA_CUDA(cudaMemcpyAsync(W.parts.p, parts.data(), (size_t)nparts * 4, cudaMemcpyHostToDevice, s));
-    CA_CUDA(cudaMemcpyAsync(W.slot_of.p, h_slot_of.data(), (size_t)m * 4, cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaMemcpyAsync(W.w.p, h_w.data(), h_w.size() * 8, cudaMemcpyHostToDevice, s));
-    Item* d_items = W.items.as<Item>();
-    {
-        size_t off = 0;
-        for (auto& v : items_k) {
-            if (!v.empty()) CA_CUDA(cudaMemcpyAsync(d_items + off, v.data(), v.size() * sizeof(Item), cudaMemcpyHostToDevice, s));
-            off += v.size();
-        }
-    }
+    if (!items.empty()) CA_CUDA(cudaMemcpyAsync(W.items.p, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaEventRecord(c.ev[3], s));
     CA_TRY(launch_sort(L.d_raw, n, L.d_min.as<int32_t>(), L.identity ? nullptr : L.d_rank.as<uint32_t>(),
                        L.d_roff.as<int64_t>(), W.cstart.as<int32_t>(), L.kp, W.parts.as<int32_t>(), nparts,
                        W.perm.as<int32_t>(), perm_stride, s));
     CA_CUDA(cudaEventRecord(c.ev[4], s));
 
-    // ---- row-block kernels ------------------------------------------------------------------------
-    RowBlockParams P;
-    P.lab16 = L.d_lab16.as<uint16_t>();
-    P.perm = W.perm.as<int32_t>();
-    P.slot_of = W.slot_of.as<int32_t>();
-    P.sizes = L.d_sizes.as<int32_t>();
-    P.invsizes = L.d_invsizes.as<double>();
+    // ---- the wave kernel ----------------------------------------------------------------------------
+    TileParams T;
+    T.lab16 = L.d_lab16.as<uint16_t>();
+    T.n = n;
+    T.perm = W.perm.as<int32_t>();
+    T.sizes = L.d_sizes.as<int32_t>();
+    T.spack = L.d_spack.as<uint32_t>();
+    T.kinfo = L.d_kinfo.as<int32_t>();
     {
         static DevBuf zeros;
         if (!zeros.p) {
             CA_TRY(zeros.ensure(256 * 1024));
             CA_CUDA(cudaMemsetAsync(zeros.p, 0, 256 * 1024, s));
         }
-        P.zeros = zeros.p;
+        T.zeros = zeros.p;
     }
-    P.crow = W.crow.as<uint16_t>();
-    P.w = W.w.as<double>();
-    P.items = d_items;
-    P.ecc = d_ecc;
-    P.sim = d_sim;
-    P.perm_stride = perm_stride;
-    P.m = m;
-    P.mpad = L.mpad;
-    P.kp = L.kp;
-    P.smem_bytes = smem_bytes;
-    P.inv_norm = inv_norm;
-    P.dbg = 0;
-    P.timeline = nullptr;
-#ifdef CA_ABLATE
-    if (const char* e = getenv("CA_ABLATE")) P.dbg = atoi(e);
-    static DevBuf tl;
-    const size_t tl_bytes = 256 * 16 * 10 * sizeof(long long);
-    if (getenv("CA_TIMELINE")) {
-        CA_TRY(tl.ensure(tl_bytes));
-        CA_CUDA(cudaMemsetAsync(tl.p, 0, tl_bytes, s));
-        P.timeline = tl.as<long long>();
-    }
-#endif
-    if (tile_engine) {
-        TileParams T;
-        T.lab16 = P.lab16;
-        T.perm = P.perm;
-        T.slot_of = P.slot_of;
-        T.sizes = P.sizes;
-        T.spack = L.d_spack.as<uint32_t>();
-        T.kinfo = L.d_kinfo.as<int32_t>();
-        T.zeros = P.zeros;
-        T.crow = P.crow;
-        T.w = P.w;
-        T.items = d_items;
-        T.ecc = d_ecc;
-        T.sim = d_sim;
-        T.perm_stride = perm_stride;
-        T.m = m;
-        T.mpad = L.mpad;
-        T.kp = L.kp;
-        T.smem_bytes = smem_bytes;
-        T.inv_norm = inv_norm;
-        CA_TRY(launch_tile(T, (int32_t)items_k[0].size(), s));  // items sorted by cost, longest first
-    } else if (d_ecc || d_sim) {
-        // the long streaming items first, then the resident blocks fill the machine behind them
-        const Item* base_k[NK];
-        {
-            size_t off = 0;
-            for (int k = 0; k < NK; k++) {
-                base_k[k] = d_items + off;
-                off += items_k[k].size();
-            }
-        }
-        for (int kind : {2, 1, 3, 0}) {
-            P.items = base_k[kind];
-            CA_TRY(launch_rowblock(P, (int32_t)items_k[kind].size(), kind, s));
-        }
-    }
+    T.crow = W.crow.as<uint16_t>();
+    T.w = W.w.as<double>();
+    T.items = W.items.as<Item>();
+    T.wu_prefix = W.wu_prefix.as<int32_t>();
+    T.qinfo = W.qinfo.as<uint32_t>();
+    T.nsuper = (int32_t)h_wu_prefix.size() - 1;
+    T.nwu = h_wu_prefix.back();
+    T.ecc = d_ecc;
+    T.sim = d_sim;
+    T.perm_stride = perm_stride;
+    T.m = m;
+    T.mpad = L.mpad;
+    T.kp = L.kp;
+    T.smem_bytes = smem_bytes;
+    T.inv_norm = inv_norm;
+    CA_TRY(launch_qinfo(T, W.parts.as<int32_t>(), nparts, s));
+    CA_TRY(launch_tile(T, s));
     CA_CUDA(cudaEventRecord(c.ev[5], s));
     CA_CUDA(cudaStreamSynchronize(s));
-#ifdef CA_ABLATE
-    if (P.timeline) {  // average section cycles per warp over the first 256 pipelined blocks
-        std::vector<long long> h(256 * 16 * 10);
-        CA_CUDA(cudaMemcpy(h.data(), P.timeline, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-        double sum[10] = {0}, nw = 0, gsum = 0;
-        for (size_t w = 0; w < 256 * 16; w++) {
-            if (h[w * 10 + 7] == 0) continue;
-            nw++;
-            gsum += (double)h[w * 10 + 8];
-            for (int k = 0; k < 10; k++) sum[k] += (double)h[w * 10 + k];
-        }
-        if (nw > 0) {
-            const char* nm[8] = {"labels", "wait_zero", "hist", "refill", "wait_hist", "wait_sizes", "gather", "total"};
-            fprintf(stderr, "[timeline] %d warps, avg partners %.1f, ring %.1f; cycles per warp-partner:", (int)nw, gsum / nw, sum[9] / nw);
-            for (int k = 0; k < 8; k++) fprintf(stderr, " %s=%.0f", nm[k], sum[k] / gsum);
-            fprintf(stderr, "\n");
-        }
-    }
-#endif
     float ms;
     CA_CUDA(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
     c.prof[0] = ms;
@@ -514,7 +454,7 @@ void ca_shutdown(void) {
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
     Workspace& W = ws();
-    W.perm.release(); W.cstart.release(); W.crow.release(); W.items.release(); W.parts.release(); W.slot_of.release(); W.w.release();
+    W.perm.release(); W.cstart.release(); W.crow.release(); W.items.release(); W.parts.release(); W.w.release(); W.wu_prefix.release(); W.qinfo.release();
     for (int i = 0; i < 8; i++)
         if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
     if (c.own_stream) { cudaStreamDestroy(c.own_stream); c.own_stream = nullptr; }
@@ -610,7 +550,7 @@ int ca_labels_destroy(ca_labels_t* h) {
     Labels& L = h->L;
     if (L.d_raw) cudaFree(L.d_raw);
     L.d_min.release(); L.d_max.release(); L.d_cnt.release(); L.d_rank.release(); L.d_kcount.release();
-    L.d_roff.release(); L.d_sizes.release(); L.d_invsizes.release(); L.d_lab16.release();
+    L.d_roff.release(); L.d_sizes.release(); L.d_lab16.release();
     L.d_spack.release(); L.d_kinfo.release();
     delete h;
     return CA_OK;

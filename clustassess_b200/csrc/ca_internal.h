@@ -50,24 +50,18 @@ struct DevBuf {
     template <typename T> T* as() { return static_cast<T*>(p); }
 };
 
-// ---- row-block engine geometry ----------------------------------------------------------------------
-// A thread owns CPT consecutive positions of a partition's cluster-sorted cell order; a block of
-// RB_THREADS threads owns RB_CAP positions ("resident" items keep their labels in registers).
-constexpr int RB_CPT = 4;
-constexpr int RB_THREADS = 512;
-constexpr int RB_CAP = RB_CPT * RB_THREADS;  // 2048 positions per resident block
-constexpr int RB_JW = 8;                     // partitions per label tile: 8 x uint16 = one 16-byte load
-constexpr int RB_MAX_ROWS = 255;
-
-struct Item {       // one unit of work of the row-block kernel: rows [..] x cells [pos0, pos0+npos) of partition m
-    int32_t m;      // partition whose cluster-sorted order / table rows this block owns
-    int32_t pos0;   // first padded position (multiple of RB_CPT) in perm[m]
-    int32_t npos;   // padded positions (multiple of RB_CPT); > RB_CAP => single-cluster streaming item
-    int32_t nrows;  // table rows (clusters) in this block
+// ---- work items -------------------------------------------------------------------------------------
+// A thread owns a quad (TL_CPT) of consecutive positions of a partition's cluster-sorted cell order; a block of
+// TL_THREADS threads owns up to TL_CAP positions.
+struct Item {       // a set of complete clusters of partition m: positions [pos0, pos0+npos) of its cluster-sorted order
+    int32_t m;      // partition whose table rows this item owns
+    int32_t pos0;   // first padded position (multiple of TL_CPT) in perm[slot]
+    int32_t npos;   // padded positions (multiple of TL_CPT); > TL_CAP => single-cluster streaming item
+    int32_t nrows;  // table rows (clusters); bit 30 = more than 65535 cells, 32-bit counters
     int32_t jbeg;   // partner partitions j in [jbeg, jend)
     int32_t jend;
     int32_t sa;     // cluster size when nrows == 1 (else 0)
-    int32_t pad_;   // tile engine: 1 = streaming item with more than 65535 cells (32-bit counters)
+    int32_t pad_;   // perm slot of partition m
 };
 
 // host planner (ca_plan.cpp)
@@ -84,18 +78,25 @@ struct Labels {
     int32_t m = 0;
     int32_t* d_raw = nullptr;  // M x N int32 (partition-major)
     bool ranked = false;    // min/max, ranks, compact sizes are valid
-    bool prepared = false;  // ... and the cell-major uint16 matrix
+    bool prepared = false;  // ... and the uint16 label matrix (super-tile-major, see lab16_index)
     // filled by prepare():
     std::vector<int32_t> h_min, h_max, h_k;
     std::vector<int64_t> h_roff;  // offset of partition p's range in d_cnt / d_rank
     bool identity = true;         // every partition's labels are already dense (rank == label - min)
     int32_t kmax = 0, kp = 0, mpad = 0;
-    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_invsizes, d_lab16, d_spack, d_kinfo;
+    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_lab16, d_spack, d_kinfo;
     std::vector<int32_t> h_sizes;  // [m][kp]
 };
 
 int prepare_ranks(Labels& L);
 int prepare_labels(Labels& L);
+
+// Compact labels live in a uint16 array laid out super-tile-major: the 16 partitions [16 t, 16 t + 16) of cell c
+// are the 32 contiguous bytes at element index (t * n + c) * 16.  All cells' labels for one super-tile are thus one
+// DENSE 32 n-byte slab (an L2 line holds 4 cells), which is what lets a whole super-tile stay L2-resident while
+// every owner partition sweeps over it; with a cell-major [n][mpad] layout the same sectors sit 2 mpad bytes apart,
+// each in its own 128-byte L2 line, and the effective footprint is four times larger than the cache.
+__host__ __device__ inline int64_t lab16_index(int64_t n, int64_t cell, int32_t p) { return ((int64_t)(p >> 4) * n + cell) * 16 + (p & 15); }
 
 // kernels' host launchers -----------------------------------------------------------------------------
 // ca_pack.cu
@@ -107,62 +108,41 @@ int launch_rank(const uint32_t* d_cnt, const int64_t* d_roff, const int32_t* d_m
                 uint32_t* d_rank, int32_t* d_kcount, cudaStream_t s);
 int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_min,
                  const int32_t* d_max, int32_t m, int32_t max_range, int32_t kp, int32_t* d_sizes, cudaStream_t s);
-int launch_invsizes(const int32_t* d_sizes, int64_t count, double* d_inv, cudaStream_t s);
 int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t mpad, const int32_t* d_min,
                              const uint32_t* d_rank, const int64_t* d_roff, uint16_t* d_lab16, cudaStream_t s);
 int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
                 const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
                 int64_t perm_stride, cudaStream_t s);
 
-// ca_rowblock.cu
-struct RowBlockParams {
-    const uint16_t* lab16;   // [n][mpad] compact labels, cell-major
-    const int32_t* perm;     // [m_slots][perm_stride] cluster-sorted cell ids, -1 = padding
-    const int32_t* slot_of;  // [m] partition -> perm slot (or -1)
-    const int32_t* sizes;    // [m][kp]
-    const double* invsizes;  // [m][kp] 1 / size (0 where the slot is unused)
-    const void* zeros;       // >= 256 KB of zero bytes: source of the bulk copy that clears the tables
-    const uint16_t* crow;    // [m_slots][kp] row of a cluster inside its block
-    const double* w;         // [m] weights
-    const Item* items;
-    double* ecc;             // [n] accumulated with atomics (may be null)
-    double* sim;             // [m*m] accumulated with atomics (may be null)
-    int64_t perm_stride;
-    int32_t m, mpad, kp;
-    int32_t smem_bytes;      // dynamic shared memory available to sizes + tables
-    double inv_norm;
-    long long* timeline;     // per-warp section cycle counters (-DCA_ABLATE build with CA_TIMELINE=1 only), else null
-    int32_t dbg;             // ablation switches, honoured only by the -DCA_ABLATE profiling build (tools/ablate.py)
-};
-// kind: 0 = resident items, 1 = streaming items with 16-bit counters, 2 = streaming items with 32-bit counters
-int launch_rowblock(const RowBlockParams& p, int32_t nitems, int kind, cudaStream_t s);
-int rowblock_smem_budget(int32_t kp, int32_t* max_rows_out);
-int rowblock_pipe_buffers(int32_t kp, int32_t nrows, int32_t smem_bytes);  // ring buffers the pipelined kernel gets (>= 3 to use it)
-
-// ca_tile.cu -- second-generation engine: 1024 threads x 4 cells, 8-partner phases, lanes mapped to partners
+// ca_tile.cu -- the all-pairs engine: persistent blocks of 1024 threads x 4 cells, work units of 16 partners
 constexpr int TL_CPT = 4;
 constexpr int TL_THREADS = 1024;
 constexpr int TL_CAP = TL_CPT * TL_THREADS;  // 4096 positions per resident block
 constexpr int TL_MAX_ROWS = 1024;
+constexpr int TL_SUPER = 16;                 // partners per work unit: one 32-byte label sector per cell
 struct TileParams {
-    const uint16_t* lab16;    // [n][mpad] compact labels, cell-major
+    const uint16_t* lab16;    // [mpad/16][n][16] compact labels, see lab16_index()
+    int64_t n;
     const int32_t* perm;      // [m_slots][perm_stride] cluster-sorted cell ids, -1 = padding
-    const int32_t* slot_of;   // [m] partition -> perm slot (or -1)
     const int32_t* sizes;     // [m][kp] cluster sizes
     const uint32_t* spack;    // [m][kp] min(size, 65535) << 16: the initial value of a table entry (size : count = 0)
     const int32_t* kinfo;     // [mpad] K_j | (1 << 30 if partition j has a cluster with >= 65535 cells), 0 beyond m
     const void* zeros;        // >= 256 KB of zero bytes: source of the bulk copy that clears the tables
     const uint16_t* crow;     // [m_slots][kp] row of a cluster inside its block
     const double* w;          // [mpad + 8] weights
-    const Item* items;
+    const Item* items;        // sorted by jbeg; nrows carries bit 30 = 32-bit counters, pad_ = perm slot
+    const int32_t* wu_prefix; // [nsuper + 1] work units before super-tile s (work unit = item x 16-partner super-tile)
+    uint32_t* qinfo;          // [m_slots][perm_stride / 4] x {row in block, cluster size} of every quad of positions
     double* ecc;              // [n] accumulated with atomics (may be null)
     double* sim;              // [m*m] accumulated with atomics (may be null)
     int64_t perm_stride;
     int32_t m, mpad, kp;
+    int32_t nsuper, nwu;      // super-tiles, work units
     int32_t smem_bytes;       // dynamic shared memory per block
     double inv_norm;
 };
-int launch_tile(const TileParams& p, int32_t nitems, cudaStream_t s);
+int launch_tile(const TileParams& p, cudaStream_t s);
+int launch_qinfo(const TileParams& p, const int32_t* d_parts, int32_t nparts, cudaStream_t s);
 int tile_smem_budget(int32_t kmax, int32_t* max_rows_out);
 
 // ca_pair.cu

@@ -7,7 +7,7 @@
 //   rank     -> dense rank of every used label (unused labels inside the range only produce all-zero
 //               table rows in the reference and never influence ECS, so the engine drops them)
 //   sizes    -> compact cluster sizes S[p][k]
-//   relabel_transpose -> cell-major uint16 label matrix lab16[n][mpad]
+//   relabel_transpose -> uint16 label matrix lab16[mpad/16][n][16]: 32 contiguous bytes per (cell, 16 partitions)
 //   sort     -> per-partition stable counting sort: perm[p] lists the cells grouped by cluster, every
 //               cluster at the padded start position chosen by the host planner (ca_plan.cpp)
 // All kernels are HBM-bound streaming passes over the M x N int32 input (coalesced loads), a few
@@ -179,23 +179,8 @@ int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d
     return CA_OK;
 }
 
-__global__ void invsizes_kernel(const int32_t* __restrict__ sizes, int64_t count, double* __restrict__ inv) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) {
-        int32_t s = sizes[i];
-        inv[i] = s > 0 ? 1.0 / (double)s : 0.0;  // correctly rounded reciprocal, once per cluster
-    }
-}
-
-int launch_invsizes(const int32_t* d_sizes, int64_t count, double* d_inv, cudaStream_t s) {
-    if (count <= 0) return CA_OK;
-    invsizes_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_sizes, count, d_inv);
-    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
-    return CA_OK;
-}
-
 // ------------------------------------------------------------------------------------------------
-// relabel + transpose: raw int32 [m][n] (partition-major)  ->  lab16 uint16 [n][mpad] (cell-major)
+// relabel + transpose: raw int32 [m][n] (partition-major)  ->  lab16 uint16 [mpad/16][n][16] (super-tile-major, lab16_index)
 // A block moves a 32-partition x 128-cell tile through shared memory: coalesced 4-byte reads along n,
 // 32-byte writes along the partition axis.
 // ------------------------------------------------------------------------------------------------
@@ -240,7 +225,7 @@ __global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* _
             uint32_t lo = tile[half * 16 + 2 * q][cell], hi = tile[half * 16 + 2 * q + 1][cell];
             wds[q] = lo | (hi << 16);
         }
-        uint4* dst = reinterpret_cast<uint4*>(lab16 + c * mpad + p0 + half * 16);
+        uint4* dst = reinterpret_cast<uint4*>(lab16 + lab16_index(n, c, p0 + half * 16));
         dst[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
         dst[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
     }

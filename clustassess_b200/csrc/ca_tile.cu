@@ -32,6 +32,8 @@
 //
 // The division is T * r with r = 1/max from rcp.approx.ftz.f64 + one Newton step (relative error < 1e-13);
 // the batched path has to meet 1e-9 absolute, the per-pair entry points (ca_pair.cu) keep the IEEE division.
+#include <algorithm>
+
 #include "ca_internal.h"
 
 namespace ca {
@@ -43,10 +45,13 @@ static_assert(TL_CPT == 4, "a thread owns one quad of cells");
 
 // shared-memory map (byte offsets from the dynamic shared base)
 static constexpr int SM_MBAR = 0;       // two mbarriers (one per buffer): tables initialised + meta published
-static constexpr int SM_META = 16;      // two Meta records of 128 bytes
-static constexpr int META_J0 = 0, META_G0 = 4, META_CNT = 8, META_TB = 16, META_RB = 48, META_KK = 80;
-static constexpr int SM_SIMACC = 272;   // [2][8] double: sum of ECS over the block's cells, per buffer and partner
-static constexpr int SM_DYN = 512;      // two table buffers
+static constexpr int SM_META = 16;      // two Meta records
+static constexpr int META_BYTES = 160;
+static constexpr int META_J0 = 0, META_G0 = 4, META_CNT = 8, META_FIRST = 12, META_M = 16, META_POS0 = 20, META_NPOS = 24,
+                     META_NROWS = 28, META_SA = 32, META_SLOT = 36, META_JHI = 40, META_TB = 64, META_RB = 96, META_KK = 128;
+static constexpr int SM_SIMACC = 336;   // [2][8] double: sum of ECS over the block's cells, per buffer and partner
+static constexpr int SM_PLAN = 464;     // warp 0's Planner (26 words) and, at +112, K_j | flags of the super-tile's 16 partners
+static constexpr int SM_DYN = 640;      // two table buffers
 static constexpr uint32_t KK_BIG = 1u << 30;  // partner has a cluster with >= 65535 cells
 
 // ---- shared-space accessors ---------------------------------------------------------------------------------
@@ -105,45 +110,212 @@ __device__ __forceinline__ double ecs_of(uint32_t count, uint32_t sa, uint32_t s
     return (double)count * r;
 }
 
-template <int JT>
-__device__ __forceinline__ uint32_t label_of(const uint4& v) {
-    const uint32_t w = (JT >> 1) == 0 ? v.x : (JT >> 1) == 1 ? v.y : (JT >> 1) == 2 ? v.z : v.w;
-    return (JT & 1) ? (w >> 16) : (w & 0xffffu);
-}
-
-// labels of the 8 partners [j0, j0+8) for a quad of cells: one 16-byte load per cell
-__device__ __forceinline__ void load_quad(const uint16_t* __restrict__ lab16j, int mpad, int4 cell, uint4 (&L)[4]) {
+// labels of the 8 partners [j0, j0+8) for a quad of cells: one 16-byte load per cell (lab16j = lab16 + lab16_index(n, 0, j0))
+__device__ __forceinline__ void load_quad(const uint16_t* __restrict__ lab16j, int4 cell, uint4 (&L)[4]) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    L[0] = cell.x >= 0 ? ldg_u4(lab16j + (int64_t)cell.x * mpad) : z;
-    L[1] = cell.y >= 0 ? ldg_u4(lab16j + (int64_t)cell.y * mpad) : z;
-    L[2] = cell.z >= 0 ? ldg_u4(lab16j + (int64_t)cell.z * mpad) : z;
-    L[3] = cell.w >= 0 ? ldg_u4(lab16j + (int64_t)cell.w * mpad) : z;
+    L[0] = cell.x >= 0 ? ldg_u4(lab16j + (int64_t)cell.x * 16) : z;
+    L[1] = cell.y >= 0 ? ldg_u4(lab16j + (int64_t)cell.y * 16) : z;
+    L[2] = cell.z >= 0 ? ldg_u4(lab16j + (int64_t)cell.z * 16) : z;
+    L[3] = cell.w >= 0 ? ldg_u4(lab16j + (int64_t)cell.w * 16) : z;
 }
 
-// ---- phase planning (warp 0) -----------------------------------------------------------------------------------
-struct Planner {    // cursor of the next phase to plan; lives in warp 0's registers
-    int j0, g0;     // tile and first tile slot
-    int kreg;       // lanes 0..7: K_j | flags of tile j0's partners
-    int knext;      // ... of tile j0 + 8
+struct Phase {
+    int j0, g0, cnt;  // partners [j0+g0, j0+g0+cnt) of the 8-partner tile at j0
 };
 
+// ---- histogram / gather of one phase for a quad of cells -------------------------------------------------------
+// labels of tile slot jt (block-uniform) for the quad: a uniform switch picks the register, PRMT the half
+__device__ __forceinline__ void pick_labels(const uint4 (&L)[4], int jt, uint32_t (&lab)[4]) {
+    uint32_t w[4];
+    switch (jt >> 1) {
+        case 0: w[0] = L[0].x; w[1] = L[1].x; w[2] = L[2].x; w[3] = L[3].x; break;
+        case 1: w[0] = L[0].y; w[1] = L[1].y; w[2] = L[2].y; w[3] = L[3].y; break;
+        case 2: w[0] = L[0].z; w[1] = L[1].z; w[2] = L[2].z; w[3] = L[3].z; break;
+        default: w[0] = L[0].w; w[1] = L[1].w; w[2] = L[2].w; w[3] = L[3].w; break;
+    }
+    const uint32_t sel = (jt & 1) ? 0x4432u : 0x4410u;
+#pragma unroll
+    for (int c = 0; c < 4; c++) lab[c] = __byte_perm(w[c], 0u, sel);
+}
+
+__device__ __forceinline__ void hist_quad(uint32_t meta, const Phase ph, const uint4 (&L)[4], uint32_t rowidx, int nvalid) {
+#pragma unroll 2
+    for (int q = 0; q < ph.cnt; q++) {
+        uint32_t lab[4];
+        pick_labels(L, ph.g0 + q, lab);
+        const uint32_t rb = lds_u32(meta + META_TB + q * 4) + rowidx * lds_u32(meta + META_RB + q * 4);
+        if (nvalid == 4) {  // all but the last quad of a cluster
+#pragma unroll
+            for (int c = 0; c < 4; c++) red_inc(rb + lab[c] * 4u);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (c < nvalid) red_inc(rb + lab[c] * 4u);
+        }
+    }
+}
+
+template <bool WIDE, bool WANT_SIM>
+__device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, const uint4 (&L)[4],
+                                            uint32_t rowidx, uint32_t sa, int nvalid, int lane, double (&acc)[4]) {
+#pragma unroll 1
+    for (int q = 0; q < ph.cnt; q++) {
+        const int jt = ph.g0 + q;
+        uint32_t lab[4];
+        pick_labels(L, jt, lab);
+        const uint32_t rb = lds_u32(meta + META_TB + q * 4) + rowidx * lds_u32(meta + META_RB + q * 4);
+        const uint32_t kk = lds_u32(meta + META_KK + q * 4);
+        const double wj = __ldg(P.w + ph.j0 + jt);
+        const int32_t* szg = P.sizes + (int64_t)(ph.j0 + jt) * P.kp;
+        double es = 0.0;
+        auto one = [&](int c, bool lookup) {
+            const uint32_t e = lds_u32(rb + lab[c] * 4u);
+            uint32_t count, sb;
+            if (WIDE) {
+                count = e;
+                sb = (uint32_t)__ldg(szg + lab[c]);
+            } else {
+                count = e & 0xffffu;
+                sb = e >> 16;
+                if (lookup && sb == 0xffffu) sb = (uint32_t)__ldg(szg + lab[c]);
+            }
+            const double v = ecs_of(count, sa, sb);
+            acc[c] = fma(v, wj, acc[c]);
+            if (WANT_SIM) es += v;
+        };
+        if (nvalid == 4 && !(kk & KK_BIG)) {  // the common case: a full quad, no partner cluster beyond 16 bits
+#pragma unroll
+            for (int c = 0; c < 4; c++) one(c, false);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c < nvalid) one(c, true);
+        }
+        if (WANT_SIM) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
+            if (lane == 0 && es != 0.0) red_add_f64(simacc + q * 8u, es);
+        }
+    }
+}
+
+// the per-partner ECS sums of a finished phase go to the ECS matrix (called by 8 threads after a block barrier)
+__device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, const Phase ph, int m, int t) {
+    if (m < 0) return;
+    if (t < ph.cnt) {
+        const double v = lds_f64(simacc + t * 8u);
+        if (v != 0.0) atomicAdd(P.sim + (int64_t)m * P.m + (ph.j0 + ph.g0 + t), v);
+        sts_f64(simacc + t * 8u, 0.0);
+    }
+}
+
+// ---- work units and phase planning (warp 0) -------------------------------------------------------------------
+// Work unit (WU) = (item, super-tile of SUPER partners).  WUs are numbered super-tile-major: WU w belongs to the
+// super-tile s with wu_prefix[s] <= w < wu_prefix[s+1] and to item w - wu_prefix[s]; the items are sorted by their
+// first partner, so the items that have partners inside super-tile s are a PREFIX of the item list.  Block b of
+// the persistent grid takes WUs b, b + grid, b + 2 grid, ...: all SMs sweep the partner axis together, so the label
+// sectors of the current super-tile (32 bytes per cell) are fetched from HBM once and then served by L2 to every
+// owner partition -- instead of one random HBM sector read per (cell, tile, owner), which is what bounds a
+// block-per-item schedule (measured: 42 G random sectors/s, tools/gatherbench.cu).
+static constexpr int SUPER = TL_SUPER;
+static constexpr uint32_t NROWS_WIDE = 1u << 30;  // Item::nrows flag: more than 65535 cells, 32-bit counters
+
+struct Planner {          // parked in shared memory between warp 0's planning steps (all values warp-uniform)
+    int w;                // current WU
+    int s;                // its super-tile
+    int wend;             // wu_prefix[s + 1]
+    Item it;              // its item
+    int jhi;              // partners of this WU: [.., jhi)
+    int j0, g0;           // cursor: tile and first tile slot of the next phase to plan
+    int first;            // the next phase is the first of its WU
+    Item nit;             // item of the NEXT WU of this block (loaded one WU ahead), nw/ns/nwend its ids
+    int nw, ns, nwend;
+};
+
+// ids of WU w (w ascending over calls): advance the super-tile while w is beyond it
+__device__ __forceinline__ void locate_wu(const TileParams& P, int w, int& s, int& wend) {
+    while (w >= wend && s + 1 < P.nsuper) {
+        s++;
+        wend = __ldg(P.wu_prefix + s + 1);
+    }
+}
+__device__ __forceinline__ Item load_item(const TileParams& P, int w, int s) {
+    const int4* q = reinterpret_cast<const int4*>(P.items + (w - __ldg(P.wu_prefix + s)));
+    const int4 a = __ldg(q), b = __ldg(q + 1);
+    Item it;
+    it.m = a.x; it.pos0 = a.y; it.npos = a.z; it.nrows = a.w;
+    it.jbeg = b.x; it.jend = b.y; it.sa = b.z; it.pad_ = b.w;
+    return it;
+}
+// make the prefetched WU current (or mark the end) and start loading the one after it
+__device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int lane, uint32_t sbase) {
+    pl.w = pl.nw;
+    pl.s = pl.ns;
+    pl.wend = pl.nwend;
+    pl.it = pl.nit;
+    if (pl.w < P.nwu) {
+        const int slo = pl.s * SUPER;
+        const int jlo = max(pl.it.jbeg, slo);
+        pl.jhi = min(pl.it.jend, slo + SUPER);
+        pl.j0 = jlo & ~7;
+        pl.g0 = jlo - pl.j0;
+        pl.first = 1;
+        if (lane < SUPER) sts_u32(sbase + SM_PLAN + 112 + lane * 4, (uint32_t)__ldg(P.kinfo + slo + lane));
+        __syncwarp();
+        pl.nw = pl.w + (int)gridDim.x;
+        if (pl.nw < P.nwu) {
+            locate_wu(P, pl.nw, pl.ns, pl.nwend);
+            pl.nit = load_item(P, pl.nw, pl.ns);
+        }
+    }
+}
+#define CA_PLANNER_FIELDS(X) \
+    X(0, w) X(1, s) X(2, wend) X(3, it.m) X(4, it.pos0) X(5, it.npos) X(6, it.nrows) X(7, it.jbeg) X(8, it.jend) X(9, it.sa) \
+    X(10, it.pad_) X(11, jhi) X(12, j0) X(13, g0) X(14, first) X(15, nit.m) X(16, nit.pos0) X(17, nit.npos) X(18, nit.nrows) \
+    X(19, nit.jbeg) X(20, nit.jend) X(21, nit.sa) X(22, nit.pad_) X(23, nw) X(24, ns) X(25, nwend)
+__device__ __forceinline__ void planner_load(Planner& pl, uint32_t sbase) {
+#define X(i, f) pl.f = (int)lds_u32(sbase + SM_PLAN + (i) * 4);
+    CA_PLANNER_FIELDS(X)
+#undef X
+}
+__device__ __forceinline__ void planner_store(const Planner& pl, uint32_t sbase, int lane) {
+    if (lane == 0) {
+#define X(i, f) sts_u32(sbase + SM_PLAN + (i) * 4, (uint32_t)pl.f);
+        CA_PLANNER_FIELDS(X)
+#undef X
+    }
+    __syncwarp();
+}
+static_assert(sizeof(Planner) <= 112, "Planner must fit its shared-memory slot");
+__device__ __forceinline__ void planner_init(const TileParams& P, Planner& pl, int lane, uint32_t sbase) {
+    pl.nw = (int)blockIdx.x;
+    pl.ns = 0;
+    pl.nwend = __ldg(P.wu_prefix + 1);
+    if (pl.nw < P.nwu) {
+        locate_wu(P, pl.nw, pl.ns, pl.nwend);
+        pl.nit = load_item(P, pl.nw, pl.ns);
+    }
+    advance_wu(P, pl, lane, sbase);
+}
+
 // Plans the phase at the cursor into buffer `buf`: how many partners of the tile fit (R rows of K_j entries each,
-// K_j rounded to 4), their table addresses, and the bulk copies that initialise them.  Past the last partner it
-// publishes cnt = 0.  Everything written here is published by the arrive on the buffer's mbarrier.
-template <bool WIDE>
+// K_j rounded to 4), their table addresses, the WU's item, and the bulk copies that initialise the tables.  After
+// the last WU it publishes cnt = 0.  Everything written here is published by the arrive on the buffer's mbarrier.
 __device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, uint32_t buf, uint32_t bufaddr, int half, int lane,
-                                           Planner& pl, int jbeg, int jend, int R) {
-    const uint32_t meta = sbase + SM_META + buf * 128u, bar = sbase + SM_MBAR + buf * 8u;
-    if (pl.j0 >= jend) {
+                                           Planner& pl) {
+    const uint32_t meta = sbase + SM_META + buf * META_BYTES, bar = sbase + SM_MBAR + buf * 8u;
+    if (pl.w >= P.nwu) {
         if (lane == 0) {
             sts_u32(meta + META_CNT, 0u);
             mbar_arrive(bar);
         }
         return;
     }
-    const int thi = min(8, jend - pl.j0);
+    const bool wide = (pl.it.nrows & NROWS_WIDE) != 0;
+    const int R = pl.it.npos <= CAP ? (int)(pl.it.nrows & 0xffff) : 1;
+    const int thi = min(8, pl.jhi - pl.j0);
     const int q = pl.g0 + lane;                                 // tile slot served by meta entry `lane`
-    const uint32_t kk = (uint32_t)__shfl_sync(FULL, pl.kreg, q & 7);
+    const uint32_t kk = lds_u32(sbase + SM_PLAN + 112 + ((((uint32_t)pl.j0 & (SUPER - 1)) + q) & (SUPER - 1)) * 4);
     const bool ok = lane < 8 && q < thi;
     const uint32_t rowb = ok ? (((kk & 0xffffu) + 3u) & ~3u) * 4u : 0u;  // bytes of one table row
     const uint32_t tbytes = rowb * (uint32_t)R;
@@ -167,15 +339,23 @@ __device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, 
         sts_u32(meta + META_J0, (uint32_t)pl.j0);
         sts_u32(meta + META_G0, (uint32_t)pl.g0);
         sts_u32(meta + META_CNT, (uint32_t)cnt);
+        sts_u32(meta + META_FIRST, (uint32_t)pl.first);
+        sts_u32(meta + META_M, (uint32_t)pl.it.m);
+        sts_u32(meta + META_POS0, (uint32_t)pl.it.pos0);
+        sts_u32(meta + META_NPOS, (uint32_t)pl.it.npos);
+        sts_u32(meta + META_NROWS, (uint32_t)pl.it.nrows);
+        sts_u32(meta + META_SA, (uint32_t)pl.it.sa);
+        sts_u32(meta + META_SLOT, (uint32_t)pl.it.pad_);
+        sts_u32(meta + META_JHI, (uint32_t)pl.jhi);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the block's generic accesses before the async writes
     __syncwarp();
     if (lane == 0) {
         mbar_expect_tx(bar, ttot);
-        if (WIDE) bulk_g2s(bufaddr, P.zeros, ttot, bar);
+        if (wide) bulk_g2s(bufaddr, P.zeros, ttot, bar);
     }
     __syncwarp();
-    if (!WIDE) {
+    if (!wide) {
         for (int t = 0; t < cnt; t++) {  // partner t: R row copies, a lane each
             const uint32_t tbt = __shfl_sync(FULL, tb, t), rbt = __shfl_sync(FULL, rowb, t);
             const uint32_t* src = P.spack + (int64_t)(pl.j0 + pl.g0 + t) * P.kp;
@@ -183,134 +363,28 @@ __device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, 
         }
     }
     // advance the cursor
+    pl.first = 0;
     pl.g0 += cnt;
     if (pl.g0 >= thi) {
         pl.j0 += 8;
         pl.g0 = 0;
-        pl.kreg = pl.knext;
-        pl.knext = (lane < 8 && pl.j0 + 8 < jend) ? __ldg(P.kinfo + pl.j0 + 8 + lane) : 0;
-    }
-}
-
-__device__ __forceinline__ void planner_init(const TileParams& P, Planner& pl, int jbeg, int jend, int lane) {
-    pl.j0 = jbeg & ~7;
-    pl.g0 = jbeg - pl.j0;
-    pl.kreg = lane < 8 ? __ldg(P.kinfo + pl.j0 + lane) : 0;
-    pl.knext = (lane < 8 && pl.j0 + 8 < jend) ? __ldg(P.kinfo + pl.j0 + 8 + lane) : 0;
-}
-
-struct Phase {
-    int j0, g0, cnt;
-};
-
-// ---- per-slot histogram / gather for a quad (tile slot JT is a compile-time constant so that the label comes
-//      straight out of its register; slots outside the phase are skipped by a block-uniform branch) -------------
-template <int JT>
-__device__ __forceinline__ void hist_slot(uint32_t meta, const Phase ph, const uint4 (&L)[4], uint32_t rowidx, int nvalid) {
-    if (JT < ph.g0 || JT >= ph.g0 + ph.cnt) return;
-    const int q = JT - ph.g0;
-    const uint32_t rb = lds_u32(meta + META_TB + q * 4) + rowidx * lds_u32(meta + META_RB + q * 4);
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-        if (c < nvalid) red_inc(rb + label_of<JT>(L[c]) * 4u);
-}
-__device__ __forceinline__ void hist_quad(uint32_t meta, const Phase ph, const uint4 (&L)[4], uint32_t rowidx, int nvalid) {
-    hist_slot<0>(meta, ph, L, rowidx, nvalid);
-    hist_slot<1>(meta, ph, L, rowidx, nvalid);
-    hist_slot<2>(meta, ph, L, rowidx, nvalid);
-    hist_slot<3>(meta, ph, L, rowidx, nvalid);
-    hist_slot<4>(meta, ph, L, rowidx, nvalid);
-    hist_slot<5>(meta, ph, L, rowidx, nvalid);
-    hist_slot<6>(meta, ph, L, rowidx, nvalid);
-    hist_slot<7>(meta, ph, L, rowidx, nvalid);
-}
-
-template <int JT, bool WIDE, bool WANT_SIM>
-__device__ __forceinline__ void gather_slot(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, const uint4 (&L)[4],
-                                            uint32_t rowidx, uint32_t sa, int nvalid, int lane, double (&acc)[4]) {
-    if (JT < ph.g0 || JT >= ph.g0 + ph.cnt) return;
-    const int q = JT - ph.g0;
-    const uint32_t rb = lds_u32(meta + META_TB + q * 4) + rowidx * lds_u32(meta + META_RB + q * 4);
-    const uint32_t kk = lds_u32(meta + META_KK + q * 4);
-    const double wj = __ldg(P.w + ph.j0 + JT);
-    const int32_t* szg = P.sizes + (int64_t)(ph.j0 + JT) * P.kp;
-    double es = 0.0;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        if (c < nvalid) {
-            const uint32_t lab = label_of<JT>(L[c]);
-            const uint32_t e = lds_u32(rb + lab * 4u);
-            uint32_t count, sb;
-            if (WIDE) {
-                count = e;
-                sb = (uint32_t)__ldg(szg + lab);
-            } else {
-                count = e & 0xffffu;
-                sb = e >> 16;
-                if ((kk & KK_BIG) && sb == 0xffffu) sb = (uint32_t)__ldg(szg + lab);
-            }
-            const double v = ecs_of(count, sa, sb);
-            acc[c] = fma(v, wj, acc[c]);
-            if (WANT_SIM) es += v;
-        }
-    }
-    if (WANT_SIM) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
-        if (lane == 0 && es != 0.0) red_add_f64(simacc + q * 8u, es);
-    }
-}
-template <bool WIDE, bool WANT_SIM>
-__device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, const uint4 (&L)[4],
-                                            uint32_t rowidx, uint32_t sa, int nvalid, int lane, double (&acc)[4]) {
-    gather_slot<0, WIDE, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
-    gather_slot<1, WIDE, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
-    gather_slot<2, WIDE, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
-    gather_slot<3, WIDE, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
-    gather_slot<4, WIDE, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
-    gather_slot<5, WIDE, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
-    gather_slot<6, WIDE, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
-    gather_slot<7, WIDE, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
-}
-
-// the per-partner ECS sums of a finished phase go to the ECS matrix (called by 8 threads after a block barrier)
-__device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, const Phase ph, int m, int t) {
-    if (t < ph.cnt) {
-        const double v = lds_f64(simacc + t * 8u);
-        if (v != 0.0) atomicAdd(P.sim + (int64_t)m * P.m + (ph.j0 + ph.g0 + t), v);
-        sts_f64(simacc + t * 8u, 0.0);
+        if (pl.j0 >= pl.jhi) advance_wu(P, pl, lane, sbase);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One work item.  RESIDENT: <= CAP positions, R >= 1 complete clusters, accumulators in registers over all
-// partners.  Otherwise ONE cluster with more than CAP cells, streamed in chunks of CAP positions in both passes.
+// The persistent kernel: one block per SM walks its work units; the phases of consecutive WUs form one stream
+// (the fill of the next WU's first phase is in flight during the last gather of the current one).
+// A WU of a RESIDENT item (<= CAP positions, R >= 1 complete clusters) keeps the labels of its cells in registers
+// between the histogram and the gather and adds its per-cell sums to ecc once; a WU of a larger cluster streams
+// the cells in chunks of CAP positions in both passes and adds to ecc per phase.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool RESIDENT, bool WIDE, bool WANT_ECC, bool WANT_SIM>
-__device__ __forceinline__ void run_item(const TileParams& P, const Item it, unsigned char* smem) {
+template <bool WANT_ECC, bool WANT_SIM>
+__global__ void __launch_bounds__(NT, 1) wave_kernel(const TileParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m = it.m, R = RESIDENT ? it.nrows : 1;
-    const int jbeg = it.jbeg, jend = it.jend;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const int half = ((P.smem_bytes - SM_DYN) / 2) & ~127;
-    const int slot = P.slot_of[m];
-    const int32_t* perm = P.perm + (int64_t)slot * P.perm_stride + it.pos0;
-    const int mpad = P.mpad, npos = it.npos;
-    const double wscale = P.w[m] * P.inv_norm;
-
-    int4 cell = make_int4(-1, -1, -1, -1);
-    int nvalid = 0;
-    uint32_t rowidx = 0, sa = (uint32_t)it.sa;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    if (RESIDENT) {
-        if (tid * 4 < npos) cell = __ldg(reinterpret_cast<const int4*>(perm + tid * 4));
-        nvalid = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);
-        if (R > 1 && cell.x >= 0) {
-            const int a = (int)__ldg(P.lab16 + (int64_t)cell.x * mpad + m);
-            rowidx = (uint32_t)__ldg(P.crow + (int64_t)slot * P.kp + a);
-            sa = (uint32_t)__ldg(P.sizes + (int64_t)m * P.kp + a);
-        }
-    }
     if (tid == 0) {
         mbar_init(sbase + SM_MBAR, 1);
         mbar_init(sbase + SM_MBAR + 8, 1);
@@ -318,96 +392,129 @@ __device__ __forceinline__ void run_item(const TileParams& P, const Item it, uns
     }
     if (tid < 16) sts_f64(sbase + SM_SIMACC + tid * 8u, 0.0);
     __syncthreads();
-    Planner pl;
     if (warp == 0) {
-        planner_init(P, pl, jbeg, jend, lane);
-        plan_phase<WIDE>(P, sbase, 0u, sbase + SM_DYN, half, lane, pl, jbeg, jend, R);
+        Planner pl;
+        planner_init(P, pl, lane, sbase);
+        plan_phase(P, sbase, 0u, sbase + SM_DYN, half, lane, pl);
+        planner_store(pl, sbase, lane);
     }
 
-    uint4 L[4];
+    // the current WU, as seen by every thread (everything else is re-read from the phase's meta record)
+    int m = -1;
+    bool resident = true;
+    int4 cell = make_int4(-1, -1, -1, -1);
+    int nvalid = 0;
+    uint32_t rowidx = 0, sa = 0;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    uint4 L[4];  // labels of the current tile for this thread's quad
     int cur_j0 = -1;
     Phase prev;
     prev.j0 = prev.g0 = prev.cnt = 0;
+    int prev_m = -1;
+
+    auto flush_acc = [&]() {
+        if (WANT_ECC && resident && m >= 0) {
+            const double wscale = __ldg(P.w + m) * P.inv_norm;
+            if (cell.x >= 0) atomicAdd(P.ecc + cell.x, acc[0] * wscale);
+            if (cell.y >= 0) atomicAdd(P.ecc + cell.y, acc[1] * wscale);
+            if (cell.z >= 0) atomicAdd(P.ecc + cell.z, acc[2] * wscale);
+            if (cell.w >= 0) atomicAdd(P.ecc + cell.w, acc[3] * wscale);
+        }
+    };
+
     uint32_t p = 0;
     for (;; p++) {
         const uint32_t b = p & 1u;
-        const uint32_t meta = sbase + SM_META + b * 128u, simacc = sbase + SM_SIMACC + b * 64u;
+        const uint32_t meta = sbase + SM_META + b * META_BYTES, simacc = sbase + SM_SIMACC + b * 64u;
         mbar_wait(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);  // buffer b initialised, meta of phase p published
         Phase ph;
         ph.cnt = (int)lds_u32(meta + META_CNT);
         if (ph.cnt == 0) break;
         ph.j0 = (int)lds_u32(meta + META_J0);
         ph.g0 = (int)lds_u32(meta + META_G0);
-        // ---- histogram ----
-        if (RESIDENT) {
-            if (ph.j0 != cur_j0) {
-                cur_j0 = ph.j0;
-                load_quad(P.lab16 + ph.j0, mpad, cell, L);
-                if (ph.j0 + 8 < jend) {  // ask L2 for the next tile's sectors now; its loads then hit
-                    const uint16_t* ln = P.lab16 + ph.j0 + 8;
-                    if (cell.x >= 0) prefetch_l2(ln + (int64_t)cell.x * mpad);
-                    if (cell.y >= 0) prefetch_l2(ln + (int64_t)cell.y * mpad);
-                    if (cell.z >= 0) prefetch_l2(ln + (int64_t)cell.z * mpad);
-                    if (cell.w >= 0) prefetch_l2(ln + (int64_t)cell.w * mpad);
+        if (lds_u32(meta + META_FIRST)) {  // a new work unit: retire the old one, pick up the new item
+            flush_acc();
+            m = (int)lds_u32(meta + META_M);
+            const int npos = (int)lds_u32(meta + META_NPOS);
+            resident = npos <= CAP;
+            const int64_t off = (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
+            const int32_t* perm = P.perm + off;
+            sa = lds_u32(meta + META_SA);
+            rowidx = 0;
+            cur_j0 = -1;
+            if (resident) {
+                cell = make_int4(-1, -1, -1, -1);
+                uint2 qi = make_uint2(0u, sa);
+                if (tid * 4 < npos) {
+                    cell = __ldg(reinterpret_cast<const int4*>(perm + tid * 4));
+                    qi = __ldg(reinterpret_cast<const uint2*>(P.qinfo) + (off >> 2) + tid);
                 }
+                nvalid = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);
+                rowidx = qi.x;
+                sa = qi.y;
+                acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+            }
+        }
+        // ---- histogram ----
+        if (resident) {
+            if (ph.j0 != cur_j0) {  // an L2 hit: the super-tile's sectors were fetched by the first block that needed them
+                cur_j0 = ph.j0;
+                load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), cell, L);
             }
             hist_quad(meta, ph, L, rowidx, nvalid);
         } else {
+            const int npos = (int)lds_u32(meta + META_NPOS);
+            const int32_t* perm = P.perm + (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
             for (int cb = tid * 4; cb < npos; cb += CAP) {
-                cell = __ldg(reinterpret_cast<const int4*>(perm + cb));
-                nvalid = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);
-                load_quad(P.lab16 + ph.j0, mpad, cell, L);
-                hist_quad(meta, ph, L, 0u, nvalid);
+                const int4 cl = __ldg(reinterpret_cast<const int4*>(perm + cb));
+                const int nv = (cl.x >= 0) + (cl.y >= 0) + (cl.z >= 0) + (cl.w >= 0);
+                load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), cl, L);
+                hist_quad(meta, ph, L, 0u, nv);
             }
         }
         __syncthreads();  // the tables of phase p are complete; every thread has left phase p-1
-        if (warp == 0) plan_phase<WIDE>(P, sbase, b ^ 1u, sbase + SM_DYN + (b ^ 1u) * (uint32_t)half, half, lane, pl, jbeg, jend, R);
-        if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, m, lane);
+        if (warp == 0) {
+            Planner pl;
+            planner_load(pl, sbase);
+            plan_phase(P, sbase, b ^ 1u, sbase + SM_DYN + (b ^ 1u) * (uint32_t)half, half, lane, pl);
+            planner_store(pl, sbase, lane);
+        }
+        if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
         // ---- gather ----
-        if (RESIDENT) {
-            gather_quad<WIDE, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
+        if (resident) {
+            gather_quad<false, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
         } else {
+            const int npos = (int)lds_u32(meta + META_NPOS);
+            const bool wide = (lds_u32(meta + META_NROWS) & NROWS_WIDE) != 0;
+            const int32_t* perm = P.perm + (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
+            const double wscale = __ldg(P.w + m) * P.inv_norm;
             for (int cb0 = 0; cb0 < npos; cb0 += CAP) {  // block-uniform trip count: gather_quad shuffles when WANT_SIM
                 const int cb = cb0 + tid * 4;
-                cell = make_int4(-1, -1, -1, -1);
-                if (cb < npos) cell = __ldg(reinterpret_cast<const int4*>(perm + cb));
-                nvalid = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);
-                load_quad(P.lab16 + ph.j0, mpad, cell, L);
+                int4 cl = make_int4(-1, -1, -1, -1);
+                if (cb < npos) cl = __ldg(reinterpret_cast<const int4*>(perm + cb));
+                const int nv = (cl.x >= 0) + (cl.y >= 0) + (cl.z >= 0) + (cl.w >= 0);
+                load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), cl, L);
                 double a4[4] = {0.0, 0.0, 0.0, 0.0};
-                gather_quad<WIDE, WANT_SIM>(P, meta, simacc, ph, L, 0u, sa, nvalid, lane, a4);
+                if (wide)
+                    gather_quad<true, WANT_SIM>(P, meta, simacc, ph, L, 0u, sa, nv, lane, a4);
+                else
+                    gather_quad<false, WANT_SIM>(P, meta, simacc, ph, L, 0u, sa, nv, lane, a4);
                 if (WANT_ECC) {
-                    if (cell.x >= 0) atomicAdd(P.ecc + cell.x, a4[0] * wscale);
-                    if (cell.y >= 0) atomicAdd(P.ecc + cell.y, a4[1] * wscale);
-                    if (cell.z >= 0) atomicAdd(P.ecc + cell.z, a4[2] * wscale);
-                    if (cell.w >= 0) atomicAdd(P.ecc + cell.w, a4[3] * wscale);
+                    if (cl.x >= 0) atomicAdd(P.ecc + cl.x, a4[0] * wscale);
+                    if (cl.y >= 0) atomicAdd(P.ecc + cl.y, a4[1] * wscale);
+                    if (cl.z >= 0) atomicAdd(P.ecc + cl.z, a4[2] * wscale);
+                    if (cl.w >= 0) atomicAdd(P.ecc + cl.w, a4[3] * wscale);
                 }
             }
         }
         prev = ph;
+        prev_m = m;
     }
+    flush_acc();
     if (WANT_SIM) {
         __syncthreads();
-        if (warp == 1) flush_sim(P, sbase + SM_SIMACC + ((p - 1u) & 1u) * 64u, prev, m, lane);
+        if (warp == 1) flush_sim(P, sbase + SM_SIMACC + ((p - 1u) & 1u) * 64u, prev, prev_m, lane);
     }
-    if (RESIDENT && WANT_ECC) {
-        if (cell.x >= 0) atomicAdd(P.ecc + cell.x, acc[0] * wscale);
-        if (cell.y >= 0) atomicAdd(P.ecc + cell.y, acc[1] * wscale);
-        if (cell.z >= 0) atomicAdd(P.ecc + cell.z, acc[2] * wscale);
-        if (cell.w >= 0) atomicAdd(P.ecc + cell.w, acc[3] * wscale);
-    }
-}
-
-template <bool WANT_ECC, bool WANT_SIM>
-__global__ void __launch_bounds__(NT, 1) tile_kernel(const TileParams P) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const Item it = P.items[blockIdx.x];
-    if (it.jbeg >= it.jend) return;
-    if (it.npos <= CAP)
-        run_item<true, false, WANT_ECC, WANT_SIM>(P, it, smem);
-    else if (it.pad_)
-        run_item<false, true, WANT_ECC, WANT_SIM>(P, it, smem);
-    else
-        run_item<false, false, WANT_ECC, WANT_SIM>(P, it, smem);
 }
 
 // Shared memory one block asks for and the number of table rows a resident block may own so that at least one
@@ -424,22 +531,50 @@ int tile_smem_budget(int32_t kmax, int32_t* max_rows_out) {
     return budget;
 }
 
-template <bool E, bool S>
-static int launch_tile_t(const TileParams& p, int32_t nitems, cudaStream_t s) {
-    auto kern = tile_kernel<E, S>;
-    CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-    kern<<<(unsigned)nitems, NT, (size_t)p.smem_bytes, s>>>(p);
+// per-quad row index and cluster size of every owned partition's cluster-sorted order (streamed by the wave kernel
+// instead of three dependent random loads per work unit)
+__global__ void __launch_bounds__(256) qinfo_kernel(const TileParams P, const int32_t* __restrict__ parts, int32_t nparts, int64_t nquads) {
+    const int sl = blockIdx.y;
+    if (sl >= nparts) return;
+    const int m = parts[sl];
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (int64_t)gridDim.x * blockDim.x) {
+        const int cellx = __ldg(P.perm + (int64_t)sl * P.perm_stride + q * 4);
+        uint2 v = make_uint2(0u, 0u);
+        if (cellx >= 0) {
+            const int a = (int)__ldg(P.lab16 + lab16_index(P.n, cellx, m));
+            v.x = (uint32_t)__ldg(P.crow + (int64_t)sl * P.kp + a);
+            v.y = (uint32_t)__ldg(P.sizes + (int64_t)m * P.kp + a);
+        }
+        reinterpret_cast<uint2*>(P.qinfo)[(int64_t)sl * (P.perm_stride >> 2) + q] = v;
+    }
+}
+int launch_qinfo(const TileParams& p, const int32_t* d_parts, int32_t nparts, cudaStream_t s) {
+    if (nparts <= 0) return CA_OK;
+    const int64_t nquads = p.perm_stride >> 2;
+    unsigned gx = (unsigned)std::min<int64_t>((nquads + 255) / 256, 1024);
+    qinfo_kernel<<<dim3(gx, (unsigned)nparts), 256, 0, s>>>(p, d_parts, nparts, nquads);
     CA_CUDA(cudaGetLastError());
     ca::ctx().launches++;
     return CA_OK;
 }
 
-int launch_tile(const TileParams& p, int32_t nitems, cudaStream_t s) {
-    if (nitems <= 0) return CA_OK;
+template <bool E, bool S>
+static int launch_wave_t(const TileParams& p, cudaStream_t s) {
+    auto kern = wave_kernel<E, S>;
+    CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    const int grid = std::min<int>(ca::ctx().sm_count, p.nwu);
+    kern<<<(unsigned)grid, NT, (size_t)p.smem_bytes, s>>>(p);
+    CA_CUDA(cudaGetLastError());
+    ca::ctx().launches++;
+    return CA_OK;
+}
+
+int launch_tile(const TileParams& p, cudaStream_t s) {
+    if (p.nwu <= 0) return CA_OK;
     const bool e = p.ecc != nullptr, sm = p.sim != nullptr;
-    if (e && sm) return launch_tile_t<true, true>(p, nitems, s);
-    if (e) return launch_tile_t<true, false>(p, nitems, s);
-    if (sm) return launch_tile_t<false, true>(p, nitems, s);
+    if (e && sm) return launch_wave_t<true, true>(p, s);
+    if (e) return launch_wave_t<true, false>(p, s);
+    if (sm) return launch_wave_t<false, true>(p, s);
     return CA_OK;
 }
 
