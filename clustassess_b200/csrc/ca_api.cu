@@ -394,6 +394,13 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     T.kp = L.kp;
     T.smem_bytes = smem_bytes;
     T.inv_norm = inv_norm;
+    T.unit_w = 1;
+    T.dbg = 0;
+#ifdef CA_ABLATE
+    if (const char* e = getenv("CA_ABLATE")) T.dbg = atoi(e);
+#endif
+    for (int32_t p = 0; p < mw; p++)
+        if (h_w[p] != 1.0) T.unit_w = 0;
     CA_TRY(launch_qinfo(T, W.parts.as<int32_t>(), nparts, s));
     CA_TRY(launch_tile(T, s));
     CA_CUDA(cudaEventRecord(c.ev[5], s));

@@ -114,10 +114,18 @@ int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint3
                 const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
                 int64_t perm_stride, cudaStream_t s);
 
-// ca_tile.cu -- the all-pairs engine: persistent blocks of 1024 threads x 4 cells, work units of 16 partners
+// ca_tile.cu -- the all-pairs engine: persistent blocks of TL_THREADS consumer threads x 4 cells (+ 1 producer warp),
+// work units of 16 partners
 constexpr int TL_CPT = 4;
-constexpr int TL_THREADS = 1024;
-constexpr int TL_CAP = TL_CPT * TL_THREADS;  // 4096 positions per resident block
+#ifndef CA_TL_THREADS
+#define CA_TL_THREADS 992
+#endif
+#ifndef CA_TL_BLOCKS
+#define CA_TL_BLOCKS 1
+#endif
+constexpr int TL_THREADS = CA_TL_THREADS;   // tuning builds (tools/build_variant.sh) override these two
+constexpr int TL_BLOCKS = CA_TL_BLOCKS;     // persistent blocks per SM (they share the SM's shared memory)
+constexpr int TL_CAP = TL_CPT * TL_THREADS;  // positions per resident item
 constexpr int TL_MAX_ROWS = 1024;
 constexpr int TL_SUPER = 16;                 // partners per work unit: one 32-byte label sector per cell
 struct TileParams {
@@ -140,6 +148,8 @@ struct TileParams {
     int32_t nsuper, nwu;      // super-tiles, work units
     int32_t smem_bytes;       // dynamic shared memory per block
     double inv_norm;
+    int32_t unit_w;           // every weight is exactly 1
+    int32_t dbg;              // ablation switches of -DCA_ABLATE tuning builds (tools/build_variant.sh), else 0
 };
 int launch_tile(const TileParams& p, cudaStream_t s);
 int launch_qinfo(const TileParams& p, const int32_t* d_parts, int32_t nparts, cudaStream_t s);

@@ -32,6 +32,8 @@
 //
 // The division is T * r with r = 1/max from rcp.approx.ftz.f64 + one Newton step (relative error < 1e-13);
 // the batched path has to meet 1e-9 absolute, the per-pair entry points (ca_pair.cu) keep the IEEE division.
+#include <stdio.h>
+
 #include <algorithm>
 
 #include "ca_internal.h"
@@ -39,19 +41,21 @@
 namespace ca {
 
 static constexpr unsigned FULL = 0xffffffffu;
-static constexpr int NT = TL_THREADS;
+static constexpr int NC = TL_THREADS;       // consumer threads (a quad of cells each)
+static constexpr int NT = NC + 32;          // + the producer warp
 static constexpr int CAP = TL_CAP;
 static_assert(TL_CPT == 4, "a thread owns one quad of cells");
 
 // shared-memory map (byte offsets from the dynamic shared base)
-static constexpr int SM_MBAR = 0;       // two mbarriers (one per buffer): tables initialised + meta published
-static constexpr int SM_META = 16;      // two Meta records
-static constexpr int META_BYTES = 160;
+static constexpr int SM_MBAR = 0;       // four mbarriers: full[2] (tables initialised + meta published), empty[2] (buffer released)
+static constexpr int SM_META = 32;      // two Meta records
+static constexpr int META_BYTES = 224;
 static constexpr int META_J0 = 0, META_G0 = 4, META_CNT = 8, META_FIRST = 12, META_M = 16, META_POS0 = 20, META_NPOS = 24,
-                     META_NROWS = 28, META_SA = 32, META_SLOT = 36, META_JHI = 40, META_TB = 64, META_RB = 96, META_KK = 128;
-static constexpr int SM_SIMACC = 336;   // [2][8] double: sum of ECS over the block's cells, per buffer and partner
-static constexpr int SM_PLAN = 464;     // warp 0's Planner (26 words) and, at +112, K_j | flags of the super-tile's 16 partners
-static constexpr int SM_DYN = 640;      // two table buffers
+                     META_NROWS = 28, META_SA = 32, META_SLOT = 36, META_JHI = 40, META_TB = 64, META_RB = 96, META_KK = 128,
+                     META_W = 160;  // [8] double: weights of the phase's partners
+static constexpr int SM_SIMACC = 480;   // [2][8] double: sum of ECS over the block's cells, per buffer and partner
+static constexpr int SM_PLAN = 608;     // at +112 K_j | flags, at +176 the weights of the current super-tile's 16 partners (producer's scratch)
+static constexpr int SM_DYN = 1024;     // two table buffers
 static constexpr uint32_t KK_BIG = 1u << 30;  // partner has a cluster with >= 65535 cells
 
 // ---- shared-space accessors ---------------------------------------------------------------------------------
@@ -101,15 +105,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ uint4 ldg_u4(const uint16_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// T / max(sa, sb): reciprocal seed + one Newton step, then one multiply
-__device__ __forceinline__ double ecs_of(uint32_t count, uint32_t sa, uint32_t sb) {
-    const double mx = (double)max(sa, sb);
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
-    r = fma(fma(-mx, r, 1.0), r, r);
-    return (double)count * r;
-}
-
 // labels of the 8 partners [j0, j0+8) for a quad of cells: one 16-byte load per cell (lab16j = lab16 + lab16_index(n, 0, j0))
 __device__ __forceinline__ void load_quad(const uint16_t* __restrict__ lab16j, int4 cell, uint4 (&L)[4]) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -124,73 +119,89 @@ struct Phase {
 };
 
 // ---- histogram / gather of one phase for a quad of cells -------------------------------------------------------
-// labels of tile slot jt (block-uniform) for the quad: a uniform switch picks the register, PRMT the half
-__device__ __forceinline__ void pick_labels(const uint4 (&L)[4], int jt, uint32_t (&lab)[4]) {
-    uint32_t w[4];
+// The 4 words that hold tile slot jt's label of the quad's cells are picked by a block-uniform switch (the body is
+// inlined four times), the half by one PRMT per label with a uniform selector.
+template <typename F>
+__device__ __forceinline__ void with_slot_words(const uint4 (&L)[4], int jt, F&& f) {
     switch (jt >> 1) {
-        case 0: w[0] = L[0].x; w[1] = L[1].x; w[2] = L[2].x; w[3] = L[3].x; break;
-        case 1: w[0] = L[0].y; w[1] = L[1].y; w[2] = L[2].y; w[3] = L[3].y; break;
-        case 2: w[0] = L[0].z; w[1] = L[1].z; w[2] = L[2].z; w[3] = L[3].z; break;
-        default: w[0] = L[0].w; w[1] = L[1].w; w[2] = L[2].w; w[3] = L[3].w; break;
+        case 0: f(L[0].x, L[1].x, L[2].x, L[3].x); break;
+        case 1: f(L[0].y, L[1].y, L[2].y, L[3].y); break;
+        case 2: f(L[0].z, L[1].z, L[2].z, L[3].z); break;
+        default: f(L[0].w, L[1].w, L[2].w, L[3].w); break;
     }
-    const uint32_t sel = (jt & 1) ? 0x4432u : 0x4410u;
-#pragma unroll
-    for (int c = 0; c < 4; c++) lab[c] = __byte_perm(w[c], 0u, sel);
 }
 
 __device__ __forceinline__ void hist_quad(uint32_t meta, const Phase ph, const uint4 (&L)[4], uint32_t rowidx, int nvalid) {
-#pragma unroll 2
+#pragma unroll 1
     for (int q = 0; q < ph.cnt; q++) {
-        uint32_t lab[4];
-        pick_labels(L, ph.g0 + q, lab);
+        const int jt = ph.g0 + q;
+        const uint32_t sel = (jt & 1) ? 0x4432u : 0x4410u;
         const uint32_t rb = lds_u32(meta + META_TB + q * 4) + rowidx * lds_u32(meta + META_RB + q * 4);
-        if (nvalid == 4) {  // all but the last quad of a cluster
-#pragma unroll
-            for (int c = 0; c < 4; c++) red_inc(rb + lab[c] * 4u);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (c < nvalid) red_inc(rb + lab[c] * 4u);
-        }
+        with_slot_words(L, jt, [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+            if (nvalid == 4) {  // all but the last quad of a cluster
+                red_inc(rb + __byte_perm(w0, 0u, sel) * 4u);
+                red_inc(rb + __byte_perm(w1, 0u, sel) * 4u);
+                red_inc(rb + __byte_perm(w2, 0u, sel) * 4u);
+                red_inc(rb + __byte_perm(w3, 0u, sel) * 4u);
+            } else {
+                if (nvalid > 0) red_inc(rb + __byte_perm(w0, 0u, sel) * 4u);
+                if (nvalid > 1) red_inc(rb + __byte_perm(w1, 0u, sel) * 4u);
+                if (nvalid > 2) red_inc(rb + __byte_perm(w2, 0u, sel) * 4u);
+            }
+        });
     }
 }
 
-template <bool WIDE, bool WANT_SIM>
+// UNITW: all weights are 1 (element_consistency of distinct partitions): ECS = count * r is accumulated by one FMA
+template <bool WIDE, bool WANT_SIM, bool UNITW>
 __device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, const uint4 (&L)[4],
                                             uint32_t rowidx, uint32_t sa, int nvalid, int lane, double (&acc)[4]) {
 #pragma unroll 1
     for (int q = 0; q < ph.cnt; q++) {
         const int jt = ph.g0 + q;
-        uint32_t lab[4];
-        pick_labels(L, jt, lab);
+        const uint32_t sel = (jt & 1) ? 0x4432u : 0x4410u;
         const uint32_t rb = lds_u32(meta + META_TB + q * 4) + rowidx * lds_u32(meta + META_RB + q * 4);
         const uint32_t kk = lds_u32(meta + META_KK + q * 4);
-        const double wj = __ldg(P.w + ph.j0 + jt);
+        const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + q * 8);
         const int32_t* szg = P.sizes + (int64_t)(ph.j0 + jt) * P.kp;
         double es = 0.0;
-        auto one = [&](int c, bool lookup) {
-            const uint32_t e = lds_u32(rb + lab[c] * 4u);
+        auto one = [&](double& a, uint32_t w, bool lookup) {
+            const uint32_t lab = __byte_perm(w, 0u, sel);
+            const uint32_t e = lds_u32(rb + lab * 4u);
             uint32_t count, sb;
             if (WIDE) {
                 count = e;
-                sb = (uint32_t)__ldg(szg + lab[c]);
+                sb = (uint32_t)__ldg(szg + lab);
             } else {
                 count = e & 0xffffu;
                 sb = e >> 16;
-                if (lookup && sb == 0xffffu) sb = (uint32_t)__ldg(szg + lab[c]);
+                if (lookup && sb == 0xffffu) sb = (uint32_t)__ldg(szg + lab);
             }
-            const double v = ecs_of(count, sa, sb);
-            acc[c] = fma(v, wj, acc[c]);
-            if (WANT_SIM) es += v;
+            const double mx = (double)max(sa, sb);
+            double r;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
+            r = fma(fma(-mx, r, 1.0), r, r);  // one Newton step: relative error < 1e-13
+            if (UNITW && !WANT_SIM) {
+                a = fma((double)count, r, a);
+            } else {
+                const double v = (double)count * r;
+                a = UNITW ? a + v : fma(v, wj, a);
+                if (WANT_SIM) es += v;
+            }
         };
-        if (nvalid == 4 && !(kk & KK_BIG)) {  // the common case: a full quad, no partner cluster beyond 16 bits
-#pragma unroll
-            for (int c = 0; c < 4; c++) one(c, false);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (c < nvalid) one(c, true);
-        }
+        with_slot_words(L, jt, [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+            if (nvalid == 4 && !(kk & KK_BIG)) {  // the common case: a full quad, no partner cluster beyond 16 bits
+                one(acc[0], w0, false);
+                one(acc[1], w1, false);
+                one(acc[2], w2, false);
+                one(acc[3], w3, false);
+            } else {
+                if (nvalid > 0) one(acc[0], w0, true);
+                if (nvalid > 1) one(acc[1], w1, true);
+                if (nvalid > 2) one(acc[2], w2, true);
+                if (nvalid > 3) one(acc[3], w3, true);
+            }
+        });
         if (WANT_SIM) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
@@ -218,9 +229,14 @@ __device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, 
 // owner partition -- instead of one random HBM sector read per (cell, tile, owner), which is what bounds a
 // block-per-item schedule (measured: 42 G random sectors/s, tools/gatherbench.cu).
 static constexpr int SUPER = TL_SUPER;
+#ifdef CA_ABLATE
+#define CA_DBG(P, bit) (((P).dbg >> (bit)) & 1)  // tuning builds: 0 no ecc flush, 1 no table fill, 2 no label loads, 3 no hist, 4 no gather
+#else
+#define CA_DBG(P, bit) 0
+#endif
 static constexpr uint32_t NROWS_WIDE = 1u << 30;  // Item::nrows flag: more than 65535 cells, 32-bit counters
 
-struct Planner {          // parked in shared memory between warp 0's planning steps (all values warp-uniform)
+struct Planner {          // the producer warp's registers (all values warp-uniform)
     int w;                // current WU
     int s;                // its super-tile
     int wend;             // wu_prefix[s + 1]
@@ -260,7 +276,10 @@ __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int
         pl.j0 = jlo & ~7;
         pl.g0 = jlo - pl.j0;
         pl.first = 1;
-        if (lane < SUPER) sts_u32(sbase + SM_PLAN + 112 + lane * 4, (uint32_t)__ldg(P.kinfo + slo + lane));
+        if (lane < SUPER) {
+            sts_u32(sbase + SM_PLAN + 112 + lane * 4, (uint32_t)__ldg(P.kinfo + slo + lane));
+            sts_f64(sbase + SM_PLAN + 176 + lane * 8, __ldg(P.w + slo + lane));
+        }
         __syncwarp();
         pl.nw = pl.w + (int)gridDim.x;
         if (pl.nw < P.nwu) {
@@ -269,24 +288,6 @@ __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int
         }
     }
 }
-#define CA_PLANNER_FIELDS(X) \
-    X(0, w) X(1, s) X(2, wend) X(3, it.m) X(4, it.pos0) X(5, it.npos) X(6, it.nrows) X(7, it.jbeg) X(8, it.jend) X(9, it.sa) \
-    X(10, it.pad_) X(11, jhi) X(12, j0) X(13, g0) X(14, first) X(15, nit.m) X(16, nit.pos0) X(17, nit.npos) X(18, nit.nrows) \
-    X(19, nit.jbeg) X(20, nit.jend) X(21, nit.sa) X(22, nit.pad_) X(23, nw) X(24, ns) X(25, nwend)
-__device__ __forceinline__ void planner_load(Planner& pl, uint32_t sbase) {
-#define X(i, f) pl.f = (int)lds_u32(sbase + SM_PLAN + (i) * 4);
-    CA_PLANNER_FIELDS(X)
-#undef X
-}
-__device__ __forceinline__ void planner_store(const Planner& pl, uint32_t sbase, int lane) {
-    if (lane == 0) {
-#define X(i, f) sts_u32(sbase + SM_PLAN + (i) * 4, (uint32_t)pl.f);
-        CA_PLANNER_FIELDS(X)
-#undef X
-    }
-    __syncwarp();
-}
-static_assert(sizeof(Planner) <= 112, "Planner must fit its shared-memory slot");
 __device__ __forceinline__ void planner_init(const TileParams& P, Planner& pl, int lane, uint32_t sbase) {
     pl.nw = (int)blockIdx.x;
     pl.ns = 0;
@@ -315,7 +316,8 @@ __device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, 
     const int R = pl.it.npos <= CAP ? (int)(pl.it.nrows & 0xffff) : 1;
     const int thi = min(8, pl.jhi - pl.j0);
     const int q = pl.g0 + lane;                                 // tile slot served by meta entry `lane`
-    const uint32_t kk = lds_u32(sbase + SM_PLAN + 112 + ((((uint32_t)pl.j0 & (SUPER - 1)) + q) & (SUPER - 1)) * 4);
+    const uint32_t sq = (((uint32_t)pl.j0 & (SUPER - 1)) + q) & (SUPER - 1);  // position inside the super-tile
+    const uint32_t kk = lds_u32(sbase + SM_PLAN + 112 + sq * 4);
     const bool ok = lane < 8 && q < thi;
     const uint32_t rowb = ok ? (((kk & 0xffffu) + 3u) & ~3u) * 4u : 0u;  // bytes of one table row
     const uint32_t tbytes = rowb * (uint32_t)R;
@@ -334,6 +336,7 @@ __device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, 
         sts_u32(meta + META_TB + lane * 4, tb);
         sts_u32(meta + META_RB + lane * 4, rowb);
         sts_u32(meta + META_KK + lane * 4, kk);
+        sts_f64(meta + META_W + lane * 8, lds_f64(sbase + SM_PLAN + 176 + sq * 8));
     }
     if (lane == 0) {
         sts_u32(meta + META_J0, (uint32_t)pl.j0);
@@ -350,12 +353,14 @@ __device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, 
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the block's generic accesses before the async writes
     __syncwarp();
-    if (lane == 0) {
+    if (CA_DBG(P, 1)) {
+        if (lane == 0) mbar_arrive(bar);
+    } else if (lane == 0) {
         mbar_expect_tx(bar, ttot);
         if (wide) bulk_g2s(bufaddr, P.zeros, ttot, bar);
     }
     __syncwarp();
-    if (!wide) {
+    if (!wide && !CA_DBG(P, 1)) {
         for (int t = 0; t < cnt; t++) {  // partner t: R row copies, a lane each
             const uint32_t tbt = __shfl_sync(FULL, tb, t), rbt = __shfl_sync(FULL, rowb, t);
             const uint32_t* src = P.spack + (int64_t)(pl.j0 + pl.g0 + t) * P.kp;
@@ -373,32 +378,48 @@ __device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The persistent kernel: one block per SM walks its work units; the phases of consecutive WUs form one stream
-// (the fill of the next WU's first phase is in flight during the last gather of the current one).
+// The persistent kernel: one block per SM walks its work units; the phases of consecutive WUs form one stream.
+// Warp 0 is the PRODUCER: it plans phases and issues their table fills, running up to two phases ahead of the
+// CONSUMER warps (every other warp; a thread owns a quad of cells).  Hand-offs are mbarriers: full[b] (fill landed
+// + meta published) and empty[b] (every consumer warp has finished gathering from buffer b); the consumers meet
+// at one named barrier per phase, between histogram and gather.
 // A WU of a RESIDENT item (<= CAP positions, R >= 1 complete clusters) keeps the labels of its cells in registers
 // between the histogram and the gather and adds its per-cell sums to ecc once; a WU of a larger cluster streams
 // the cells in chunks of CAP positions in both passes and adds to ecc per phase.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool WANT_ECC, bool WANT_SIM>
-__global__ void __launch_bounds__(NT, 1) wave_kernel(const TileParams P) {
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
+
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW>
+__global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const int half = ((P.smem_bytes - SM_DYN) / 2) & ~127;
-    if (tid == 0) {
-        mbar_init(sbase + SM_MBAR, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(sbase + SM_MBAR, 1);                 // full[0], full[1]: the producer's arrive + the fill's bytes
         mbar_init(sbase + SM_MBAR + 8, 1);
+        mbar_init(sbase + SM_MBAR + 16, NC / 32);      // empty[0], empty[1]: one arrive per consumer warp
+        mbar_init(sbase + SM_MBAR + 24, NC / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 16) sts_f64(sbase + SM_SIMACC + tid * 8u, 0.0);
+    if (threadIdx.x < 16) sts_f64(sbase + SM_SIMACC + threadIdx.x * 8u, 0.0);
     __syncthreads();
-    if (warp == 0) {
+
+    if (warp == 0) {  // ---- producer ----
         Planner pl;
         planner_init(P, pl, lane, sbase);
-        plan_phase(P, sbase, 0u, sbase + SM_DYN, half, lane, pl);
-        planner_store(pl, sbase, lane);
+        for (uint32_t p = 0;; p++) {
+            const uint32_t b = p & 1u;
+            if (p >= 2) mbar_wait(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u);  // consumers are done with buffer b
+            const bool last = pl.w >= P.nwu;
+            plan_phase(P, sbase, b, sbase + SM_DYN + b * (uint32_t)half, half, lane, pl);
+            if (last) break;
+        }
+        return;
     }
 
+    // ---- consumers ----
+    const int tid = (int)threadIdx.x - 32;  // consumer thread id: owns positions [4 tid, 4 tid + 4) of a resident item
     // the current WU, as seen by every thread (everything else is re-read from the phase's meta record)
     int m = -1;
     bool resident = true;
@@ -406,14 +427,14 @@ __global__ void __launch_bounds__(NT, 1) wave_kernel(const TileParams P) {
     int nvalid = 0;
     uint32_t rowidx = 0, sa = 0;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    uint4 L[4];  // labels of the current tile for this thread's quad
+    uint4 L[4] = {};  // labels of the current tile for this thread's quad
     int cur_j0 = -1;
     Phase prev;
     prev.j0 = prev.g0 = prev.cnt = 0;
     int prev_m = -1;
 
     auto flush_acc = [&]() {
-        if (WANT_ECC && resident && m >= 0) {
+        if (WANT_ECC && resident && m >= 0 && !CA_DBG(P, 0)) {
             const double wscale = __ldg(P.w + m) * P.inv_norm;
             if (cell.x >= 0) atomicAdd(P.ecc + cell.x, acc[0] * wscale);
             if (cell.y >= 0) atomicAdd(P.ecc + cell.y, acc[1] * wscale);
@@ -459,9 +480,9 @@ __global__ void __launch_bounds__(NT, 1) wave_kernel(const TileParams P) {
         if (resident) {
             if (ph.j0 != cur_j0) {  // an L2 hit: the super-tile's sectors were fetched by the first block that needed them
                 cur_j0 = ph.j0;
-                load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), cell, L);
+                if (!CA_DBG(P, 2)) load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), cell, L);
             }
-            hist_quad(meta, ph, L, rowidx, nvalid);
+            if (!CA_DBG(P, 3)) hist_quad(meta, ph, L, rowidx, nvalid);
         } else {
             const int npos = (int)lds_u32(meta + META_NPOS);
             const int32_t* perm = P.perm + (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
@@ -472,23 +493,17 @@ __global__ void __launch_bounds__(NT, 1) wave_kernel(const TileParams P) {
                 hist_quad(meta, ph, L, 0u, nv);
             }
         }
-        __syncthreads();  // the tables of phase p are complete; every thread has left phase p-1
-        if (warp == 0) {
-            Planner pl;
-            planner_load(pl, sbase);
-            plan_phase(P, sbase, b ^ 1u, sbase + SM_DYN + (b ^ 1u) * (uint32_t)half, half, lane, pl);
-            planner_store(pl, sbase, lane);
-        }
+        consumer_sync();  // the tables of phase p are complete; every consumer has left phase p-1
         if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
         // ---- gather ----
         if (resident) {
-            gather_quad<false, WANT_SIM>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
+            if (!CA_DBG(P, 4)) gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
         } else {
             const int npos = (int)lds_u32(meta + META_NPOS);
             const bool wide = (lds_u32(meta + META_NROWS) & NROWS_WIDE) != 0;
             const int32_t* perm = P.perm + (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
             const double wscale = __ldg(P.w + m) * P.inv_norm;
-            for (int cb0 = 0; cb0 < npos; cb0 += CAP) {  // block-uniform trip count: gather_quad shuffles when WANT_SIM
+            for (int cb0 = 0; cb0 < npos; cb0 += CAP) {  // warp-uniform trip count: gather_quad shuffles when WANT_SIM
                 const int cb = cb0 + tid * 4;
                 int4 cl = make_int4(-1, -1, -1, -1);
                 if (cb < npos) cl = __ldg(reinterpret_cast<const int4*>(perm + cb));
@@ -496,9 +511,9 @@ __global__ void __launch_bounds__(NT, 1) wave_kernel(const TileParams P) {
                 load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), cl, L);
                 double a4[4] = {0.0, 0.0, 0.0, 0.0};
                 if (wide)
-                    gather_quad<true, WANT_SIM>(P, meta, simacc, ph, L, 0u, sa, nv, lane, a4);
+                    gather_quad<true, WANT_SIM, UNITW>(P, meta, simacc, ph, L, 0u, sa, nv, lane, a4);
                 else
-                    gather_quad<false, WANT_SIM>(P, meta, simacc, ph, L, 0u, sa, nv, lane, a4);
+                    gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, L, 0u, sa, nv, lane, a4);
                 if (WANT_ECC) {
                     if (cl.x >= 0) atomicAdd(P.ecc + cl.x, a4[0] * wscale);
                     if (cl.y >= 0) atomicAdd(P.ecc + cl.y, a4[1] * wscale);
@@ -509,10 +524,12 @@ __global__ void __launch_bounds__(NT, 1) wave_kernel(const TileParams P) {
         }
         prev = ph;
         prev_m = m;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sbase + SM_MBAR + 16 + b * 8u);  // this warp is done with buffer b (and its meta record)
     }
     flush_acc();
     if (WANT_SIM) {
-        __syncthreads();
+        consumer_sync();
         if (warp == 1) flush_sim(P, sbase + SM_SIMACC + ((p - 1u) & 1u) * 64u, prev, prev_m, lane);
     }
 }
@@ -522,7 +539,7 @@ __global__ void __launch_bounds__(NT, 1) wave_kernel(const TileParams P) {
 int tile_smem_budget(int32_t kmax, int32_t* max_rows_out) {
     Ctx& c = ctx();
     const size_t optin = c.smem_optin ? c.smem_optin : 227 * 1024;
-    const int budget = (int)optin;
+    const int budget = TL_BLOCKS == 1 ? (int)optin : (int)(((optin + 1024) / TL_BLOCKS - 1024) & ~127);  // 1 KB per block is reserved by the system
     const long long half = (((long long)budget - SM_DYN) / 2) & ~127LL;
     const long long rowb = (((long long)(kmax > 0 ? kmax : 1) + 3) & ~3LL) * 4;
     long long rows = half / rowb;
@@ -558,11 +575,11 @@ int launch_qinfo(const TileParams& p, const int32_t* d_parts, int32_t nparts, cu
     return CA_OK;
 }
 
-template <bool E, bool S>
+template <bool E, bool S, bool U>
 static int launch_wave_t(const TileParams& p, cudaStream_t s) {
-    auto kern = wave_kernel<E, S>;
+    auto kern = wave_kernel<E, S, U>;
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-    const int grid = std::min<int>(ca::ctx().sm_count, p.nwu);
+    const int grid = std::min<int>(ca::ctx().sm_count * TL_BLOCKS, p.nwu);
     kern<<<(unsigned)grid, NT, (size_t)p.smem_bytes, s>>>(p);
     CA_CUDA(cudaGetLastError());
     ca::ctx().launches++;
@@ -572,9 +589,15 @@ static int launch_wave_t(const TileParams& p, cudaStream_t s) {
 int launch_tile(const TileParams& p, cudaStream_t s) {
     if (p.nwu <= 0) return CA_OK;
     const bool e = p.ecc != nullptr, sm = p.sim != nullptr;
-    if (e && sm) return launch_wave_t<true, true>(p, s);
-    if (e) return launch_wave_t<true, false>(p, s);
-    if (sm) return launch_wave_t<false, true>(p, s);
+    if (p.unit_w) {
+        if (e && sm) return launch_wave_t<true, true, true>(p, s);
+        if (e) return launch_wave_t<true, false, true>(p, s);
+        if (sm) return launch_wave_t<false, true, true>(p, s);
+    } else {
+        if (e && sm) return launch_wave_t<true, true, false>(p, s);
+        if (e) return launch_wave_t<true, false, false>(p, s);
+        if (sm) return launch_wave_t<false, true, false>(p, s);
+    }
     return CA_OK;
 }
 
