@@ -105,6 +105,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ uint4 ldg_u4(const uint16_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// labels of a whole super-tile (16 partners) for a quad of cells: ONE 32-byte load per cell (SASS LDG.E.256, sm_100+),
+// i.e. one L2 sector request per (cell, work unit); lo = partners [16 s, 16 s + 8), hi = [16 s + 8, 16 s + 16)
+__device__ __forceinline__ void ldg_256(const uint16_t* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+// (padding positions load cell 0's labels: never used, every use is guarded by the quad's valid count)
+__device__ __forceinline__ void load_quad_super(const uint16_t* __restrict__ lab16s, int4 cell, uint4 (&Lo)[4], uint4 (&Hi)[4]) {
+    ldg_256(lab16s + (int64_t)max(cell.x, 0) * 16, Lo[0], Hi[0]);
+    ldg_256(lab16s + (int64_t)max(cell.y, 0) * 16, Lo[1], Hi[1]);
+    ldg_256(lab16s + (int64_t)max(cell.z, 0) * 16, Lo[2], Hi[2]);
+    ldg_256(lab16s + (int64_t)max(cell.w, 0) * 16, Lo[3], Hi[3]);
+}
 // labels of the 8 partners [j0, j0+8) for a quad of cells: one 16-byte load per cell (lab16j = lab16 + lab16_index(n, 0, j0))
 __device__ __forceinline__ void load_quad(const uint16_t* __restrict__ lab16j, int4 cell, uint4 (&L)[4]) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -265,6 +279,7 @@ __device__ __forceinline__ Item load_item(const TileParams& P, int w, int s) {
 }
 // make the prefetched WU current (or mark the end) and start loading the one after it
 __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int lane, uint32_t sbase) {
+    const int olds = pl.w < 0 ? -1 : pl.s;
     pl.w = pl.nw;
     pl.s = pl.ns;
     pl.wend = pl.nwend;
@@ -276,11 +291,13 @@ __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int
         pl.j0 = jlo & ~7;
         pl.g0 = jlo - pl.j0;
         pl.first = 1;
-        if (lane < SUPER) {
-            sts_u32(sbase + SM_PLAN + 112 + lane * 4, (uint32_t)__ldg(P.kinfo + slo + lane));
-            sts_f64(sbase + SM_PLAN + 176 + lane * 8, __ldg(P.w + slo + lane));
+        if (pl.s != olds) {  // a new super-tile: its partners' K | flags and weights
+            if (lane < SUPER) {
+                sts_u32(sbase + SM_PLAN + 112 + lane * 4, (uint32_t)__ldg(P.kinfo + slo + lane));
+                sts_f64(sbase + SM_PLAN + 176 + lane * 8, __ldg(P.w + slo + lane));
+            }
+            __syncwarp();
         }
-        __syncwarp();
         pl.nw = pl.w + (int)gridDim.x;
         if (pl.nw < P.nwu) {
             locate_wu(P, pl.nw, pl.ns, pl.nwend);
@@ -289,6 +306,7 @@ __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int
     }
 }
 __device__ __forceinline__ void planner_init(const TileParams& P, Planner& pl, int lane, uint32_t sbase) {
+    pl.w = -1;
     pl.nw = (int)blockIdx.x;
     pl.ns = 0;
     pl.nwend = __ldg(P.wu_prefix + 1);
@@ -299,28 +317,27 @@ __device__ __forceinline__ void planner_init(const TileParams& P, Planner& pl, i
     advance_wu(P, pl, lane, sbase);
 }
 
-// Plans the phase at the cursor into buffer `buf`: how many partners of the tile fit (R rows of K_j entries each,
-// K_j rounded to 4), their table addresses, the WU's item, and the bulk copies that initialise the tables.  After
-// the last WU it publishes cnt = 0.  Everything written here is published by the arrive on the buffer's mbarrier.
-__device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, uint32_t buf, uint32_t bufaddr, int half, int lane,
-                                           Planner& pl) {
-    const uint32_t meta = sbase + SM_META + buf * META_BYTES, bar = sbase + SM_MBAR + buf * 8u;
-    if (pl.w >= P.nwu) {
-        if (lane == 0) {
-            sts_u32(meta + META_CNT, 0u);
-            mbar_arrive(bar);
-        }
-        return;
-    }
-    const bool wide = (pl.it.nrows & NROWS_WIDE) != 0;
-    const int R = pl.it.npos <= CAP ? (int)(pl.it.nrows & 0xffff) : 1;
+// Plans the phase at the cursor (how many partners of the tile fit into one buffer: R rows of K_j entries each,
+// K_j rounded to 4) -- this part needs no buffer, so the producer does it BEFORE it waits for the buffer to be
+// released -- then publishes it into buffer `buf`: table addresses, the WU's item, and the bulk copies that
+// initialise the tables.  After the last WU it publishes cnt = 0.  Everything written here is published by the
+// arrive on the buffer's `full` mbarrier.
+struct PhasePlan {
+    uint32_t kk, rowb, toff, ttot, sq;  // per lane (= tile slot g0 + lane): K | flags, row bytes, table offset; total bytes
+    int cnt, R;
+    bool wide;
+};
+__device__ __forceinline__ PhasePlan plan_compute(const TileParams& P, uint32_t sbase, int half, int lane, const Planner& pl) {
+    PhasePlan pp;
+    pp.wide = (pl.it.nrows & NROWS_WIDE) != 0;
+    pp.R = pl.it.npos <= CAP ? (int)(pl.it.nrows & 0xffff) : 1;
     const int thi = min(8, pl.jhi - pl.j0);
     const int q = pl.g0 + lane;                                 // tile slot served by meta entry `lane`
-    const uint32_t sq = (((uint32_t)pl.j0 & (SUPER - 1)) + q) & (SUPER - 1);  // position inside the super-tile
-    const uint32_t kk = lds_u32(sbase + SM_PLAN + 112 + sq * 4);
+    pp.sq = (((uint32_t)pl.j0 & (SUPER - 1)) + q) & (SUPER - 1);  // position inside the super-tile
+    pp.kk = lds_u32(sbase + SM_PLAN + 112 + pp.sq * 4);
     const bool ok = lane < 8 && q < thi;
-    const uint32_t rowb = ok ? (((kk & 0xffffu) + 3u) & ~3u) * 4u : 0u;  // bytes of one table row
-    const uint32_t tbytes = rowb * (uint32_t)R;
+    pp.rowb = ok ? (((pp.kk & 0xffffu) + 3u) & ~3u) * 4u : 0u;  // bytes of one table row
+    const uint32_t tbytes = pp.rowb * (uint32_t)pp.R;
     uint32_t pre = tbytes;                                      // inclusive prefix of the bytes needed
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
@@ -328,20 +345,26 @@ __device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, 
         if (lane >= o) pre += v;
     }
     const unsigned fm = __ballot_sync(FULL, ok && pre <= (uint32_t)half);
-    const int cnt = __popc(fm & 0xffu);                         // >= 1: the planner bounds R so that one partner always fits
-    if (cnt == 0) __trap();                                     // cannot happen; never hang the GPU
-    const uint32_t ttot = __shfl_sync(FULL, pre, cnt - 1);
-    const uint32_t tb = bufaddr + pre - tbytes;
-    if (lane < cnt) {
+    pp.cnt = __popc(fm & 0xffu);                                // >= 1: the host bounds R so that one partner always fits
+    if (pp.cnt == 0) __trap();                                  // cannot happen; never hang the GPU
+    pp.ttot = __shfl_sync(FULL, pre, pp.cnt - 1);
+    pp.toff = pre - tbytes;
+    return pp;
+}
+__device__ __forceinline__ void plan_publish(const TileParams& P, uint32_t sbase, uint32_t buf, uint32_t bufaddr, int lane,
+                                             const Planner& pl, const PhasePlan& pp) {
+    const uint32_t meta = sbase + SM_META + buf * META_BYTES, bar = sbase + SM_MBAR + buf * 8u;
+    const uint32_t tb = bufaddr + pp.toff;
+    if (lane < pp.cnt) {
         sts_u32(meta + META_TB + lane * 4, tb);
-        sts_u32(meta + META_RB + lane * 4, rowb);
-        sts_u32(meta + META_KK + lane * 4, kk);
-        sts_f64(meta + META_W + lane * 8, lds_f64(sbase + SM_PLAN + 176 + sq * 8));
+        sts_u32(meta + META_RB + lane * 4, pp.rowb);
+        sts_u32(meta + META_KK + lane * 4, pp.kk);
+        sts_f64(meta + META_W + lane * 8, lds_f64(sbase + SM_PLAN + 176 + pp.sq * 8));
     }
     if (lane == 0) {
         sts_u32(meta + META_J0, (uint32_t)pl.j0);
         sts_u32(meta + META_G0, (uint32_t)pl.g0);
-        sts_u32(meta + META_CNT, (uint32_t)cnt);
+        sts_u32(meta + META_CNT, (uint32_t)pp.cnt);
         sts_u32(meta + META_FIRST, (uint32_t)pl.first);
         sts_u32(meta + META_M, (uint32_t)pl.it.m);
         sts_u32(meta + META_POS0, (uint32_t)pl.it.pos0);
@@ -351,25 +374,37 @@ __device__ __forceinline__ void plan_phase(const TileParams& P, uint32_t sbase, 
         sts_u32(meta + META_SLOT, (uint32_t)pl.it.pad_);
         sts_u32(meta + META_JHI, (uint32_t)pl.jhi);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the block's generic accesses before the async writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the consumers' generic accesses before the async writes
     __syncwarp();
     if (CA_DBG(P, 1)) {
         if (lane == 0) mbar_arrive(bar);
-    } else if (lane == 0) {
-        mbar_expect_tx(bar, ttot);
-        if (wide) bulk_g2s(bufaddr, P.zeros, ttot, bar);
+        return;
+    }
+    if (lane == 0) {
+        mbar_expect_tx(bar, pp.ttot);
+        if (pp.wide) bulk_g2s(bufaddr, P.zeros, pp.ttot, bar);
     }
     __syncwarp();
-    if (!wide && !CA_DBG(P, 1)) {
-        for (int t = 0; t < cnt; t++) {  // partner t: R row copies, a lane each
-            const uint32_t tbt = __shfl_sync(FULL, tb, t), rbt = __shfl_sync(FULL, rowb, t);
-            const uint32_t* src = P.spack + (int64_t)(pl.j0 + pl.g0 + t) * P.kp;
-            for (int r = lane; r < R; r += 32) bulk_g2s(tbt + (uint32_t)r * rbt, src, rbt, bar);
+    if (!pp.wide) {  // cnt partners x R rows: one bulk copy per (partner, row), spread over the lanes
+        const int ncopy = pp.cnt * pp.R;
+        for (int base = 0; base < ncopy; base += 32) {  // warp-uniform trip count: the shuffles need every lane
+            const int idx = base + lane;
+            const int t = min(idx / pp.R, pp.cnt - 1), r = idx - t * pp.R;
+            const uint32_t tbt = __shfl_sync(FULL, tb, t), rbt = __shfl_sync(FULL, pp.rowb, t);
+            if (idx < ncopy) bulk_g2s(tbt + (uint32_t)r * rbt, P.spack + (int64_t)(pl.j0 + pl.g0 + t) * P.kp, rbt, bar);
         }
     }
-    // advance the cursor
+}
+__device__ __forceinline__ void plan_terminal(uint32_t sbase, uint32_t buf, int lane) {
+    if (lane == 0) {
+        sts_u32(sbase + SM_META + buf * META_BYTES + META_CNT, 0u);
+        mbar_arrive(sbase + SM_MBAR + buf * 8u);
+    }
+}
+__device__ __forceinline__ void plan_advance(const TileParams& P, Planner& pl, const PhasePlan& pp, int lane, uint32_t sbase) {
+    const int thi = min(8, pl.jhi - pl.j0);
     pl.first = 0;
-    pl.g0 += cnt;
+    pl.g0 += pp.cnt;
     if (pl.g0 >= thi) {
         pl.j0 += 8;
         pl.g0 = 0;
@@ -410,10 +445,16 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         planner_init(P, pl, lane, sbase);
         for (uint32_t p = 0;; p++) {
             const uint32_t b = p & 1u;
-            if (p >= 2) mbar_wait(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u);  // consumers are done with buffer b
             const bool last = pl.w >= P.nwu;
-            plan_phase(P, sbase, b, sbase + SM_DYN + b * (uint32_t)half, half, lane, pl);
-            if (last) break;
+            PhasePlan pp;
+            if (!last) pp = plan_compute(P, sbase, half, lane, pl);
+            if (p >= 2) mbar_wait(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u);  // consumers are done with buffer b
+            if (last) {
+                plan_terminal(sbase, b, lane);
+                break;
+            }
+            plan_publish(P, sbase, b, sbase + SM_DYN + b * (uint32_t)half, lane, pl, pp);
+            plan_advance(P, pl, pp, lane, sbase);
         }
         return;
     }
@@ -427,7 +468,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
     int nvalid = 0;
     uint32_t rowidx = 0, sa = 0;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    uint4 L[4] = {};  // labels of the current tile for this thread's quad
+    uint4 L[4], Lh[4];  // labels of the current tile for this thread's quad; Lh: the super-tile's upper tile
     int cur_j0 = -1;
     Phase prev;
     prev.j0 = prev.g0 = prev.cnt = 0;
@@ -478,9 +519,14 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         }
         // ---- histogram ----
         if (resident) {
-            if (ph.j0 != cur_j0) {  // an L2 hit: the super-tile's sectors were fetched by the first block that needed them
+            if (ph.j0 != cur_j0) {
+                if (cur_j0 < 0)  // first phase of the WU: an L2 hit, the super-tile's sectors were fetched by the first block that needed them
+                    load_quad_super(P.lab16 + lab16_index(P.n, 0, ph.j0 & ~(SUPER - 1)), cell, L, Lh);
+                if ((ph.j0 & 8) != 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) L[c] = Lh[c];
+                }
                 cur_j0 = ph.j0;
-                if (!CA_DBG(P, 2)) load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), cell, L);
             }
             if (!CA_DBG(P, 3)) hist_quad(meta, ph, L, rowidx, nvalid);
         } else {
