@@ -5,7 +5,7 @@
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path, host cores
 
 One "step" = one complete element_consistency job over the workload (all M(M-1)/2 partition pairs, all N
-cells): label packing, cell-major transposition, per-partition sort, row-block ECS kernels, all-reduce
+cells): label packing, cell-major transposition, per-partition sort, the wave kernel (tables + per-element ECS), all-reduce
 (N > 1) and finish.  The default workload is BASELINE.json's config 5 (500 partitions x 1M cells, up to
 2000 clusters, Louvain-like family), which fits one GPU; at N > 1 the SAME job is
 pair-sharded over the ranks (scaling = strong).
@@ -14,7 +14,7 @@ Printed JSON line (rank 0): metric = partition-pairs x cells per second.
   value     inputs (the raw int32 M x N label matrix) already resident in HBM; CUDA-event timed.
   e2e       the same job through the C-ABI entry the R shim binds (ca_consistency) with HOST buffers:
             pinned host -> device copy of the labels and device -> host copy of ecc inside the timed region.
-  roofline  the row-block ECS kernel: algorithmic bytes (16 B per pair-cell) / its
+  roofline  the wave kernel (ca_tile.cu): algorithmic bytes (16 B per pair-cell) / its
             CUDA-event duration, against the measured HBM peak of MEASURED_PEAKS.json.
   cpu_baseline  the reference's own disjointECS (oracle/_ref, else the C port) on 1 host core over a
             bounded sample of the same workload's pairs.
@@ -237,7 +237,7 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
     _capi.check(lib.ca_set_stream(stream.cuda_stream))
 
-    prof_acc = {"rowblock_ms": 0.0, "pack_ms": 0.0, "transpose_ms": 0.0, "sort_ms": 0.0, "plan_ms": 0.0, "finish_ms": 0.0}
+    prof_acc = {"engine_ms": 0.0, "pack_ms": 0.0, "transpose_ms": 0.0, "sort_ms": 0.0, "plan_ms": 0.0, "finish_ms": 0.0}
     launches = [0]
 
     def partial(r, w, ecc, sim):
@@ -247,7 +247,7 @@ def run_b200(args):
         for k in prof_acc:
             if k != "finish_ms":
                 prof_acc[k] += p[k]
-        launches[0] += int(p["rowblock_launches"])
+        launches[0] += int(p["launches"])
 
     def finish(ecc, sim):
         _capi.consistency_finish(n, m, weights, ecc.data_ptr(), None if sim is None else sim.data_ptr())
@@ -290,7 +290,7 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    rb = torch.tensor([prof_acc["rowblock_ms"]], dtype=torch.float64, device="cuda")
+    rb = torch.tensor([prof_acc["engine_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(rb, op=dist.ReduceOp.MAX)
@@ -324,7 +324,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (row-block ECS), measured live ------------------------------------------
+    # ---- roofline of the dominant kernel (wave_kernel: tables + per-element ECS), measured live ------------------------------------------
     peak, peak_src = measured_peak()
     rb_ms_per_step = float(rb.item()) / args.steps           # max over ranks; each rank runs 1/world of the pairs
     units_per_launch_set = units / world
@@ -339,7 +339,7 @@ def run_b200(args):
         except Exception:
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "rowblock_kernel", "kernel_ms_per_step": rb_ms_per_step, "kernel_share_of_step": rb_ms_per_step / (ms_total / args.steps),
+                "kernel": "wave_kernel (ca_tile.cu)", "kernel_ms_per_step": rb_ms_per_step, "kernel_share_of_step": rb_ms_per_step / (ms_total / args.steps),
                 "algorithmic_bytes_per_unit": BYTES_PER_UNIT, "peak_source": peak_src}
 
     cpu = None

@@ -89,7 +89,7 @@ def _opt(a):
 def profile():
     out = np.zeros(8, dtype=np.float64)
     lib().ca_get_profile(out, 8)
-    keys = ["pack_ms", "transpose_ms", "plan_ms", "sort_ms", "rowblock_ms", "finish_ms", "call_ms", "rowblock_launches"]
+    keys = ["pack_ms", "transpose_ms", "plan_ms", "sort_ms", "engine_ms", "finish_ms", "call_ms", "launches"]
     return dict(zip(keys, out.tolist()))
 
 

@@ -1,7 +1,7 @@
 """Pair-sharded all-pairs ECS over several GPUs: one process per GPU, torch.distributed for plumbing.
 
 Partitions are dealt to ranks in zigzag order (0..w-1, w-1..0, ...), which balances the number of
-pairs (i, j>i) per rank; every rank runs its share of row-block kernels on its own GPU and produces a
+pairs (i, j>i) per rank; every rank runs the wave kernel over its share of the work items on its own GPU and produces a
 partial per-cell sum (and, optionally, its rows of the ECS matrix).  The only exchange step of the whole
 path is ONE all-reduce of the N-vector (8 MB at N = 1M) and, when the matrix is wanted, one of the M x M
 buffer -- there is no data-path collective inside the kernels because pairs are independent
