@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <numeric>
 #include <thread>
 
@@ -28,13 +29,73 @@ Ctx& ctx() {
     return c;
 }
 
+// ---- device memory: a small caching allocator ----------------------------------------------------------
+// The host-pointer entry points (the ones the R shim binds) create and drop a label set per call; cudaMalloc /
+// cudaFree of multi-gigabyte buffers cost more than the kernels of a small job and cudaFree synchronises the
+// device.  Freed blocks are parked here and handed out again (best fit, at most 2x oversized); ca_shutdown()
+// returns everything to the driver.
+namespace {
+struct CacheBlock {
+    void* p;
+    size_t bytes;
+};
+std::vector<CacheBlock>& cache() {
+    static std::vector<CacheBlock> c;
+    return c;
+}
+std::mutex& cache_mutex() {
+    static std::mutex m;
+    return m;
+}
+constexpr size_t CACHE_LIMIT = 96ull << 30;  // parked bytes beyond this go back to the driver
+}  // namespace
+
+cudaError_t dev_alloc(void** out, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> g(cache_mutex());
+        auto& c = cache();
+        int best = -1;
+        for (int i = 0; i < (int)c.size(); i++)
+            if (c[i].bytes >= bytes && c[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || c[i].bytes < c[best].bytes)) best = i;
+        if (best >= 0) {
+            *out = c[best].p;
+            c.erase(c.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
+        (void)cudaGetLastError();
+        dev_cache_release();
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+void dev_free(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(cache_mutex());
+    auto& c = cache();
+    size_t parked = bytes;
+    for (auto& b : c) parked += b.bytes;
+    if (parked > CACHE_LIMIT) {
+        cudaFree(p);
+        return;
+    }
+    c.push_back({p, bytes});
+}
+void dev_cache_release() {
+    std::lock_guard<std::mutex> g(cache_mutex());
+    for (auto& b : cache()) cudaFree(b.p);
+    cache().clear();
+}
+
 int DevBuf::ensure(size_t bytes) {
     if (bytes <= cap) return CA_OK;
-    if (p) cudaFree(p);
+    if (p) dev_free(p, cap);
     p = nullptr;
     cap = 0;
     size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
+    cudaError_t e = dev_alloc(&p, want);
     if (e != cudaSuccess) {
         p = nullptr;
         set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
@@ -44,7 +105,7 @@ int DevBuf::ensure(size_t bytes) {
     return CA_OK;
 }
 void DevBuf::release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p, cap);
     p = nullptr;
     cap = 0;
 }
@@ -462,6 +523,7 @@ void ca_shutdown(void) {
     cudaDeviceSynchronize();
     Workspace& W = ws();
     W.perm.release(); W.cstart.release(); W.crow.release(); W.items.release(); W.parts.release(); W.w.release(); W.wu_prefix.release(); W.qinfo.release();
+    dev_cache_release();
     for (int i = 0; i < 8; i++)
         if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
     if (c.own_stream) { cudaStreamDestroy(c.own_stream); c.own_stream = nullptr; }
@@ -514,7 +576,7 @@ int ca_labels_create(int64_t n, int32_t m, ca_labels_t** out) {
     h->L.n = n;
     h->L.m = m;
     size_t bytes = (size_t)std::max<int64_t>(n, 1) * (size_t)m * 4;
-    cudaError_t e = cudaMalloc(&h->L.d_raw, bytes);
+    cudaError_t e = dev_alloc((void**)&h->L.d_raw, bytes);
     if (e != cudaSuccess) {
         set_error("cudaMalloc(%zu bytes) for the label matrix failed: %s", bytes, cudaGetErrorString(e));
         delete h;
@@ -555,7 +617,7 @@ int ca_labels_destroy(ca_labels_t* h) {
     if (!h) return CA_OK;
     if (ctx().inited) cudaSetDevice(ctx().device);
     Labels& L = h->L;
-    if (L.d_raw) cudaFree(L.d_raw);
+    if (L.d_raw) dev_free(L.d_raw, (size_t)std::max<int64_t>(L.n, 1) * (size_t)L.m * 4);
     L.d_min.release(); L.d_max.release(); L.d_cnt.release(); L.d_rank.release(); L.d_kcount.release();
     L.d_roff.release(); L.d_sizes.release(); L.d_lab16.release();
     L.d_spack.release(); L.d_kinfo.release();

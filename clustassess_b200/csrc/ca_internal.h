@@ -41,6 +41,11 @@ struct Ctx {
 Ctx& ctx();
 int ensure_init();
 
+// device memory comes from a small caching allocator (ca_api.cu): freed blocks are parked and reused
+cudaError_t dev_alloc(void** out, size_t bytes);
+void dev_free(void* p, size_t bytes);
+void dev_cache_release();
+
 // grow-only device buffer
 struct DevBuf {
     void* p = nullptr;
