@@ -355,7 +355,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         }
         for (int t = 0; t < nthreads; t++) {
             if (rc_t[t] != CA_OK) {
-                set_error("row-block planning failed (code %d)", rc_t[t]);
+                set_error("item planning failed (code %d)", rc_t[t]);
                 return rc_t[t];
             }
             perm_stride = std::max(perm_stride, stride_t[t]);
@@ -475,7 +475,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     c.prof[3] = ms;
     CA_CUDA(cudaEventElapsedTime(&ms, c.ev[4], c.ev[5]));
     c.prof[4] = ms;
-    c.prof[7] = (double)c.launches;  // every kernel of this call (pack, transpose, sort, row-block)
+    c.prof[7] = (double)c.launches;  // every kernel of this call (pack, transpose, sort, qinfo, wave)
     c.prof[6] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     return CA_OK;
 }

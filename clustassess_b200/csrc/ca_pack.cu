@@ -11,7 +11,7 @@
 //   sort     -> per-partition stable counting sort: perm[p] lists the cells grouped by cluster, every
 //               cluster at the padded start position chosen by the host planner (ca_plan.cpp)
 // All kernels are HBM-bound streaming passes over the M x N int32 input (coalesced loads), a few
-// percent of the row-block kernels' time.
+// percent of the wave kernel's time.
 #include <algorithm>
 
 #include "ca_internal.h"
@@ -250,7 +250,7 @@ int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t m
 //                      (shared memory) by the group size and every lane writes its cell id at
 //                      cursor + (its rank inside the group).
 // Cells of a cluster therefore stay in ascending cell order (stable), which keeps runs of equal partner
-// labels together for the row-block kernel.  Each warp is a sequential chain, so the segment count is what
+// labels together for the wave kernel.  Each warp is a sequential chain, so the segment count is what
 // buys parallelism (thousands of chains in flight).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t compact_of(const int32_t* x, int64_t i, int mn, const uint32_t* rk) {

@@ -1,15 +1,17 @@
-// ca_plan.cpp -- host-side row-block planner (pure C++, no CUDA).
+// ca_plan.cpp -- host-side item planner (pure C++, no CUDA).
 //
 // For one partition i with cluster sizes S[0..K) it decides where every cluster sits in the
-// cluster-sorted cell order perm_i and which clusters share one thread block of the row-block kernel:
+// cluster-sorted cell order perm_i and which clusters form one ITEM of the wave kernel (ca_tile.cu), i.e. are
+// processed together by one thread block and share its shared-memory tables:
 //   * every cluster's segment starts at a multiple of `align` (= cells per thread), so a thread never
 //     straddles two clusters; the tail of a segment is padding (perm = -1);
 //   * a cluster whose padded size exceeds `cap` becomes its own "streaming" item (one table row,
 //     cells processed in several sub-chunks; 32-bit counters if it has more than 65535 cells);
 //   * all other clusters are packed best-fit-decreasing into "resident" items of at most `cap`
-//     positions and at most `max_rows` table rows (their labels live in registers for a whole tile).
+//     positions and at most `max_rows` table rows (their labels live in registers for a whole work unit).
 // The reference has no counterpart: it re-scans both label vectors for every pair
 // (src/calculate_ecs.cpp:23-26); this planning is what lets one block own complete table rows.
+// Note: the wave kernel's fill traffic and phase count grow with the number of rows, whatever the packing.
 #include <algorithm>
 #include <map>
 #include <numeric>

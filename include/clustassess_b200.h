@@ -132,15 +132,15 @@ int ca_consistency_finish_dev(int64_t n, int32_t m, const double *weights_host, 
                               double *sim_dev);
 
 /* Stage timings (milliseconds, CUDA events on the library's stream) of the last batched call on this
- * thread: [0] pack (min/max, cluster sizes, compaction)  [1] relabel + transpose to the cell-major uint16
- * layout  [2] host planning (row blocks)  [3] per-partition stable counting sort  [4] row-block ECS
- * kernels  [5] finish  [6] whole call  [7] number of row-block kernel launches.  Returns how many
+ * thread: [0] pack (min/max, cluster sizes, compaction)  [1] relabel + transpose to the uint16 label
+ * layout  [2] host planning (items)  [3] per-partition stable counting sort  [4] the wave kernel (tables + ECS)
+ * [5] finish  [6] whole call  [7] number of kernel launches of the call.  Returns how many
  * entries were written (<= cap). */
 int ca_get_profile(double *ms_out, int cap);
 
 /* ---- host-only test hook --------------------------------------------------------------------------- */
 
-/* The row-block planner, exposed so that CPU tests can check its invariants without a GPU.
+/* The item planner, exposed so that CPU tests can check its invariants without a GPU.
  * sizes[k] > 0 for k < K.  align = cells per thread, cap = cells per resident block, max_rows = table rows
  * that fit in shared memory.  Outputs: cstart[k] (first padded position of cluster k), crow[k] (row of
  * cluster k inside its block), items[4*t .. 4*t+3] = {pos0, npos, nrows, wide}.  Returns the number of
