@@ -123,7 +123,7 @@ int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint3
 // work units of 16 partners
 constexpr int TL_CPT = 4;
 #ifndef CA_TL_THREADS
-#define CA_TL_THREADS 992
+#define CA_TL_THREADS 864
 #endif
 #ifndef CA_TL_BLOCKS
 #define CA_TL_BLOCKS 1

@@ -298,6 +298,15 @@ __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int
             }
             __syncwarp();
         }
+        // the consumers read this WU's cell ids and quad info (streamed from HBM, 6 bytes per position) when they
+        // reach its first phase, one or two phases from now: ask L2 for the lines already
+        if (pl.it.npos <= CAP) {
+            const int64_t off = (int64_t)pl.it.pad_ * P.perm_stride + pl.it.pos0;
+            const char* pc = reinterpret_cast<const char*>(P.perm + off);
+            const char* pq = reinterpret_cast<const char*>(reinterpret_cast<const uint2*>(P.qinfo) + (off >> 2));
+            for (int b = lane * 128; b < pl.it.npos * 4; b += 32 * 128) prefetch_l2(pc + b);
+            for (int b = lane * 128; b < pl.it.npos * 2; b += 32 * 128) prefetch_l2(pq + b);
+        }
         pl.nw = pl.w + (int)gridDim.x;
         if (pl.nw < P.nwu) {
             locate_wu(P, pl.nw, pl.ns, pl.nwend);
