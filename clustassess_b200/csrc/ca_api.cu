@@ -318,7 +318,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     int64_t perm_stride = 4;
     {   // plan every owned partition; partitions are independent, so the host threads share them
         const int nthreads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, nparts}));
-        std::vector<std::vector<Item>> items_t(nthreads);
+        std::vector<std::vector<Item>> items_s(nparts);  // per slot, the long (streaming) items first
         std::vector<int64_t> stride_t(nthreads, 4);
         std::vector<int> rc_t(nthreads, CA_OK);
         auto work = [&](int tix) {
@@ -332,6 +332,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                     h_cstart[(size_t)sl * L.kp + k] = po.cstart[k];
                     h_crow[(size_t)sl * L.kp + k] = (uint16_t)po.crow[k];
                 }
+                std::vector<Item>& v = items_s[sl];
+                v.reserve(po.pos0.size());
                 for (size_t t = 0; t < po.pos0.size(); t++) {
                     Item it;
                     it.m = p;
@@ -342,8 +344,9 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                     it.jend = ref_only >= 0 ? m_partners : m;
                     it.sa = po.sa[t];
                     it.pad_ = sl;  // perm slot
-                    items_t[tix].push_back(it);
+                    v.push_back(it);
                 }
+                std::stable_sort(v.begin(), v.end(), [](const Item& a, const Item& b) { return a.npos > b.npos; });
             }
         };
         if (nthreads == 1) {
@@ -353,22 +356,21 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
             for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
             for (auto& t : th) t.join();
         }
+        size_t total = 0;
         for (int t = 0; t < nthreads; t++) {
             if (rc_t[t] != CA_OK) {
                 set_error("item planning failed (code %d)", rc_t[t]);
                 return rc_t[t];
             }
             perm_stride = std::max(perm_stride, stride_t[t]);
-            items.insert(items.end(), items_t[t].begin(), items_t[t].end());
         }
+        // Work unit = (item, super-tile of TL_SUPER partners), numbered super-tile-major.  With the items in the order
+        // of their first partner (`parts` is ascending, so slot order is that order), the items that reach into
+        // super-tile s are a prefix of the list, and a work-unit number decodes with one prefix array.
+        for (auto& v : items_s) total += v.size();
+        items.reserve(total);
+        for (auto& v : items_s) items.insert(items.end(), v.begin(), v.end());
     }
-    // Work unit = (item, super-tile of TL_SUPER partners), numbered super-tile-major.  With the items sorted by
-    // their first partner (the long streaming items first among equals), the items that reach into super-tile s
-    // are a prefix of the list, so a work-unit number decodes with one prefix array.
-    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
-        if (a.jbeg != b.jbeg) return a.jbeg < b.jbeg;
-        return a.npos > b.npos;
-    });
     std::vector<int32_t> h_wu_prefix(1, 0);
     {
         int32_t jmax = 0;

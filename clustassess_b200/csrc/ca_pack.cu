@@ -8,7 +8,7 @@
 //               table rows in the reference and never influence ECS, so the engine drops them)
 //   sizes    -> compact cluster sizes S[p][k]
 //   relabel_transpose -> uint16 label matrix lab16[mpad/16][n][16]: 32 contiguous bytes per (cell, 16 partitions)
-//   sort     -> per-partition stable counting sort: perm[p] lists the cells grouped by cluster, every
+//   sort     -> per-partition counting sort: perm[p] lists the cells grouped by cluster, every
 //               cluster at the padded start position chosen by the host planner (ca_plan.cpp)
 // All kernels are HBM-bound streaming passes over the M x N int32 input (coalesced loads), a few
 // percent of the wave kernel's time.
@@ -241,17 +241,15 @@ int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t m
 }
 
 // ------------------------------------------------------------------------------------------------
-// stable counting sort of the cells of every owned partition by cluster.
-// A partition's cells are cut into `nseg` contiguous segments; ONE WARP sorts one (partition, segment):
+// counting sort of the cells of every owned partition by cluster.
+// A partition's cells are cut into `nseg` contiguous segments; one BLOCK sorts one (partition, segment):
 //   seg_count_kernel : per (partition, segment) histogram of the labels
 //   seg_scan_kernel  : cursor[p][seg][k] = cstart[p][k] + #cells of cluster k in earlier segments
-//   sort_kernel      : the warp walks its segment in index order, 32 cells at a time; __match_any_sync groups
-//                      equal labels inside the 32, the group's first lane advances that cluster's cursor
-//                      (shared memory) by the group size and every lane writes its cell id at
-//                      cursor + (its rank inside the group).
-// Cells of a cluster therefore stay in ascending cell order (stable), which keeps runs of equal partner
-// labels together for the wave kernel.  Each warp is a sequential chain, so the segment count is what
-// buys parallelism (thousands of chains in flight).
+//   sort_kernel      : every thread takes a cell, claims the next free position of its cluster with one
+//                      shared-memory atomic on the segment's cursor and writes its cell id there.
+// The order of the cells INSIDE a cluster is therefore arbitrary (it varies from run to run); nothing downstream
+// depends on it: a cell's ECS is a function of its (row, label) table entry only, and the quad a cell shares a
+// thread with is irrelevant to its value.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t compact_of(const int32_t* x, int64_t i, int mn, const uint32_t* rk) {
     uint32_t v = (uint32_t)(__ldg(x + i) - mn);
@@ -292,54 +290,36 @@ __global__ void seg_scan_kernel(const int32_t* __restrict__ d_cstart, int32_t kp
 }
 
 template <bool SMEM_CURSOR>
-__global__ void __launch_bounds__(128) sort_kernel(const int32_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ d_min,
+__global__ void __launch_bounds__(512) sort_kernel(const int32_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ d_min,
                                                    const uint32_t* __restrict__ d_rank, const int64_t* __restrict__ d_roff,
-                                                   int32_t kp, const int32_t* __restrict__ d_parts, int32_t nparts, int32_t nseg,
-                                                   int64_t seglen, int32_t* __restrict__ d_perm, int64_t perm_stride,
-                                                   int32_t* __restrict__ d_segcur) {
+                                                   int32_t kp, const int32_t* __restrict__ d_parts, int32_t nseg, int64_t seglen,
+                                                   int32_t* __restrict__ d_perm, int64_t perm_stride, int32_t* __restrict__ d_segcur) {
     extern __shared__ int32_t cur_sh[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t job = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
-    if (job >= (int64_t)nparts * nseg) return;
-    const int slot = (int)(job / nseg), seg = (int)(job % nseg);
+    const int slot = blockIdx.y, seg = blockIdx.x;
     const int p = d_parts[slot];
     const int32_t* x = raw + (int64_t)p * n;
     const int mn = d_min[p];
     const uint32_t* rk = d_rank ? d_rank + d_roff[p] : nullptr;
     int32_t* gcur = d_segcur + ((int64_t)slot * nseg + seg) * kp;
-    int32_t* cur = SMEM_CURSOR ? cur_sh + (size_t)wid * kp : gcur;
+    int32_t* cur = SMEM_CURSOR ? cur_sh : gcur;
     if (SMEM_CURSOR) {
-        for (int k = lane; k < kp; k += 32) cur[k] = gcur[k];
-        __syncwarp();
+        for (int k = threadIdx.x; k < kp; k += blockDim.x) cur[k] = gcur[k];
+        __syncthreads();
     }
     int32_t* out = d_perm + (int64_t)slot * perm_stride;
     const int64_t lo = (int64_t)seg * seglen, hi = min(n, lo + seglen);
     constexpr int U = 4;
-    for (int64_t base = lo; base < hi; base += 32 * U) {
+    for (int64_t base = lo + threadIdx.x; base < hi; base += (int64_t)blockDim.x * U) {
         uint32_t lab[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            int64_t i = base + u * 32 + lane;
-            lab[u] = 0xffffffffu - (uint32_t)lane;  // unique key for out-of-range lanes
-            if (i < hi) lab[u] = compact_of(x, i, mn, rk);
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            lab[u] = i < hi ? compact_of(x, i, mn, rk) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            int64_t i = base + u * 32 + lane;
-            if (base + u * 32 >= hi) break;
-            const bool valid = i < hi;
-            unsigned grp = __match_any_sync(FULL, lab[u]);
-            int leader = __ffs(grp) - 1;
-            int r = __popc(grp & ((1u << lane) - 1));
-            int32_t old = 0;
-            if (lane == leader && valid) {
-                old = cur[lab[u]];
-                cur[lab[u]] = old + __popc(grp);
-            }
-            if (!SMEM_CURSOR) __threadfence_block();
-            __syncwarp();
-            old = __shfl_sync(FULL, old, leader);
-            if (valid) out[old + r] = (int32_t)i;
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            if (i < hi) out[atomicAdd(cur + lab[u], 1)] = (int32_t)i;
         }
     }
 }
@@ -352,11 +332,11 @@ int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint3
     static DevBuf segcur;
     const size_t per_warp = (size_t)kp * 4;
     const bool smem_ok = per_warp <= 200 * 1024;
-    // segments: enough chains to fill the machine, each at least 16k cells long; the shared-memory count
+    // segments: enough blocks to fill the machine, each at least 16k cells long; the shared-memory count
     // kernel needs the label table in shared memory too, so very large cluster counts stay at one segment
     int32_t nseg = 1;
     if (smem_ok) {
-        int64_t want = (int64_t)ctx().sm_count * 24 / nparts + 1;
+        int64_t want = (int64_t)ctx().sm_count * 16 / nparts + 1;
         int64_t cap = n / 16384 + 1;
         nseg = (int32_t)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, cap), 64));
     }
@@ -373,18 +353,15 @@ int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint3
     } else {
         CA_CUDA(cudaMemcpyAsync(segcur.p, d_cstart, (size_t)nparts * kp * 4, cudaMemcpyDeviceToDevice, s));
     }
-    const int64_t jobs = (int64_t)nparts * nseg;
+    const dim3 grid((unsigned)nseg, (unsigned)nparts);
     if (smem_ok) {
-        int wpb = 4;
-        while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
-        const size_t smem = per_warp * wpb;
-        if (smem > 48 * 1024)
-            CA_CUDA(cudaFuncSetAttribute(sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sort_kernel<true><<<(unsigned)((jobs + wpb - 1) / wpb), wpb * 32, smem, s>>>(raw, n, d_min, d_rank, d_roff, kp, d_parts, nparts,
-                                                                                    nseg, seglen, d_perm, perm_stride, segcur.as<int32_t>());
+        if (per_warp > 48 * 1024)
+            CA_CUDA(cudaFuncSetAttribute(sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_warp));
+        sort_kernel<true><<<grid, 512, per_warp, s>>>(raw, n, d_min, d_rank, d_roff, kp, d_parts, nseg, seglen, d_perm, perm_stride,
+                                                      segcur.as<int32_t>());
     } else {  // cursors stay in global memory for very large cluster counts
-        sort_kernel<false><<<(unsigned)((jobs + 3) / 4), 128, 0, s>>>(raw, n, d_min, d_rank, d_roff, kp, d_parts, nparts, nseg, seglen,
-                                                                      d_perm, perm_stride, segcur.as<int32_t>());
+        sort_kernel<false><<<grid, 512, 0, s>>>(raw, n, d_min, d_rank, d_roff, kp, d_parts, nseg, seglen, d_perm, perm_stride,
+                                                segcur.as<int32_t>());
     }
     CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
     return CA_OK;

@@ -13,7 +13,6 @@
 // (src/calculate_ecs.cpp:23-26); this planning is what lets one block own complete table rows.
 // Note: the wave kernel's fill traffic and phase count grow with the number of rows, whatever the packing.
 #include <algorithm>
-#include <map>
 #include <numeric>
 
 #include "ca_internal.h"
@@ -45,7 +44,19 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
         int64_t used = 0;
     };
     std::vector<Bin> bins;
-    std::multimap<int64_t, int32_t> open;  // remaining capacity -> bin index (bins that can still take a row)
+    // open bins by remaining capacity (in units of `align`): bucket lists + a bitmap of the non-empty buckets, so
+    // "smallest remaining capacity that still holds p" is a find-next-set-bit
+    const int32_t nb = cap / align + 1;
+    std::vector<std::vector<int32_t>> bucket(nb);
+    std::vector<uint64_t> nonempty((nb + 63) / 64, 0);
+    auto find_from = [&](int32_t u) -> int32_t {  // first non-empty bucket >= u, or -1
+        for (int32_t w = u >> 6; w < (int32_t)nonempty.size(); w++) {
+            uint64_t bits = nonempty[w];
+            if (w == (u >> 6)) bits &= ~0ULL << (u & 63);
+            if (bits) return w * 64 + __builtin_ctzll(bits);
+        }
+        return -1;
+    };
     std::vector<int32_t> big;
 
     for (int32_t idx = 0; idx < k; idx++) {
@@ -59,19 +70,24 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
             big.push_back(c);
             continue;
         }
-        auto it = open.lower_bound(p);  // best fit: smallest remaining capacity that still holds p
+        const int32_t u = find_from((int32_t)(p / align));  // best fit
         int32_t b;
-        if (it == open.end()) {
+        if (u < 0) {
             b = (int32_t)bins.size();
             bins.emplace_back();
         } else {
-            b = it->second;
-            open.erase(it);
+            b = bucket[u].back();
+            bucket[u].pop_back();
+            if (bucket[u].empty()) nonempty[u >> 6] &= ~(1ULL << (u & 63));
         }
         bins[b].members.push_back(c);
         bins[b].used += p;
-        int64_t rem = cap - bins[b].used;
-        if (rem >= align && (int32_t)bins[b].members.size() < max_rows) open.emplace(rem, b);
+        const int64_t rem = cap - bins[b].used;
+        if (rem >= align && (int32_t)bins[b].members.size() < max_rows) {
+            const int32_t r = (int32_t)(rem / align);
+            bucket[r].push_back(b);
+            nonempty[r >> 6] |= 1ULL << (r & 63);
+        }
     }
 
     int64_t pos = 0;

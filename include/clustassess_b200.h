@@ -133,7 +133,7 @@ int ca_consistency_finish_dev(int64_t n, int32_t m, const double *weights_host, 
 
 /* Stage timings (milliseconds, CUDA events on the library's stream) of the last batched call on this
  * thread: [0] pack (min/max, cluster sizes, compaction)  [1] relabel + transpose to the uint16 label
- * layout  [2] host planning (items)  [3] per-partition stable counting sort  [4] the wave kernel (tables + ECS)
+ * layout  [2] host planning (items)  [3] per-partition counting sort  [4] the wave kernel (tables + ECS)
  * [5] finish  [6] whole call  [7] number of kernel launches of the call.  Returns how many
  * entries were written (<= cap). */
 int ca_get_profile(double *ms_out, int cap);
