@@ -314,3 +314,64 @@ def test_rank_sharding_sums_to_the_whole():
     assert np.abs(ecc.cpu().numpy() - ecc_ref).max() < TOL
     assert np.abs(sim.cpu().numpy().reshape(m, m) - sim_ref).max() < TOL
     dl.close()
+
+
+# ---- the wave engine's own structure (work units of 16 partners, phases, resident / streaming items) --------------
+@pytest.mark.parametrize("m", [2, 15, 16, 17, 31, 33, 49])
+def test_super_tile_boundaries_weights_and_matrix(m):
+    """Partition counts around the 16-partner super-tile and 8-partner tile boundaries, non-unit weights."""
+    rng = np.random.default_rng(100 + m)
+    n = 6000
+    base = rng.integers(0, 30, size=n)
+    L = np.stack([np.where(rng.random(n) < 0.2, rng.integers(0, 30 + p % 7, size=n), base) for p in range(m)]).astype(np.int32)
+    w = (1 + rng.poisson(1.0, size=m)).astype(np.float64)
+    ecc, sim = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), weights=w, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+    assert np.abs(ecs.weighted_element_consistency(list(L)) - oracle.weighted_element_consistency(L)).max() < TOL
+
+
+def test_agreement_against_many_partitions():
+    L, _ = synth.config("C3", m=41, n=20_000)
+    got = ecs.element_agreement(L[0], list(L[1:]))
+    want = np.mean([oracle.disjoint_ecs(L[0], L[p]) for p in range(1, 41)], axis=0)
+    assert np.abs(got - want).max() < TOL
+
+
+def test_mixed_item_kinds_in_one_job():
+    """One partition with a cluster beyond a resident item (streaming), one beyond 65535 cells (32-bit counters),
+    many tiny clusters (items with many table rows) and a partner with > 65535-cell clusters (size look-up path)."""
+    rng = np.random.default_rng(23)
+    n = 200_000
+    big = np.where(np.arange(n) < 70_000, 0, 1 + rng.integers(0, 5, size=n))          # 70k cells in one cluster
+    mid = np.where(np.arange(n) % 3 == 0, 0, 1 + rng.integers(0, 400, size=n))        # a 66k cluster + small ones
+    tiny = rng.integers(0, 5000, size=n)                                               # ~40 cells per cluster
+    L = np.stack([big, mid, tiny, rng.permutation(big), rng.integers(0, 50, size=n)]).astype(np.int32)
+    w = np.array([2.0, 1.0, 3.0, 1.0, 1.0])
+    ecc, sim = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), weights=w, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+
+
+def test_full_size_properties_config5_shape():
+    """Size-independent properties at BASELINE.json's cell count (1M cells, K up to 2000): permuting the partitions
+    and relabelling their clusters leaves ecc unchanged; duplicating the list leaves the weighted result unchanged
+    (R/ECS.R:1470-1491: merging identical partitions is an algebraic identity); 0 <= ecc <= 1."""
+    L, _ = synth.config("C5", m=12)
+    ecc = ecs.weighted_element_consistency(list(L))
+    assert ecc.min() >= 0.0 and ecc.max() <= 1.0 + 1e-12
+    rng = np.random.default_rng(5)
+    order = rng.permutation(12)
+    L2 = np.stack([(L[p].max() + 1 - L[p]) for p in order]).astype(np.int32)  # reversed label order, shuffled partitions
+    assert np.abs(ecs.weighted_element_consistency(list(L2)) - ecc).max() < TOL
+    # the list taken twice with unit weights == the list once with weight 2 each
+    twice = ecs.weighted_element_consistency(list(L) + list(L))
+    w2 = ecs.weighted_element_consistency(list(L), weights=np.full(12, 2.0))
+    assert np.abs(twice - w2).max() < TOL
+    # a sample of cells against the oracle's per-pair routine
+    idx = rng.choice(L.shape[1], size=2000, replace=False)
+    acc = np.zeros(2000)
+    for i in range(12):
+        for j in range(i + 1, 12):
+            acc += oracle.disjoint_ecs(L[i], L[j])[idx]
+    assert np.abs(ecc[idx] - acc / 66.0).max() < TOL
