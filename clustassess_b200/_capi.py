@@ -38,6 +38,7 @@ SYMBOLS = {
     "ca_agreement": (C.c_int, [_I32, _I32, C.c_int64, C.c_int32, _F64]),
     "ca_merge_identical": (C.c_int, [_I32, C.c_int64, C.c_int32, C.c_void_p, _I32, _F64, C.POINTER(C.c_int32)]),
     "ca_labels_create": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ca_labels_wrap": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ca_labels_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ca_labels_upload_col": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "ca_labels_device_ptr": (C.c_void_p, [C.c_void_p]),
@@ -96,10 +97,14 @@ def profile():
 class DeviceLabels:
     """A device-resident M x N int32 label matrix (ca_labels_t)."""
 
-    def __init__(self, n, m):
+    def __init__(self, n, m, device_ptr=None):
+        """device_ptr: wrap caller-owned device memory (M x N int32) instead of allocating."""
         self.n, self.m = int(n), int(m)
         h = C.c_void_p()
-        check(lib().ca_labels_create(self.n, self.m, C.byref(h)))
+        if device_ptr is None:
+            check(lib().ca_labels_create(self.n, self.m, C.byref(h)))
+        else:
+            check(lib().ca_labels_wrap(self.n, self.m, C.c_void_p(device_ptr), C.byref(h)))
         self._h = h
 
     def upload(self, labels):

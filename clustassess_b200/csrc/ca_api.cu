@@ -588,6 +588,22 @@ int ca_labels_create(int64_t n, int32_t m, ca_labels_t** out) {
     return CA_OK;
 }
 
+int ca_labels_wrap(int64_t n, int32_t m, void* device_matrix, ca_labels_t** out) {
+    if (!out || !device_matrix || n < 0 || m < 1 || n > 0x7ffffff0LL) {
+        set_error("ca_labels_wrap: bad arguments (n=%lld m=%d)", (long long)n, m);
+        return CA_E_ARG;
+    }
+    CA_TRY(ensure_init());
+    ca_labels* h = new (std::nothrow) ca_labels();
+    if (!h) return CA_E_NOMEM;
+    h->L.n = n;
+    h->L.m = m;
+    h->L.d_raw = static_cast<int32_t*>(device_matrix);
+    h->L.owns_raw = false;
+    *out = h;
+    return CA_OK;
+}
+
 int ca_labels_upload(ca_labels_t* h, const int32_t* labels) {
     if (!h || !labels) { set_error("ca_labels_upload: NULL argument"); return CA_E_ARG; }
     CA_TRY(ensure_init());
@@ -619,7 +635,7 @@ int ca_labels_destroy(ca_labels_t* h) {
     if (!h) return CA_OK;
     if (ctx().inited) cudaSetDevice(ctx().device);
     Labels& L = h->L;
-    if (L.d_raw) dev_free(L.d_raw, (size_t)std::max<int64_t>(L.n, 1) * (size_t)L.m * 4);
+    if (L.d_raw && L.owns_raw) dev_free(L.d_raw, (size_t)std::max<int64_t>(L.n, 1) * (size_t)L.m * 4);
     L.d_min.release(); L.d_max.release(); L.d_cnt.release(); L.d_rank.release(); L.d_kcount.release();
     L.d_roff.release(); L.d_sizes.release(); L.d_lab16.release();
     L.d_spack.release(); L.d_kinfo.release();

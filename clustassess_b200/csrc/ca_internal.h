@@ -82,6 +82,7 @@ struct Labels {
     int64_t n = 0;
     int32_t m = 0;
     int32_t* d_raw = nullptr;  // M x N int32 (partition-major)
+    bool owns_raw = true;      // false: the caller's device memory (ca_labels_wrap)
     bool ranked = false;    // min/max, ranks, compact sizes are valid
     bool prepared = false;  // ... and the uint16 label matrix (super-tile-major, see lab16_index)
     // filled by prepare():

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["shard_owner", "owned_partitions", "consistency_sharded"]
+__all__ = ["shard_owner", "owned_partitions", "consistency_sharded", "upload_sharded"]
 
 
 def shard_owner(i: int, world: int) -> int:
@@ -22,6 +22,40 @@ def shard_owner(i: int, world: int) -> int:
 
 def owned_partitions(m: int, rank: int, world: int):
     return [i for i in range(m - 1) if shard_owner(i, world) == rank]
+
+
+def upload_sharded(host_labels, device_labels, group=None):
+    """Host -> device upload of the M x N int32 label matrix, sharded over the ranks: every rank copies only its
+    contiguous block of partitions over PCIe (from pinned host memory) and the blocks are exchanged with ONE NCCL
+    all-gather over NVLink, so the whole job moves the matrix across PCIe once instead of once per GPU.
+
+    host_labels:   (M, N) int32 torch tensor in (pinned) host memory -- every rank sees the same data.
+    device_labels: (M, N) int32 CUDA tensor, filled in place on every rank.
+    M is split into world blocks of ceil(M / world) partitions; the tail block is padded inside a scratch buffer.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    m, n = host_labels.shape
+    if world == 1:
+        device_labels.copy_(host_labels, non_blocking=True)
+        return device_labels
+    blk = -(-m // world)
+    lo, hi = min(rank * blk, m), min((rank + 1) * blk, m)
+    if m % world == 0:
+        mine = device_labels[lo:hi]
+        mine.copy_(host_labels[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(device_labels.view(-1), mine.reshape(-1), group=group)
+        return device_labels
+    full = torch.empty((world * blk, n), dtype=device_labels.dtype, device=device_labels.device)
+    mine = full[rank * blk:(rank + 1) * blk]
+    if hi > lo:
+        mine[: hi - lo].copy_(host_labels[lo:hi], non_blocking=True)
+    dist.all_gather_into_tensor(full.view(-1), mine.reshape(-1).clone(), group=group)
+    device_labels.copy_(full[:m])
+    return device_labels
 
 
 def consistency_sharded(n, m, weights, partial_fn, finish_fn, group=None, want_sim=False, device=None):

@@ -111,6 +111,8 @@ int ca_merge_identical(const int32_t *labels, int64_t n, int32_t m, const double
 typedef struct ca_labels ca_labels_t;
 
 int ca_labels_create(int64_t n, int32_t m, ca_labels_t **out); /* device M x N int32, uninitialised    */
+int ca_labels_wrap(int64_t n, int32_t m, void *device_matrix, ca_labels_t **out); /* caller-owned device M x N int32
+                                                                  (e.g. filled by an NCCL all-gather)  */
 int ca_labels_upload(ca_labels_t *h, const int32_t *labels);   /* host -> device, whole matrix         */
 int ca_labels_upload_col(ca_labels_t *h, int32_t p, const int32_t *col);
 void *ca_labels_device_ptr(ca_labels_t *h);                    /* raw device matrix (int32 M x N)      */

@@ -18,7 +18,7 @@ import torch.multiprocessing as mp
 
 import oracle
 from clustassess_b200 import _capi, synth
-from clustassess_b200.distributed import consistency_sharded, owned_partitions, shard_owner
+from clustassess_b200.distributed import consistency_sharded, owned_partitions, shard_owner, upload_sharded
 
 
 def _free_port():
@@ -60,6 +60,12 @@ def _worker(rank, world, port, q):
         labels, weights = synth.config("C3", m=9, n=3000)
         m, n = labels.shape
         partial, finish = _oracle_partial(labels, weights)
+        # the sharded upload: every rank contributes its block of partitions, one all-gather rebuilds the matrix
+        for mm in (m, m - 1):  # divisible and non-divisible by the world size
+            host = torch.from_numpy(np.ascontiguousarray(labels[:mm]))
+            dev = torch.full((mm, n), -1, dtype=torch.int32)
+            upload_sharded(host, dev)
+            assert torch.equal(dev, host), "upload_sharded must rebuild the label matrix on every rank"
         ecc, sim = consistency_sharded(n, m, weights, partial, finish, want_sim=True, device="cpu")
         ref_ecc, ref_sim = oracle.weighted_element_consistency(labels, weights, calculate_sim_matrix=True)
         q.put((rank, float(np.abs(ecc.numpy() - ref_ecc).max()), float(np.abs(sim.numpy() - ref_sim).max())))
