@@ -219,27 +219,14 @@ int prepare_ranks(Labels& L) {
     CA_CUDA(cudaMemsetAsync(L.d_sizes.p, 0, (size_t)m * L.kp * 4, s));
     CA_TRY(launch_sizes(L.d_cnt.as<uint32_t>(), L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(), nullptr, nullptr, m,
                         (int32_t)max_range, L.kp, L.d_sizes.as<int32_t>(), s));
-    L.h_sizes.assign((size_t)m * L.kp, 0);
+    // the wave kernel's initial table entries and K | flags per partition
+    CA_TRY(L.d_spack.ensure((size_t)m * L.kp * 4));
+    CA_TRY(L.d_kinfo.ensure((size_t)L.mpad * 4));
+    CA_CUDA(cudaMemsetAsync(L.d_kinfo.p, 0, (size_t)L.mpad * 4, s));
+    CA_TRY(launch_spack(L.d_sizes.as<int32_t>(), L.d_kcount.as<int32_t>(), m, L.kp, L.d_spack.as<uint32_t>(), L.d_kinfo.as<int32_t>(), s));
+    L.h_sizes.resize((size_t)m * L.kp);
     CA_CUDA(cudaMemcpyAsync(L.h_sizes.data(), L.d_sizes.p, (size_t)m * L.kp * 4, cudaMemcpyDeviceToHost, s));
     CA_CUDA(cudaStreamSynchronize(s));
-    {   // tile engine: initial table entries min(size, 65535) << 16 (0xFFFF = look the size up) and K_j | flags per partition
-        std::vector<uint32_t> h16((size_t)m * L.kp);
-        std::vector<int32_t> hk(L.mpad, 0);
-        for (int32_t p = 0; p < m; p++) {
-            bool big = false;
-            for (int32_t k = 0; k < L.kp; k++) {
-                const int32_t v = L.h_sizes[(size_t)p * L.kp + k];
-                big = big || v >= 65535;
-                h16[(size_t)p * L.kp + k] = (uint32_t)std::min(v, 65535) << 16;
-            }
-            hk[p] = L.h_k[p] | (big ? (1 << 30) : 0);
-        }
-        CA_TRY(L.d_spack.ensure(h16.size() * 4));
-        CA_TRY(L.d_kinfo.ensure(hk.size() * 4));
-        CA_CUDA(cudaMemcpyAsync(L.d_spack.p, h16.data(), h16.size() * 4, cudaMemcpyHostToDevice, s));
-        CA_CUDA(cudaMemcpyAsync(L.d_kinfo.p, hk.data(), hk.size() * 4, cudaMemcpyHostToDevice, s));
-        CA_CUDA(cudaStreamSynchronize(s));
-    }
     L.ranked = true;
     return CA_OK;
 }

@@ -179,6 +179,26 @@ int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d
     return CA_OK;
 }
 
+// initial table entries of the wave kernel, spack[p][k] = min(size, 65535) << 16 (0xFFFF = look the size up),
+// and kinfo[p] = K_p | (1 << 30 if partition p has a cluster with >= 65535 cells); one block per partition
+__global__ void __launch_bounds__(256) spack_kernel(const int32_t* __restrict__ sizes, const int32_t* __restrict__ kcount, int32_t kp,
+                                                    uint32_t* __restrict__ spack, int32_t* __restrict__ kinfo) {
+    const int p = blockIdx.x;
+    int big = 0;
+    for (int k = threadIdx.x; k < kp; k += blockDim.x) {
+        const int32_t v = sizes[(int64_t)p * kp + k];
+        big |= v >= 65535;
+        spack[(int64_t)p * kp + k] = (uint32_t)min(v, 65535) << 16;
+    }
+    big = __syncthreads_or(big);
+    if (threadIdx.x == 0) kinfo[p] = kcount[p] | (big ? (1 << 30) : 0);
+}
+int launch_spack(const int32_t* d_sizes, const int32_t* d_kcount, int32_t m, int32_t kp, uint32_t* d_spack, int32_t* d_kinfo, cudaStream_t s) {
+    spack_kernel<<<(unsigned)m, 256, 0, s>>>(d_sizes, d_kcount, kp, d_spack, d_kinfo);
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // relabel + transpose: raw int32 [m][n] (partition-major)  ->  lab16 uint16 [mpad/16][n][16] (super-tile-major, lab16_index)
 // A block moves a 32-partition x 128-cell tile through shared memory: coalesced 4-byte reads along n,

@@ -92,13 +92,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spin = 0; !done; spin++) {
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 1; !done; spin++) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (spin > (1u << 24)) __trap();  // a lost copy must fail loudly, never hang the GPU
+        if ((spin & 0xfffffu) == 0) {  // every ~0.1 s: a lost copy or arrive must fail loudly, never hang the GPU
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            if (t - t0 > 120ull * 1000000000ull) __trap();  // 2 minutes: far beyond any legitimate phase
+        }
     }
 }
 
