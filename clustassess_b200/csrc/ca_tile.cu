@@ -1,34 +1,41 @@
-// ca_tile.cu -- the all-pairs ECS engine, second generation ("partner-tile" kernel, sm_100a).
+// ca_tile.cu -- the all-pairs ECS engine: the persistent "wave" kernel (sm_100a).
 //
 // What it replaces: the U(U-1)/2 pair loop of weighted_element_consistency (R/ECS.R:1473-1490) with one
 // disjointECS .Call per pair (src/calculate_ecs.cpp:22-46: contingency table, row/col sums, ratio table,
-// per-element gather) and the pair loop of element_sim_matrix_flat_disjoint (R/ECS.R:953-959).
+// per-element gather), the pair loop of element_sim_matrix_flat_disjoint (R/ECS.R:953-959) and the loop of
+// element_agreement's flat branch (R/ECS.R:1639-1647).
 //
-// Work item = (owner partition i, a set of COMPLETE clusters of i).  The cells of i are sorted by cluster
-// (perm_i, ca_pack.cu), so a block that owns whole clusters owns whole ROWS of every contingency table T_ij.
-// A thread owns a quad of consecutive cells of one cluster.  The block walks the partner partitions j in tiles
-// of 8 (one 16-byte load per cell from the cell-major uint16 label matrix fetches 8 partners into registers)
-// and, per PHASE (as many partners of the tile as fit in half of the shared memory):
+// ITEM = a set of COMPLETE clusters of an owner partition i (host planner, ca_plan.cpp).  The cells of i are
+// sorted by cluster (perm_i, ca_pack.cu), so a block that works on an item owns whole ROWS of every contingency
+// table T_ij.  A consumer thread owns a quad of consecutive positions of one cluster.
 //
-//   fill    warp 0 initialises the phase's tables with TMA bulk copies completing on an mbarrier: row r of
-//           partner j's table is a copy of the global array spack[j][b] = min(|B_j(b)|, 65535) << 16, so every
-//           32-bit entry is born as (partner cluster size : 16 | count = 0 : 16);
+// WORK UNIT = (item, super-tile of 16 partner partitions).  Work units are numbered super-tile-major and the
+// persistent blocks (one per SM) take them round-robin, so all SMs sweep the partner axis together and the labels
+// of the current super-tile -- a dense 32 N-byte slab of the super-tile-major uint16 label array, lab16_index() --
+// are fetched from HBM once and then served by L2 to every owner partition.  A thread fetches the 16 labels of a
+// cell with ONE 32-byte load (LDG.E.256) per work unit.
+//
+// PHASE = as many partners of the current 8-partner tile as fit into one of the two shared-memory buffers:
+//   fill    the producer warp initialises the phase's tables with TMA bulk copies completing on the buffer's
+//           `full` mbarrier: row r of partner j's table is a copy of the global array
+//           spack[j][b] = min(|B_j(b)|, 65535) << 16, so every 32-bit entry is born as
+//           (partner cluster size : 16 | count = 0 : 16); the same mbarrier publishes the phase's meta record;
 //   hist    for each partner and cell: red.shared.add.u32 [entry], 1 -- with a CONSTANT 1 this is the SASS
 //           instruction ATOMS.POPC.INC, which merges lanes that hit the same address in hardware (measured,
 //           tools/microbench2.cu: 1.1 SM-cycles per warp instruction whether 32 lanes hit 32 banks or one
 //           word; an add of a register value serialises instead).  Peaked label distributions -- the normal
 //           case for similar partitions -- are therefore the FAST case and need no aggregation code;
+//   sync    ONE named barrier among the consumer warps;
 //   gather  one shared load per (cell, partner) returns count and partner cluster size together;
-//           ECS = T[a][b] / max(S_i[a], S_j[b])  (calculate_ecs.cpp:35) is accumulated in registers.
+//           ECS = T[a][b] / max(S_i[a], S_j[b])  (calculate_ecs.cpp:35) is accumulated in registers; the
+//           consumer warps then release the buffer through its `empty` mbarrier.
+// Tables are row-major per partner with row stride K_j (rounded to 4), so a table takes R * K_j entries whatever
+// the largest cluster count is.
 //
-// Phases are double-buffered: while the block works on buffer p&1, the fill of buffer (p+1)&1 is in flight, and
-// ONE __syncthreads per phase (between hist and gather) is the only block-wide barrier; the mbarrier of the
-// next buffer also publishes the next phase's meta data.  Tables are row-major per partner with row stride
-// K_j (rounded to 4), so a table takes R * K_j entries whatever the largest cluster count is.
-// "Resident" items (<= 4096 positions) keep per-cell accumulators in registers over ALL partners and add to
-// ecc once; clusters larger than that are "streaming" items: one row, both passes stream the cells from global
-// memory, accumulators are flushed per phase; with more than 65535 cells the entries are plain 32-bit counts
-// and the partner sizes come from global memory.
+// A work unit of a RESIDENT item (<= TL_CAP positions) adds its per-cell sums to ecc once, when the block moves on
+// to its next work unit; clusters larger than TL_CAP are "streaming" items: one row, both passes stream the cells
+// from global memory in chunks, sums are added per phase; with more than 65535 cells the entries are plain 32-bit
+// counts and the partner sizes come from global memory.
 //
 // The division is T * r with r = 1/max from rcp.approx.ftz.f64 + one Newton step (relative error < 1e-13);
 // the batched path has to meet 1e-9 absolute, the per-pair entry points (ca_pair.cu) keep the IEEE division.
