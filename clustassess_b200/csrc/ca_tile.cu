@@ -47,6 +47,10 @@
 
 namespace ca {
 
+#ifndef CA_UNROLL_HIST
+#define CA_UNROLL_HIST 1
+#endif
+static constexpr int UNROLL_HIST = CA_UNROLL_HIST;  // partners per trip of the histogram loop (tuning builds)
 static constexpr unsigned FULL = 0xffffffffu;
 static constexpr int NC = TL_THREADS;       // consumer threads (a quad of cells each)
 static constexpr int NT = NC + 32;          // + the producer warp
@@ -97,6 +101,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     unsigned long long t0 = 0;
@@ -106,6 +111,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
+        if (BACKOFF && !done) __nanosleep(200);  // the producer is usually far ahead: leave the issue slots to the consumers
         if ((spin & 0xfffffu) == 0) {  // every ~0.1 s: a lost copy or arrive must fail loudly, never hang the GPU
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -159,7 +165,7 @@ __device__ __forceinline__ void with_slot_words(const uint4 (&L)[4], int jt, F&&
 }
 
 __device__ __forceinline__ void hist_quad(uint32_t meta, const Phase ph, const uint4 (&L)[4], uint32_t rowidx, int nvalid) {
-#pragma unroll 1
+#pragma unroll UNROLL_HIST
     for (int q = 0; q < ph.cnt; q++) {
         const int jt = ph.g0 + q;
         const uint32_t sel = (jt & 1) ? 0x4432u : 0x4410u;
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
             const bool last = pl.w >= P.nwu;
             PhasePlan pp;
             if (!last) pp = plan_compute(P, sbase, half, lane, pl);
-            if (p >= 2) mbar_wait(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u);  // consumers are done with buffer b
+            if (p >= 2) mbar_wait<true>(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u);  // consumers are done with buffer b
             if (last) {
                 plan_terminal(sbase, b, lane);
                 break;
