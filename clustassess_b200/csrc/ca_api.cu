@@ -358,21 +358,29 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         items.reserve(total);
         for (auto& v : items_s) items.insert(items.end(), v.begin(), v.end());
     }
-    std::vector<int32_t> h_wu_prefix(1, 0);
-    {
+    // Two kinds of items, two launches of the wave kernel (each kind gets its own register allocation): streaming
+    // items (one cluster with more than TL_CAP cells) first, resident items second.  Both lists keep the order of
+    // the first partner, so "the items that reach into super-tile s" is a prefix of each.
+    std::vector<Item> items_kind[2];  // [0] resident, [1] streaming
+    for (const Item& it : items) items_kind[it.npos > TL_CAP ? 1 : 0].push_back(it);
+    std::vector<int32_t> h_wu_prefix_kind[2];
+    for (int kind = 0; kind < 2; kind++) {
+        std::vector<int32_t>& pre = h_wu_prefix_kind[kind];
+        const std::vector<Item>& v = items_kind[kind];
+        pre.assign(1, 0);
         int32_t jmax = 0;
-        for (const Item& it : items) jmax = std::max(jmax, it.jend);
+        for (const Item& it : v) jmax = std::max(jmax, it.jend);
         const int32_t nsuper = (jmax + TL_SUPER - 1) / TL_SUPER;
         size_t k = 0;
         int64_t tot = 0;
         for (int32_t sp = 0; sp < nsuper; sp++) {
-            while (k < items.size() && items[k].jbeg < (sp + 1) * TL_SUPER) k++;
+            while (k < v.size() && v[k].jbeg < (sp + 1) * TL_SUPER) k++;
             tot += (int64_t)k;
             if (tot > 0x7fffff00LL) {
                 set_error("too many work units (%lld)", (long long)tot);
                 return CA_E_UNSUPPORTED;
             }
-            h_wu_prefix.push_back((int32_t)tot);
+            pre.push_back((int32_t)tot);
         }
     }
     std::vector<double> h_w(L.mpad + 8, 0.0);
@@ -393,7 +401,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
 
     // ---- upload plan, sort ------------------------------------------------------------------------
     Workspace& W = ws();
-    CA_TRY(W.wu_prefix.ensure(h_wu_prefix.size() * 4));
+    const size_t npre0 = h_wu_prefix_kind[0].size(), npre1 = h_wu_prefix_kind[1].size();
+    CA_TRY(W.wu_prefix.ensure((npre0 + npre1) * 4));
     CA_TRY(W.qinfo.ensure((size_t)std::max(nparts, 1) * perm_stride * 2));
     CA_TRY(W.perm.ensure((size_t)std::max(nparts, 1) * perm_stride * 4));
     CA_TRY(W.cstart.ensure(h_cstart.size() * 4));
@@ -401,12 +410,15 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     CA_TRY(W.items.ensure(std::max<size_t>(items.size(), 1) * sizeof(Item)));
     CA_TRY(W.parts.ensure((size_t)std::max(nparts, 1) * 4));
     CA_TRY(W.w.ensure(h_w.size() * 8));
-    CA_CUDA(cudaMemcpyAsync(W.wu_prefix.p, h_wu_prefix.data(), h_wu_prefix.size() * 4, cudaMemcpyHostToDevice, s));
+    CA_CUDA(cudaMemcpyAsync(W.wu_prefix.p, h_wu_prefix_kind[0].data(), npre0 * 4, cudaMemcpyHostToDevice, s));
+    CA_CUDA(cudaMemcpyAsync(W.wu_prefix.as<int32_t>() + npre0, h_wu_prefix_kind[1].data(), npre1 * 4, cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaMemcpyAsync(W.cstart.p, h_cstart.data(), h_cstart.size() * 4, cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaMemcpyAsync(W.crow.p, h_crow.data(), h_crow.size() * 2, cudaMemcpyHostToDevice, s));
     if (nparts) CA_CUDA(cudaMemcpyAsync(W.parts.p, parts.data(), (size_t)nparts * 4, cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaMemcpyAsync(W.w.p, h_w.data(), h_w.size() * 8, cudaMemcpyHostToDevice, s));
-    if (!items.empty()) CA_CUDA(cudaMemcpyAsync(W.items.p, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, s));
+    for (int kind = 0, off = 0; kind < 2; off += (int)items_kind[kind].size(), kind++)
+        if (!items_kind[kind].empty())
+            CA_CUDA(cudaMemcpyAsync(W.items.as<Item>() + off, items_kind[kind].data(), items_kind[kind].size() * sizeof(Item), cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaEventRecord(c.ev[3], s));
     CA_TRY(launch_sort(L.d_raw, n, L.d_min.as<int32_t>(), L.identity ? nullptr : L.d_rank.as<uint32_t>(),
                        L.d_roff.as<int64_t>(), W.cstart.as<int32_t>(), L.kp, W.parts.as<int32_t>(), nparts,
@@ -434,8 +446,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     T.items = W.items.as<Item>();
     T.wu_prefix = W.wu_prefix.as<int32_t>();
     T.qinfo = W.qinfo.as<uint32_t>();
-    T.nsuper = (int32_t)h_wu_prefix.size() - 1;
-    T.nwu = h_wu_prefix.back();
+    T.nsuper = T.nwu = T.streaming = 0;
     T.ecc = d_ecc;
     T.sim = d_sim;
     T.perm_stride = perm_stride;
@@ -452,7 +463,14 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     for (int32_t p = 0; p < mw; p++)
         if (h_w[p] != 1.0) T.unit_w = 0;
     CA_TRY(launch_qinfo(T, W.parts.as<int32_t>(), nparts, s));
-    CA_TRY(launch_tile(T, s));
+    for (int kind = 1; kind >= 0; kind--) {  // the long streaming items first
+        T.items = W.items.as<Item>() + (kind == 1 ? items_kind[0].size() : 0);
+        T.wu_prefix = W.wu_prefix.as<int32_t>() + (kind == 1 ? npre0 : 0);
+        T.nsuper = (int32_t)h_wu_prefix_kind[kind].size() - 1;
+        T.nwu = h_wu_prefix_kind[kind].back();
+        T.streaming = kind;
+        CA_TRY(launch_tile(T, s));
+    }
     CA_CUDA(cudaEventRecord(c.ev[5], s));
     CA_CUDA(cudaStreamSynchronize(s));
     float ms;

@@ -153,6 +153,7 @@ struct TileParams {
     int64_t perm_stride;
     int32_t m, mpad, kp;
     int32_t nsuper, nwu;      // super-tiles, work units
+    int32_t streaming;        // kind of the items of this launch: 0 resident (<= TL_CAP positions), 1 streaming
     int32_t smem_bytes;       // dynamic shared memory per block
     double inv_norm;
     int32_t unit_w;           // every weight is exactly 1

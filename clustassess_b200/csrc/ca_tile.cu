@@ -453,7 +453,7 @@ __device__ __forceinline__ void plan_advance(const TileParams& P, Planner& pl, c
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
 
-template <bool WANT_ECC, bool WANT_SIM, bool UNITW>
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool STREAMING>
 __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
     const int tid = (int)threadIdx.x - 32;  // consumer thread id: owns positions [4 tid, 4 tid + 4) of a resident item
     // the current WU, as seen by every thread (everything else is re-read from the phase's meta record)
     int m = -1;
-    bool resident = true;
+    constexpr bool resident = !STREAMING;  // a launch holds work units of one kind only: two register allocations
     int4 cell = make_int4(-1, -1, -1, -1);
     int nvalid = 0;
     uint32_t rowidx = 0, sa = 0;
@@ -527,7 +527,6 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
             flush_acc();
             m = (int)lds_u32(meta + META_M);
             const int npos = (int)lds_u32(meta + META_NPOS);
-            resident = npos <= CAP;
             const int64_t off = (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
             const int32_t* perm = P.perm + off;
             sa = lds_u32(meta + META_SA);
@@ -561,11 +560,15 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         } else {
             const int npos = (int)lds_u32(meta + META_NPOS);
             const int32_t* perm = P.perm + (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
-            for (int cb = tid * 4; cb < npos; cb += CAP) {
-                const int4 cl = __ldg(reinterpret_cast<const int4*>(perm + cb));
-                const int nv = (cl.x >= 0) + (cl.y >= 0) + (cl.z >= 0) + (cl.w >= 0);
-                load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), cl, L);
-                hist_quad(meta, ph, L, 0u, nv);
+            const uint16_t* labj = P.lab16 + lab16_index(P.n, 0, ph.j0);
+            for (int cb = tid * 4; cb < npos; cb += 2 * CAP) {  // two chunks per trip: their loads are in flight together
+                const int4 none = make_int4(-1, -1, -1, -1);
+                const int4 ca = __ldg(reinterpret_cast<const int4*>(perm + cb));
+                const int4 cb4 = cb + CAP < npos ? __ldg(reinterpret_cast<const int4*>(perm + cb + CAP)) : none;
+                load_quad(labj, ca, L);
+                load_quad(labj, cb4, Lh);
+                hist_quad(meta, ph, L, 0u, (ca.x >= 0) + (ca.y >= 0) + (ca.z >= 0) + (ca.w >= 0));
+                hist_quad(meta, ph, Lh, 0u, (cb4.x >= 0) + (cb4.y >= 0) + (cb4.z >= 0) + (cb4.w >= 0));
             }
         }
         consumer_sync();  // the tables of phase p are complete; every consumer has left phase p-1
@@ -656,15 +659,22 @@ int launch_qinfo(const TileParams& p, const int32_t* d_parts, int32_t nparts, cu
     return CA_OK;
 }
 
-template <bool E, bool S, bool U>
-static int launch_wave_t(const TileParams& p, cudaStream_t s) {
-    auto kern = wave_kernel<E, S, U>;
+template <bool E, bool S, bool U, bool STREAMING>
+static int launch_wave_k(const TileParams& p, cudaStream_t s) {
+    if (p.nwu <= 0) return CA_OK;
+    auto kern = wave_kernel<E, S, U, STREAMING>;
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
     const int grid = std::min<int>(ca::ctx().sm_count * TL_BLOCKS, p.nwu);
     kern<<<(unsigned)grid, NT, (size_t)p.smem_bytes, s>>>(p);
     CA_CUDA(cudaGetLastError());
     ca::ctx().launches++;
     return CA_OK;
+}
+
+// p.streaming selects the kind of work units in p.items: the streaming kernel first (long items), then the resident one
+template <bool E, bool S, bool U>
+static int launch_wave_t(const TileParams& p, cudaStream_t s) {
+    return p.streaming ? launch_wave_k<E, S, U, true>(p, s) : launch_wave_k<E, S, U, false>(p, s);
 }
 
 int launch_tile(const TileParams& p, cudaStream_t s) {
