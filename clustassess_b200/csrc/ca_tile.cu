@@ -125,6 +125,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ uint4 ldg_u4(const uint16_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// exact for every uint32: 2^52 + v is representable and the subtraction is exact
+__device__ __forceinline__ double u32_to_f64(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+
 // labels of a whole super-tile (16 partners) for a quad of cells: ONE 32-byte load per cell (SASS LDG.E.256, sm_100+),
 // i.e. one L2 sector request per (cell, work unit); lo = partners [16 s, 16 s + 8), hi = [16 s + 8, 16 s + 16)
 __device__ __forceinline__ void ldg_256(const uint16_t* p, uint4& lo, uint4& hi) {
@@ -211,14 +214,16 @@ __device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, 
                 sb = e >> 16;
                 if (lookup && sb == 0xffffu) sb = (uint32_t)__ldg(szg + lab);
             }
-            const double mx = (double)max(sa, sb);
+            // uint32 -> double through the 2^52 trick (one DADD on the fp64 pipe) instead of I2F.F64: with two I2F and
+            // the MUFU per (cell, partner) the gather is bound by the quarter-rate XU pipe (ncu: 85 % busy)
+            const double mx = u32_to_f64(max(sa, sb));
             double r;
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
             r = fma(fma(-mx, r, 1.0), r, r);  // one Newton step: relative error < 1e-13
             if (UNITW && !WANT_SIM) {
-                a = fma((double)count, r, a);
+                a = fma(u32_to_f64(count), r, a);
             } else {
-                const double v = (double)count * r;
+                const double v = u32_to_f64(count) * r;
                 a = UNITW ? a + v : fma(v, wj, a);
                 if (WANT_SIM) es += v;
             }
@@ -513,6 +518,9 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         }
     };
 
+#ifdef CA_ABLATE
+    long long t_all = clock64(), u_all = 0;  // tuning builds: cycles and (padded) units of this block
+#endif
     uint32_t p = 0;
     for (;; p++) {
         const uint32_t b = p & 1u;
@@ -602,9 +610,19 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         }
         prev = ph;
         prev_m = m;
+#ifdef CA_ABLATE
+        u_all += (long long)lds_u32(meta + META_NPOS) * ph.cnt;
+#endif
         __syncwarp();
         if (lane == 0) mbar_arrive(sbase + SM_MBAR + 16 + b * 8u);  // this warp is done with buffer b (and its meta record)
     }
+#ifdef CA_ABLATE
+    if ((blockIdx.x == 3 || blockIdx.x == 77) && threadIdx.x == 64) {
+        t_all = clock64() - t_all;
+        printf("[kind %s] block %d: %lld cycles, %lld padded units (%.3f cycles/unit), %u phases (%.0f units/phase)\n",
+               STREAMING ? "streaming" : "resident", blockIdx.x, t_all, u_all, (double)t_all / (double)(u_all + 1), p, (double)u_all / (p + 1.0));
+    }
+#endif
     flush_acc();
     if (WANT_SIM) {
         consumer_sync();
