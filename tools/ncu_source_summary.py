@@ -12,6 +12,8 @@ hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 col = {n: i for i, n in enumerate(hdr)}
 data = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+seen = set()  # some ncu versions print every SASS line twice (once per view): keep the first of each address
+data = [r for r in data if not (r[0] in seen or seen.add(r[0]))]
 
 
 def f(r, name):
