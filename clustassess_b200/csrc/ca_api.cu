@@ -213,7 +213,7 @@ int prepare_ranks(Labels& L) {
         set_error("a partition has %d clusters; the engine supports at most %d", L.kmax, K_LIMIT);
         return CA_E_UNSUPPORTED;
     }
-    L.kp = std::max(8, (L.kmax + 7) & ~7);
+    L.kp = std::max(8, (L.kmax + 1 + 7) & ~7);  // + the pad column
     L.mpad = (m + 31) & ~31;
     CA_TRY(L.d_sizes.ensure((size_t)m * L.kp * 4));
     CA_CUDA(cudaMemsetAsync(L.d_sizes.p, 0, (size_t)m * L.kp * 4, s));
@@ -239,10 +239,10 @@ int prepare_labels(Labels& L) {
     const int64_t n = L.n;
     CA_TRY(prepare_ranks(L));
     CA_CUDA(cudaEventRecord(c.ev[1], s));
-    CA_TRY(L.d_lab16.ensure((size_t)std::max<int64_t>(n, 1) * L.mpad * 2));
+    CA_TRY(L.d_lab16.ensure((size_t)(n + 1) * L.mpad * 2));  // n cells + the pad cell
     CA_TRY(launch_relabel_transpose(L.d_raw, n, m, L.mpad, L.d_min.as<int32_t>(),
                                     L.identity ? nullptr : L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(),
-                                    L.d_lab16.as<uint16_t>(), s));
+                                    L.d_kcount.as<int32_t>(), L.d_lab16.as<uint16_t>(), s));
     CA_CUDA(cudaEventRecord(c.ev[2], s));
     CA_CUDA(cudaStreamSynchronize(s));
     L.prepared = true;
@@ -457,6 +457,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     T.inv_norm = inv_norm;
     T.unit_w = 1;
     T.dbg = 0;
+    T.sel[0] = 0x4410u;
+    T.sel[1] = 0x4432u;
 #ifdef CA_ABLATE
     if (const char* e = getenv("CA_ABLATE")) T.dbg = atoi(e);
 #endif

@@ -98,11 +98,14 @@ int prepare_ranks(Labels& L);
 int prepare_labels(Labels& L);
 
 // Compact labels live in a uint16 array laid out super-tile-major: the 16 partitions [16 t, 16 t + 16) of cell c
-// are the 32 contiguous bytes at element index (t * n + c) * 16.  All cells' labels for one super-tile are thus one
-// DENSE 32 n-byte slab (an L2 line holds 4 cells), which is what lets a whole super-tile stay L2-resident while
-// every owner partition sweeps over it; with a cell-major [n][mpad] layout the same sectors sit 2 mpad bytes apart,
-// each in its own 128-byte L2 line, and the effective footprint is four times larger than the cache.
-__host__ __device__ inline int64_t lab16_index(int64_t n, int64_t cell, int32_t p) { return ((int64_t)(p >> 4) * n + cell) * 16 + (p & 15); }
+// are the 32 contiguous bytes at element index (t * (n + 1) + c) * 16.  All cells' labels for one super-tile are
+// thus one DENSE 32 (n + 1)-byte slab (an L2 line holds 4 cells), which is what lets a whole super-tile stay
+// L2-resident while every owner partition sweeps over it; with a cell-major [n][mpad] layout the same sectors sit
+// 2 mpad bytes apart, each in its own 128-byte L2 line, and the effective footprint is four times larger than the
+// cache.  Cell n is the PAD CELL: its label in partition p is K_p, one past the last real cluster.  Padding
+// positions of the cluster-sorted order read it, so their histogram increments land in a spare table column that
+// no real cell ever gathers from, and the inner loops need no validity tests.
+__host__ __device__ inline int64_t lab16_index(int64_t n, int64_t cell, int32_t p) { return ((int64_t)(p >> 4) * (n + 1) + cell) * 16 + (p & 15); }
 
 // kernels' host launchers -----------------------------------------------------------------------------
 // ca_pack.cu
@@ -116,7 +119,7 @@ int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d
                  const int32_t* d_max, int32_t m, int32_t max_range, int32_t kp, int32_t* d_sizes, cudaStream_t s);
 int launch_spack(const int32_t* d_sizes, const int32_t* d_kcount, int32_t m, int32_t kp, uint32_t* d_spack, int32_t* d_kinfo, cudaStream_t s);
 int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t mpad, const int32_t* d_min,
-                             const uint32_t* d_rank, const int64_t* d_roff, uint16_t* d_lab16, cudaStream_t s);
+                             const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_kcount, uint16_t* d_lab16, cudaStream_t s);
 int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
                 const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
                 int64_t perm_stride, cudaStream_t s);
@@ -136,11 +139,11 @@ constexpr int TL_CAP = TL_CPT * TL_THREADS;  // positions per resident item
 constexpr int TL_MAX_ROWS = 1024;
 constexpr int TL_SUPER = 16;                 // partners per work unit: one 32-byte label sector per cell
 struct TileParams {
-    const uint16_t* lab16;    // [mpad/16][n][16] compact labels, see lab16_index()
+    const uint16_t* lab16;    // [mpad/16][n + 1][16] compact labels (cell n = the pad cell), see lab16_index()
     int64_t n;
     const int32_t* perm;      // [m_slots][perm_stride] cluster-sorted cell ids, -1 = padding
     const int32_t* sizes;     // [m][kp] cluster sizes
-    const uint32_t* spack;    // [m][kp] min(size, 65535) << 16: the initial value of a table entry (size : count = 0)
+    const uint32_t* spack;    // [m][kp] min(size, 65535) << 16: the initial value of a table entry (size : count = 0); 1 << 16 beyond K_p
     const int32_t* kinfo;     // [mpad] K_j | (1 << 30 if partition j has a cluster with >= 65535 cells), 0 beyond m
     const void* zeros;        // >= 256 KB of zero bytes: source of the bulk copy that clears the tables
     const uint16_t* crow;     // [m_slots][kp] row of a cluster inside its block
@@ -157,6 +160,7 @@ struct TileParams {
     int32_t smem_bytes;       // dynamic shared memory per block
     double inv_norm;
     int32_t unit_w;           // every weight is exactly 1
+    uint32_t sel[2];          // PRMT selectors of a label word's low / high half (0x4410, 0x4432), see slot_label()
     int32_t dbg;              // ablation switches of -DCA_ABLATE tuning builds (tools/build_variant.sh), else 0
 };
 int launch_tile(const TileParams& p, cudaStream_t s);

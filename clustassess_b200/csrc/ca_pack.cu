@@ -7,7 +7,7 @@
 //   rank     -> dense rank of every used label (unused labels inside the range only produce all-zero
 //               table rows in the reference and never influence ECS, so the engine drops them)
 //   sizes    -> compact cluster sizes S[p][k]
-//   relabel_transpose -> uint16 label matrix lab16[mpad/16][n][16]: 32 contiguous bytes per (cell, 16 partitions)
+//   relabel_transpose -> uint16 label matrix lab16[mpad/16][n + 1][16]: 32 contiguous bytes per (cell, 16 partitions)
 //   sort     -> per-partition counting sort: perm[p] lists the cells grouped by cluster, every
 //               cluster at the padded start position chosen by the host planner (ca_plan.cpp)
 // All kernels are HBM-bound streaming passes over the M x N int32 input (coalesced loads), a few
@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(256) spack_kernel(const int32_t* __restrict__ 
     for (int k = threadIdx.x; k < kp; k += blockDim.x) {
         const int32_t v = sizes[(int64_t)p * kp + k];
         big |= v >= 65535;
-        spack[(int64_t)p * kp + k] = (uint32_t)min(v, 65535) << 16;
+        // beyond K_p (the pad column and the row's alignment slack): size 1, so that a gather of it never divides by 0
+        spack[(int64_t)p * kp + k] = k < kcount[p] ? (uint32_t)min(v, 65535) << 16 : 1u << 16;
     }
     big = __syncthreads_or(big);
     if (threadIdx.x == 0) kinfo[p] = kcount[p] | (big ? (1 << 30) : 0);
@@ -200,7 +201,7 @@ int launch_spack(const int32_t* d_sizes, const int32_t* d_kcount, int32_t m, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// relabel + transpose: raw int32 [m][n] (partition-major)  ->  lab16 uint16 [mpad/16][n][16] (super-tile-major, lab16_index)
+// relabel + transpose: raw int32 [m][n] (partition-major)  ->  lab16 uint16 [mpad/16][n + 1][16] (super-tile-major, lab16_index; cell n = pad cell with label K_p)
 // A block moves a 32-partition x 128-cell tile through shared memory: coalesced 4-byte reads along n,
 // 32-byte writes along the partition axis.
 // ------------------------------------------------------------------------------------------------
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* _
                                                                 const int32_t* __restrict__ d_min,
                                                                 const uint32_t* __restrict__ d_rank,
                                                                 const int64_t* __restrict__ d_roff,
+                                                                const int32_t* __restrict__ d_kcount,
                                                                 uint16_t* __restrict__ lab16) {
     __shared__ uint16_t tile[TP][TC + 2];
     const int64_t c0 = (int64_t)blockIdx.x * TC;
@@ -227,6 +229,8 @@ __global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* _
                 if (c < n) {
                     v = (uint32_t)(__ldg(x + c) - mn);
                     if (rk) v = __ldg(rk + v);
+                } else if (c == n) {
+                    v = (uint32_t)d_kcount[p];  // the pad cell
                 }
                 tile[pp][lane + 32 * q] = (uint16_t)v;
             }
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* _
     __syncthreads();
     const int cell = threadIdx.x >> 1, half = threadIdx.x & 1;
     const int64_t c = c0 + cell;
-    if (c < n) {
+    if (c <= n) {
         uint32_t wds[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -252,10 +256,10 @@ __global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* _
 }
 
 int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t mpad, const int32_t* d_min,
-                             const uint32_t* d_rank, const int64_t* d_roff, uint16_t* d_lab16, cudaStream_t s) {
+                             const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_kcount, uint16_t* d_lab16, cudaStream_t s) {
     if (n == 0) return CA_OK;
-    dim3 grid((unsigned)((n + TC - 1) / TC), (unsigned)(mpad / TP));
-    relabel_transpose_kernel<<<grid, 256, 0, s>>>(raw, n, m, mpad, d_min, d_rank, d_roff, d_lab16);
+    dim3 grid((unsigned)((n + 1 + TC - 1) / TC), (unsigned)(mpad / TP));  // n cells + the pad cell
+    relabel_transpose_kernel<<<grid, 256, 0, s>>>(raw, n, m, mpad, d_min, d_rank, d_roff, d_kcount, d_lab16);
     CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
     return CA_OK;
 }

@@ -62,10 +62,14 @@ static_assert(TL_CPT == 4, "a thread owns one quad of cells");
 static constexpr int SM_MBAR = 0;       // four mbarriers: full[2] (tables initialised + meta published), empty[2] (buffer released)
 static constexpr int SM_META = 32;      // two Meta records
 static constexpr int META_BYTES = 224;
-static constexpr int META_J0 = 0, META_G0 = 4, META_CNT = 8, META_FIRST = 12, META_M = 16, META_POS0 = 20, META_NPOS = 24,
-                     META_NROWS = 28, META_SA = 32, META_SLOT = 36, META_JHI = 40, META_TB = 64, META_RB = 96, META_KK = 128,
-                     META_W = 160;  // [8] double: weights of the phase's partners
-static constexpr int SM_SIMACC = 480;   // [2][8] double: sum of ECS over the block's cells, per buffer and partner
+// header word: cnt | g0 << 8 | first << 16 | big << 17 (read together with j0 by one 8-byte load); everything per partner
+// is indexed by TILE SLOT (partner j0 + slot), so the consumers' unrolled slot bodies address it with immediates
+static constexpr int META_HDR = 0, META_J0 = 4, META_M = 16, META_POS0 = 20, META_NPOS = 24, META_NROWS = 28, META_SA = 32,
+                     META_SLOT = 36, META_JHI = 40,
+                     META_TR = 64,   // [8] {table base, row bytes}
+                     META_KK = 128,  // [8] K_j | flags
+                     META_W = 160;   // [8] double: weights
+static constexpr int SM_SIMACC = 480;   // [2][8] double: sum of ECS over the block's cells, per buffer and tile slot
 static constexpr int SM_PLAN = 608;     // at +112 K_j | flags, at +176 the weights of the current super-tile's 16 partners (producer's scratch)
 static constexpr int SM_DYN = 1024;     // two table buffers
 static constexpr uint32_t KK_BIG = 1u << 30;  // partner has a cluster with >= 65535 cells
@@ -74,6 +78,11 @@ static constexpr uint32_t KK_BIG = 1u << 30;  // partner has a cluster with >= 6
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
 __device__ __forceinline__ double lds_f64(uint32_t a) {
@@ -135,20 +144,20 @@ __device__ __forceinline__ void ldg_256(const uint16_t* p, uint4& lo, uint4& hi)
                  : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                  : "l"(p));
 }
-// (padding positions load cell 0's labels: never used, every use is guarded by the quad's valid count)
-__device__ __forceinline__ void load_quad_super(const uint16_t* __restrict__ lab16s, int4 cell, uint4 (&Lo)[4], uint4 (&Hi)[4]) {
-    ldg_256(lab16s + (int64_t)max(cell.x, 0) * 16, Lo[0], Hi[0]);
-    ldg_256(lab16s + (int64_t)max(cell.y, 0) * 16, Lo[1], Hi[1]);
-    ldg_256(lab16s + (int64_t)max(cell.z, 0) * 16, Lo[2], Hi[2]);
-    ldg_256(lab16s + (int64_t)max(cell.w, 0) * 16, Lo[3], Hi[3]);
+// padding positions (cell id -1) read the pad cell n, whose label in partition p is K_p: the spare table column
+__device__ __forceinline__ int64_t cell_or_pad(int cell, uint32_t n) { return (int64_t)min((uint32_t)cell, n); }
+__device__ __forceinline__ void load_quad_super(const uint16_t* __restrict__ lab16s, uint32_t n, int4 cell, uint4 (&Lo)[4], uint4 (&Hi)[4]) {
+    ldg_256(lab16s + cell_or_pad(cell.x, n) * 16, Lo[0], Hi[0]);
+    ldg_256(lab16s + cell_or_pad(cell.y, n) * 16, Lo[1], Hi[1]);
+    ldg_256(lab16s + cell_or_pad(cell.z, n) * 16, Lo[2], Hi[2]);
+    ldg_256(lab16s + cell_or_pad(cell.w, n) * 16, Lo[3], Hi[3]);
 }
 // labels of the 8 partners [j0, j0+8) for a quad of cells: one 16-byte load per cell (lab16j = lab16 + lab16_index(n, 0, j0))
-__device__ __forceinline__ void load_quad(const uint16_t* __restrict__ lab16j, int4 cell, uint4 (&L)[4]) {
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    L[0] = cell.x >= 0 ? ldg_u4(lab16j + (int64_t)cell.x * 16) : z;
-    L[1] = cell.y >= 0 ? ldg_u4(lab16j + (int64_t)cell.y * 16) : z;
-    L[2] = cell.z >= 0 ? ldg_u4(lab16j + (int64_t)cell.z * 16) : z;
-    L[3] = cell.w >= 0 ? ldg_u4(lab16j + (int64_t)cell.w * 16) : z;
+__device__ __forceinline__ void load_quad(const uint16_t* __restrict__ lab16j, uint32_t n, int4 cell, uint4 (&L)[4]) {
+    L[0] = ldg_u4(lab16j + cell_or_pad(cell.x, n) * 16);
+    L[1] = ldg_u4(lab16j + cell_or_pad(cell.y, n) * 16);
+    L[2] = ldg_u4(lab16j + cell_or_pad(cell.z, n) * 16);
+    L[3] = ldg_u4(lab16j + cell_or_pad(cell.w, n) * 16);
 }
 
 struct Phase {
@@ -156,54 +165,111 @@ struct Phase {
 };
 
 // ---- histogram / gather of one phase for a quad of cells -------------------------------------------------------
-// The 4 words that hold tile slot jt's label of the quad's cells are picked by a block-uniform switch (the body is
-// inlined four times), the half by one PRMT per label with a uniform selector.
+// A phase covers the tile slots [g0, g0 + cnt) of the 8-partner tile whose labels sit in L.  The slot bodies are
+// instantiated per slot (the label's word and half are compile-time, the slot's meta entries are at immediate
+// offsets) and entered Duff-style: one jump to slot g0, then one compare-and-branch per slot.  There are no
+// validity tests: padding positions carry the pad label (ca_internal.h, lab16_index) and count into a spare column.
+template <int V> struct Slot { static constexpr int value = V; };
 template <typename F>
-__device__ __forceinline__ void with_slot_words(const uint4 (&L)[4], int jt, F&& f) {
-    switch (jt >> 1) {
-        case 0: f(L[0].x, L[1].x, L[2].x, L[3].x); break;
-        case 1: f(L[0].y, L[1].y, L[2].y, L[3].y); break;
-        case 2: f(L[0].z, L[1].z, L[2].z, L[3].z); break;
-        default: f(L[0].w, L[1].w, L[2].w, L[3].w); break;
+__device__ __forceinline__ void for_slots(int g0, int cnt, F&& f) {
+    int left = cnt;
+    switch (g0) {
+        case 0: f(Slot<0>{}); if (--left == 0) break; [[fallthrough]];
+        case 1: f(Slot<1>{}); if (--left == 0) break; [[fallthrough]];
+        case 2: f(Slot<2>{}); if (--left == 0) break; [[fallthrough]];
+        case 3: f(Slot<3>{}); if (--left == 0) break; [[fallthrough]];
+        case 4: f(Slot<4>{}); if (--left == 0) break; [[fallthrough]];
+        case 5: f(Slot<5>{}); if (--left == 0) break; [[fallthrough]];
+        case 6: f(Slot<6>{}); if (--left == 0) break; [[fallthrough]];
+        default: f(Slot<7>{}); break;
     }
 }
+// sel = the PRMT selector of the label's half (P.sel[0] = 0x4410 low, P.sel[1] = 0x4432 high).  It is read from the
+// kernel parameters on purpose: with an immediate selector ptxas rewrites the extraction + address into three
+// instructions (shift, mask, add); with an opaque one it stays PRMT + IMAD.
+template <int JT>
+__device__ __forceinline__ uint32_t slot_label(const TileParams& P, const uint4& l) {
+    const uint32_t w = (JT >> 1) == 0 ? l.x : (JT >> 1) == 1 ? l.y : (JT >> 1) == 2 ? l.z : l.w;
+    return __byte_perm(w, 0u, P.sel[JT & 1]);
+}
+__device__ __forceinline__ uint32_t slot_label_rt(const uint4& l, int jt) {
+    const int wi = jt >> 1;
+    const uint32_t w = wi == 0 ? l.x : wi == 1 ? l.y : wi == 2 ? l.z : l.w;
+    return (jt & 1) ? (w >> 16) : (w & 0xffffu);
+}
 
-__device__ __forceinline__ void hist_quad(uint32_t meta, const Phase ph, const uint4 (&L)[4], uint32_t rowidx, int nvalid) {
-#pragma unroll UNROLL_HIST
-    for (int q = 0; q < ph.cnt; q++) {
-        const int jt = ph.g0 + q;
-        const uint32_t sel = (jt & 1) ? 0x4432u : 0x4410u;
-        const uint32_t rb = lds_u32(meta + META_TB + q * 4) + rowidx * lds_u32(meta + META_RB + q * 4);
-        with_slot_words(L, jt, [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-            if (nvalid == 4) {  // all but the last quad of a cluster
-                red_inc(rb + __byte_perm(w0, 0u, sel) * 4u);
-                red_inc(rb + __byte_perm(w1, 0u, sel) * 4u);
-                red_inc(rb + __byte_perm(w2, 0u, sel) * 4u);
-                red_inc(rb + __byte_perm(w3, 0u, sel) * 4u);
-            } else {
-                if (nvalid > 0) red_inc(rb + __byte_perm(w0, 0u, sel) * 4u);
-                if (nvalid > 1) red_inc(rb + __byte_perm(w1, 0u, sel) * 4u);
-                if (nvalid > 2) red_inc(rb + __byte_perm(w2, 0u, sel) * 4u);
+__device__ __forceinline__ void hist_quad(const TileParams& P, uint32_t meta, const Phase ph, const uint4 (&L)[4], uint32_t rowidx) {
+    for_slots(ph.g0, ph.cnt, [&](auto slot) {
+        constexpr int JT = decltype(slot)::value;
+        const uint2 tr = lds_u64(meta + META_TR + JT * 8);
+        const uint32_t rb = tr.x + rowidx * tr.y;
+        red_inc(rb + slot_label<JT>(P, L[0]) * 4u);
+        red_inc(rb + slot_label<JT>(P, L[1]) * 4u);
+        red_inc(rb + slot_label<JT>(P, L[2]) * 4u);
+        red_inc(rb + slot_label<JT>(P, L[3]) * 4u);
+    });
+}
+
+// ECS of one (cell, partner): T[a][b] / max(S_i[a], S_j[b])  (calculate_ecs.cpp:35) as count * r, r = 1/max from
+// rcp.approx.ftz.f64 + one Newton step (relative error < 1e-13).  uint32 -> double goes through the 2^52 trick (one
+// DADD on the fp64 pipe) instead of I2F.F64: with two I2F and the MUFU per unit the gather is bound by the
+// quarter-rate XU pipe (ncu: 85 % busy).
+__device__ __forceinline__ double ecs_term(uint32_t count, uint32_t sa, uint32_t sb) {
+    const double mx = u32_to_f64(max(sa, sb));
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
+    r = fma(fma(-mx, r, 1.0), r, r);
+    return u32_to_f64(count) * r;
+}
+
+// UNITW: all weights are 1 (element_consistency of distinct partitions): ECS = count * r is accumulated by one FMA.
+// BIG (block-uniform, rare): a partner of the phase has a cluster with >= 65535 cells, whose size half reads 0xffff
+// = "look the size up in global memory"; WIDE: a streaming item with more than 65535 cells, 32-bit counters and all
+// partner sizes from global memory.  Both take the generic loop with run-time slots.
+template <bool WIDE, bool WANT_SIM, bool UNITW>
+__device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, bool big,
+                                            const uint4 (&L)[4], uint32_t rowidx, uint32_t sa, int nvalid, int lane, double (&acc)[4]) {
+    if (!WIDE && !big) {
+        for_slots(ph.g0, ph.cnt, [&](auto slot) {
+            constexpr int JT = decltype(slot)::value;
+            const uint2 tr = lds_u64(meta + META_TR + JT * 8);
+            const uint32_t rb = tr.x + rowidx * tr.y;
+            const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + JT * 8);
+            double es = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t e = lds_u32(rb + slot_label<JT>(P, L[c]) * 4u);
+                const uint32_t count = e & 0xffffu, sb = e >> 16;
+                if (UNITW && !WANT_SIM) {
+                    const double mx = u32_to_f64(max(sa, sb));
+                    double r;
+                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
+                    r = fma(fma(-mx, r, 1.0), r, r);
+                    acc[c] = fma(u32_to_f64(count), r, acc[c]);
+                } else {
+                    const double v = ecs_term(count, sa, sb);
+                    acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
+                    if (WANT_SIM) es += c < nvalid ? v : 0.0;  // padding positions gather the spare column
+                }
+            }
+            if (WANT_SIM) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
+                if (lane == 0 && es != 0.0) red_add_f64(simacc + JT * 8u, es);
             }
         });
+        return;
     }
-}
-
-// UNITW: all weights are 1 (element_consistency of distinct partitions): ECS = count * r is accumulated by one FMA
-template <bool WIDE, bool WANT_SIM, bool UNITW>
-__device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, const uint4 (&L)[4],
-                                            uint32_t rowidx, uint32_t sa, int nvalid, int lane, double (&acc)[4]) {
 #pragma unroll 1
-    for (int q = 0; q < ph.cnt; q++) {
-        const int jt = ph.g0 + q;
-        const uint32_t sel = (jt & 1) ? 0x4432u : 0x4410u;
-        const uint32_t rb = lds_u32(meta + META_TB + q * 4) + rowidx * lds_u32(meta + META_RB + q * 4);
-        const uint32_t kk = lds_u32(meta + META_KK + q * 4);
-        const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + q * 8);
+    for (int jt = ph.g0; jt < ph.g0 + ph.cnt; jt++) {
+        const uint2 tr = lds_u64(meta + META_TR + jt * 8);
+        const uint32_t rb = tr.x + rowidx * tr.y;
+        const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + jt * 8);
         const int32_t* szg = P.sizes + (int64_t)(ph.j0 + jt) * P.kp;
         double es = 0.0;
-        auto one = [&](double& a, uint32_t w, bool lookup) {
-            const uint32_t lab = __byte_perm(w, 0u, sel);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t lab = slot_label_rt(L[c], jt);
             const uint32_t e = lds_u32(rb + lab * 4u);
             uint32_t count, sb;
             if (WIDE) {
@@ -212,39 +278,16 @@ __device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, 
             } else {
                 count = e & 0xffffu;
                 sb = e >> 16;
-                if (lookup && sb == 0xffffu) sb = (uint32_t)__ldg(szg + lab);
+                if (sb == 0xffffu) sb = (uint32_t)__ldg(szg + lab);
             }
-            // uint32 -> double through the 2^52 trick (one DADD on the fp64 pipe) instead of I2F.F64: with two I2F and
-            // the MUFU per (cell, partner) the gather is bound by the quarter-rate XU pipe (ncu: 85 % busy)
-            const double mx = u32_to_f64(max(sa, sb));
-            double r;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
-            r = fma(fma(-mx, r, 1.0), r, r);  // one Newton step: relative error < 1e-13
-            if (UNITW && !WANT_SIM) {
-                a = fma(u32_to_f64(count), r, a);
-            } else {
-                const double v = u32_to_f64(count) * r;
-                a = UNITW ? a + v : fma(v, wj, a);
-                if (WANT_SIM) es += v;
-            }
-        };
-        with_slot_words(L, jt, [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-            if (nvalid == 4 && !(kk & KK_BIG)) {  // the common case: a full quad, no partner cluster beyond 16 bits
-                one(acc[0], w0, false);
-                one(acc[1], w1, false);
-                one(acc[2], w2, false);
-                one(acc[3], w3, false);
-            } else {
-                if (nvalid > 0) one(acc[0], w0, true);
-                if (nvalid > 1) one(acc[1], w1, true);
-                if (nvalid > 2) one(acc[2], w2, true);
-                if (nvalid > 3) one(acc[3], w3, true);
-            }
-        });
+            const double v = ecs_term(count, sa, sb);
+            acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
+            if (WANT_SIM) es += c < nvalid ? v : 0.0;
+        }
         if (WANT_SIM) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
-            if (lane == 0 && es != 0.0) red_add_f64(simacc + q * 8u, es);
+            if (lane == 0 && es != 0.0) red_add_f64(simacc + jt * 8u, es);
         }
     }
 }
@@ -252,9 +295,9 @@ __device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, 
 // the per-partner ECS sums of a finished phase go to the ECS matrix (called by 8 threads after a block barrier)
 __device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, const Phase ph, int m, int t) {
     if (m < 0) return;
-    if (t < ph.cnt) {
+    if (t >= ph.g0 && t < ph.g0 + ph.cnt) {  // t = tile slot
         const double v = lds_f64(simacc + t * 8u);
-        if (v != 0.0) atomicAdd(P.sim + (int64_t)m * P.m + (ph.j0 + ph.g0 + t), v);
+        if (v != 0.0) atomicAdd(P.sim + (int64_t)m * P.m + (ph.j0 + t), v);
         sts_f64(simacc + t * 8u, 0.0);
     }
 }
@@ -352,7 +395,7 @@ __device__ __forceinline__ void planner_init(const TileParams& P, Planner& pl, i
 }
 
 // Plans the phase at the cursor (how many partners of the tile fit into one buffer: R rows of K_j entries each,
-// K_j rounded to 4) -- this part needs no buffer, so the producer does it BEFORE it waits for the buffer to be
+// K_j + 1 rounded to 4) -- this part needs no buffer, so the producer does it BEFORE it waits for the buffer to be
 // released -- then publishes it into buffer `buf`: table addresses, the WU's item, and the bulk copies that
 // initialise the tables.  After the last WU it publishes cnt = 0.  Everything written here is published by the
 // arrive on the buffer's `full` mbarrier.
@@ -370,7 +413,7 @@ __device__ __forceinline__ PhasePlan plan_compute(const TileParams& P, uint32_t 
     pp.sq = (((uint32_t)pl.j0 & (SUPER - 1)) + q) & (SUPER - 1);  // position inside the super-tile
     pp.kk = lds_u32(sbase + SM_PLAN + 112 + pp.sq * 4);
     const bool ok = lane < 8 && q < thi;
-    pp.rowb = ok ? (((pp.kk & 0xffffu) + 3u) & ~3u) * 4u : 0u;  // bytes of one table row
+    pp.rowb = ok ? (((pp.kk & 0xffffu) + 1u + 3u) & ~3u) * 4u : 0u;  // bytes of one table row: K_j entries + the pad column
     const uint32_t tbytes = pp.rowb * (uint32_t)pp.R;
     uint32_t pre = tbytes;                                      // inclusive prefix of the bytes needed
 #pragma unroll
@@ -389,17 +432,17 @@ __device__ __forceinline__ void plan_publish(const TileParams& P, uint32_t sbase
                                              const Planner& pl, const PhasePlan& pp) {
     const uint32_t meta = sbase + SM_META + buf * META_BYTES, bar = sbase + SM_MBAR + buf * 8u;
     const uint32_t tb = bufaddr + pp.toff;
+    const unsigned bigm = __ballot_sync(FULL, lane < pp.cnt && (pp.kk & KK_BIG) != 0);
     if (lane < pp.cnt) {
-        sts_u32(meta + META_TB + lane * 4, tb);
-        sts_u32(meta + META_RB + lane * 4, pp.rowb);
-        sts_u32(meta + META_KK + lane * 4, pp.kk);
-        sts_f64(meta + META_W + lane * 8, lds_f64(sbase + SM_PLAN + 176 + pp.sq * 8));
+        const uint32_t slot = (uint32_t)(pl.g0 + lane);
+        sts_u32(meta + META_TR + slot * 8, tb);
+        sts_u32(meta + META_TR + slot * 8 + 4, pp.rowb);
+        sts_u32(meta + META_KK + slot * 4, pp.kk);
+        sts_f64(meta + META_W + slot * 8, lds_f64(sbase + SM_PLAN + 176 + pp.sq * 8));
     }
     if (lane == 0) {
+        sts_u32(meta + META_HDR, (uint32_t)pp.cnt | ((uint32_t)pl.g0 << 8) | ((uint32_t)pl.first << 16) | (bigm ? 1u << 17 : 0u));
         sts_u32(meta + META_J0, (uint32_t)pl.j0);
-        sts_u32(meta + META_G0, (uint32_t)pl.g0);
-        sts_u32(meta + META_CNT, (uint32_t)pp.cnt);
-        sts_u32(meta + META_FIRST, (uint32_t)pl.first);
         sts_u32(meta + META_M, (uint32_t)pl.it.m);
         sts_u32(meta + META_POS0, (uint32_t)pl.it.pos0);
         sts_u32(meta + META_NPOS, (uint32_t)pl.it.npos);
@@ -431,7 +474,7 @@ __device__ __forceinline__ void plan_publish(const TileParams& P, uint32_t sbase
 }
 __device__ __forceinline__ void plan_terminal(uint32_t sbase, uint32_t buf, int lane) {
     if (lane == 0) {
-        sts_u32(sbase + SM_META + buf * META_BYTES + META_CNT, 0u);
+        sts_u32(sbase + SM_META + buf * META_BYTES + META_HDR, 0u);
         mbar_arrive(sbase + SM_MBAR + buf * 8u);
     }
 }
@@ -500,6 +543,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
     constexpr bool resident = !STREAMING;  // a launch holds work units of one kind only: two register allocations
     int4 cell = make_int4(-1, -1, -1, -1);
     int nvalid = 0;
+    bool wactive = false;
     uint32_t rowidx = 0, sa = 0;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     uint4 L[4], Lh[4];  // labels of the current tile for this thread's quad; Lh: the super-tile's upper tile
@@ -526,12 +570,14 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         const uint32_t b = p & 1u;
         const uint32_t meta = sbase + SM_META + b * META_BYTES, simacc = sbase + SM_SIMACC + b * 64u;
         mbar_wait(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);  // buffer b initialised, meta of phase p published
+        const uint2 hdr = lds_u64(meta + META_HDR);  // {cnt | g0 << 8 | first << 16 | big << 17, j0}
         Phase ph;
-        ph.cnt = (int)lds_u32(meta + META_CNT);
+        ph.cnt = (int)(hdr.x & 0xffu);
         if (ph.cnt == 0) break;
-        ph.j0 = (int)lds_u32(meta + META_J0);
-        ph.g0 = (int)lds_u32(meta + META_G0);
-        if (lds_u32(meta + META_FIRST)) {  // a new work unit: retire the old one, pick up the new item
+        ph.g0 = (int)((hdr.x >> 8) & 0xffu);
+        ph.j0 = (int)hdr.y;
+        const bool big = (hdr.x >> 17) & 1u;
+        if ((hdr.x >> 16) & 1u) {  // a new work unit: retire the old one, pick up the new item
             flush_acc();
             m = (int)lds_u32(meta + META_M);
             const int npos = (int)lds_u32(meta + META_NPOS);
@@ -542,7 +588,8 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
             cur_j0 = -1;
             if (resident) {
                 cell = make_int4(-1, -1, -1, -1);
-                uint2 qi = make_uint2(0u, sa);
+                uint2 qi = make_uint2(0u, 0u);
+                wactive = (tid & ~31) * 4 < npos;  // warp-uniform: the warp owns at least one position of the item
                 if (tid * 4 < npos) {
                     cell = __ldg(reinterpret_cast<const int4*>(perm + tid * 4));
                     qi = __ldg(reinterpret_cast<const uint2*>(P.qinfo) + (off >> 2) + tid);
@@ -555,16 +602,24 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         }
         // ---- histogram ----
         if (resident) {
-            if (ph.j0 != cur_j0) {
-                if (cur_j0 < 0)  // first phase of the WU: an L2 hit, the super-tile's sectors were fetched by the first block that needed them
-                    load_quad_super(P.lab16 + lab16_index(P.n, 0, ph.j0 & ~(SUPER - 1)), cell, L, Lh);
-                if ((ph.j0 & 8) != 0) {
+            if (wactive) {
+                if (ph.j0 != cur_j0) {
+                    if (cur_j0 < 0) {  // first phase of the WU: an L2 hit, the super-tile's sectors were fetched by the first block that needed them
+                        if (!CA_DBG(P, 2)) {
+                            load_quad_super(P.lab16 + lab16_index(P.n, 0, ph.j0 & ~(SUPER - 1)), (uint32_t)P.n, cell, L, Lh);
+                        } else {  // tuning builds: no label loads, every cell carries label 0
 #pragma unroll
-                    for (int c = 0; c < 4; c++) L[c] = Lh[c];
+                            for (int c = 0; c < 4; c++) L[c] = Lh[c] = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+                    if ((ph.j0 & 8) != 0) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) L[c] = Lh[c];
+                    }
+                    cur_j0 = ph.j0;
                 }
-                cur_j0 = ph.j0;
+                if (!CA_DBG(P, 3)) hist_quad(P, meta, ph, L, rowidx);
             }
-            if (!CA_DBG(P, 3)) hist_quad(meta, ph, L, rowidx, nvalid);
         } else {
             const int npos = (int)lds_u32(meta + META_NPOS);
             const int32_t* perm = P.perm + (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
@@ -573,17 +628,17 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
                 const int4 none = make_int4(-1, -1, -1, -1);
                 const int4 ca = __ldg(reinterpret_cast<const int4*>(perm + cb));
                 const int4 cb4 = cb + CAP < npos ? __ldg(reinterpret_cast<const int4*>(perm + cb + CAP)) : none;
-                load_quad(labj, ca, L);
-                load_quad(labj, cb4, Lh);
-                hist_quad(meta, ph, L, 0u, (ca.x >= 0) + (ca.y >= 0) + (ca.z >= 0) + (ca.w >= 0));
-                hist_quad(meta, ph, Lh, 0u, (cb4.x >= 0) + (cb4.y >= 0) + (cb4.z >= 0) + (cb4.w >= 0));
+                load_quad(labj, (uint32_t)P.n, ca, L);
+                load_quad(labj, (uint32_t)P.n, cb4, Lh);
+                hist_quad(P, meta, ph, L, 0u);
+                if (cb + CAP < npos) hist_quad(P, meta, ph, Lh, 0u);
             }
         }
         consumer_sync();  // the tables of phase p are complete; every consumer has left phase p-1
         if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
         // ---- gather ----
         if (resident) {
-            if (!CA_DBG(P, 4)) gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, L, rowidx, sa, nvalid, lane, acc);
+            if (wactive && !CA_DBG(P, 4)) gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, rowidx, sa, nvalid, lane, acc);
         } else {
             const int npos = (int)lds_u32(meta + META_NPOS);
             const bool wide = (lds_u32(meta + META_NROWS) & NROWS_WIDE) != 0;
@@ -594,12 +649,12 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
                 int4 cl = make_int4(-1, -1, -1, -1);
                 if (cb < npos) cl = __ldg(reinterpret_cast<const int4*>(perm + cb));
                 const int nv = (cl.x >= 0) + (cl.y >= 0) + (cl.z >= 0) + (cl.w >= 0);
-                load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), cl, L);
+                load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), (uint32_t)P.n, cl, L);
                 double a4[4] = {0.0, 0.0, 0.0, 0.0};
                 if (wide)
-                    gather_quad<true, WANT_SIM, UNITW>(P, meta, simacc, ph, L, 0u, sa, nv, lane, a4);
+                    gather_quad<true, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, 0u, sa, nv, lane, a4);
                 else
-                    gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, L, 0u, sa, nv, lane, a4);
+                    gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, 0u, sa, nv, lane, a4);
                 if (WANT_ECC) {
                     if (cl.x >= 0) atomicAdd(P.ecc + cl.x, a4[0] * wscale);
                     if (cl.y >= 0) atomicAdd(P.ecc + cl.y, a4[1] * wscale);
@@ -631,7 +686,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
 }
 
 // Shared memory one block asks for and the number of table rows a resident block may own so that at least one
-// partner with kmax clusters fits into one of the two buffers (R rows of kmax 32-bit entries, kmax rounded to 4).
+// partner with kmax clusters fits into one of the two buffers (R rows of kmax + 1 32-bit entries, rounded to 4).
 int tile_smem_budget(int32_t kmax, int32_t* max_rows_out) {
     Ctx& c = ctx();
     const size_t optin = c.smem_optin ? c.smem_optin : 227 * 1024;
@@ -643,7 +698,7 @@ int tile_smem_budget(int32_t kmax, int32_t* max_rows_out) {
     if (const char* e = getenv("CA_SMEM_KB")) budget_kb = atoi(e);
     const int budget_eff = budget_kb > 0 ? std::min(budget, budget_kb * 1024) : budget;
     const long long half = (((long long)budget_eff - SM_DYN) / 2) & ~127LL;
-    const long long rowb = (((long long)(kmax > 0 ? kmax : 1) + 3) & ~3LL) * 4;
+    const long long rowb = (((long long)(kmax > 0 ? kmax : 1) + 1 + 3) & ~3LL) * 4;  // + the pad column
     long long rows = half / rowb;
     if (rows > TL_MAX_ROWS) rows = TL_MAX_ROWS;
     if (max_rows_out) *max_rows_out = (int32_t)(rows < 0 ? 0 : rows);
