@@ -224,6 +224,14 @@ int prepare_ranks(Labels& L) {
     CA_TRY(L.d_kinfo.ensure((size_t)L.mpad * 4));
     CA_CUDA(cudaMemsetAsync(L.d_kinfo.p, 0, (size_t)L.mpad * 4, s));
     CA_TRY(launch_spack(L.d_sizes.as<int32_t>(), L.d_kcount.as<int32_t>(), m, L.kp, L.d_spack.as<uint32_t>(), L.d_kinfo.as<int32_t>(), s));
+    {   // table templates: one table buffer of the wave kernel per partition
+        int32_t max_rows = 0, half = 0;
+        tile_smem_budget(L.kmax, &max_rows, &half);
+        L.tmpl_bytes = std::max(half, 16);
+        CA_TRY(L.d_tmpl.ensure((size_t)m * (size_t)L.tmpl_bytes));
+        CA_TRY(launch_table_template(L.d_spack.as<uint32_t>(), L.d_kcount.as<int32_t>(), m, L.kp, L.tmpl_bytes, std::max(max_rows, 1),
+                                     L.d_tmpl.as<uint32_t>(), s));
+    }
     L.h_sizes.resize((size_t)m * L.kp);
     CA_CUDA(cudaMemcpyAsync(L.h_sizes.data(), L.d_sizes.p, (size_t)m * L.kp * 4, cudaMemcpyDeviceToHost, s));
     CA_CUDA(cudaStreamSynchronize(s));
@@ -431,7 +439,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     T.n = n;
     T.perm = W.perm.as<int32_t>();
     T.sizes = L.d_sizes.as<int32_t>();
-    T.spack = L.d_spack.as<uint32_t>();
+    T.tmpl = L.d_tmpl.as<uint32_t>();
+    T.tmpl_bytes = L.tmpl_bytes;
     T.kinfo = L.d_kinfo.as<int32_t>();
     {
         static DevBuf zeros;
@@ -645,7 +654,7 @@ int ca_labels_destroy(ca_labels_t* h) {
     if (L.d_raw && L.owns_raw) dev_free(L.d_raw, (size_t)std::max<int64_t>(L.n, 1) * (size_t)L.m * 4);
     L.d_min.release(); L.d_max.release(); L.d_cnt.release(); L.d_rank.release(); L.d_kcount.release();
     L.d_roff.release(); L.d_sizes.release(); L.d_lab16.release();
-    L.d_spack.release(); L.d_kinfo.release();
+    L.d_spack.release(); L.d_kinfo.release(); L.d_tmpl.release();
     delete h;
     return CA_OK;
 }

@@ -90,7 +90,8 @@ struct Labels {
     std::vector<int64_t> h_roff;  // offset of partition p's range in d_cnt / d_rank
     bool identity = true;         // every partition's labels are already dense (rank == label - min)
     int32_t kmax = 0, kp = 0, mpad = 0;
-    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_lab16, d_spack, d_kinfo;
+    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_lab16, d_spack, d_kinfo, d_tmpl;
+    int64_t tmpl_bytes = 0;  // bytes of one partition's table template in d_tmpl (= one table buffer of the wave kernel)
     std::vector<int32_t> h_sizes;  // [m][kp]
 };
 
@@ -118,6 +119,8 @@ int launch_rank(const uint32_t* d_cnt, const int64_t* d_roff, const int32_t* d_m
 int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_min,
                  const int32_t* d_max, int32_t m, int32_t max_range, int32_t kp, int32_t* d_sizes, cudaStream_t s);
 int launch_spack(const int32_t* d_sizes, const int32_t* d_kcount, int32_t m, int32_t kp, uint32_t* d_spack, int32_t* d_kinfo, cudaStream_t s);
+int launch_table_template(const uint32_t* d_spack, const int32_t* d_kcount, int32_t m, int32_t kp, int64_t tmpl_bytes, int32_t max_rows,
+                          uint32_t* d_tmpl, cudaStream_t s);
 int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t mpad, const int32_t* d_min,
                              const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_kcount, uint16_t* d_lab16, cudaStream_t s);
 int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
@@ -143,7 +146,9 @@ struct TileParams {
     int64_t n;
     const int32_t* perm;      // [m_slots][perm_stride] cluster-sorted cell ids, -1 = padding
     const int32_t* sizes;     // [m][kp] cluster sizes
-    const uint32_t* spack;    // [m][kp] min(size, 65535) << 16: the initial value of a table entry (size : count = 0); 1 << 16 beyond K_p
+    const uint32_t* tmpl;     // [m][tmpl_bytes / 4] table templates: partition p's row (min(size, 65535) << 16 per cluster, 1 << 16 in the
+                              // pad column) repeated max_rows times at the table's row stride: one bulk copy initialises an R-row table
+    int64_t tmpl_bytes;
     const int32_t* kinfo;     // [mpad] K_j | (1 << 30 if partition j has a cluster with >= 65535 cells), 0 beyond m
     const void* zeros;        // >= 256 KB of zero bytes: source of the bulk copy that clears the tables
     const uint16_t* crow;     // [m_slots][kp] row of a cluster inside its block
@@ -165,7 +170,7 @@ struct TileParams {
 };
 int launch_tile(const TileParams& p, cudaStream_t s);
 int launch_qinfo(const TileParams& p, const int32_t* d_parts, int32_t nparts, cudaStream_t s);
-int tile_smem_budget(int32_t kmax, int32_t* max_rows_out);
+int tile_smem_budget(int32_t kmax, int32_t* max_rows_out, int32_t* half_out = nullptr);
 
 // ca_pair.cu
 int pair_contingency(const int32_t* d_a, const int32_t* d_b, int64_t n, int32_t min_a, int32_t min_b, int32_t ka,

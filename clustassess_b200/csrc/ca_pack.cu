@@ -200,6 +200,25 @@ int launch_spack(const int32_t* d_sizes, const int32_t* d_kcount, int32_t m, int
     return CA_OK;
 }
 
+// Table templates for the wave kernel: partition p's template is its table row (K_p entries min(size, 65535) << 16,
+// then 1 << 16 up to the row stride round4(K_p + 1)) repeated for as many rows as fit into `tmpl_bytes` (at most
+// max_rows), so that ONE bulk copy of R * row bytes initialises a whole R-row table (size : count = 0 in every entry).
+__global__ void __launch_bounds__(256) table_template_kernel(const uint32_t* __restrict__ spack, const int32_t* __restrict__ kcount, int32_t kp,
+                                                             int64_t tmpl_words, int32_t max_rows, uint32_t* __restrict__ tmpl) {
+    const int p = blockIdx.y;
+    const int roww = (kcount[p] + 1 + 3) & ~3;
+    const int64_t rows = min((int64_t)max_rows, tmpl_words / roww);
+    const uint32_t* src = spack + (int64_t)p * kp;
+    uint32_t* dst = tmpl + (int64_t)p * tmpl_words;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * roww; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i % roww];
+}
+int launch_table_template(const uint32_t* d_spack, const int32_t* d_kcount, int32_t m, int32_t kp, int64_t tmpl_bytes, int32_t max_rows,
+                          uint32_t* d_tmpl, cudaStream_t s) {
+    table_template_kernel<<<dim3(16, (unsigned)m), 256, 0, s>>>(d_spack, d_kcount, kp, tmpl_bytes / 4, max_rows, d_tmpl);
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // relabel + transpose: raw int32 [m][n] (partition-major)  ->  lab16 uint16 [mpad/16][n + 1][16] (super-tile-major, lab16_index; cell n = pad cell with label K_p)
 // A block moves a 32-partition x 128-cell tile through shared memory: coalesced 4-byte reads along n,

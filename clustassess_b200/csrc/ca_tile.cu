@@ -17,8 +17,8 @@
 //
 // PHASE = as many partners of the current 8-partner tile as fit into one of the two shared-memory buffers:
 //   fill    the producer warp initialises the phase's tables with TMA bulk copies completing on the buffer's
-//           `full` mbarrier: row r of partner j's table is a copy of the global array
-//           spack[j][b] = min(|B_j(b)|, 65535) << 16, so every 32-bit entry is born as
+//           `full` mbarrier: partner j's R-row table is ONE copy of the first R rows of j's table template in global
+//           memory (row b-th entry = min(|B_j(b)|, 65535) << 16), so every 32-bit entry is born as
 //           (partner cluster size : 16 | count = 0 : 16); the same mbarrier publishes the phase's meta record;
 //   hist    for each partner and cell: red.shared.add.u32 [entry], 1 -- with a CONSTANT 1 this is the SASS
 //           instruction ATOMS.POPC.INC, which merges lanes that hit the same address in hardware (measured,
@@ -48,10 +48,9 @@
 
 namespace ca {
 
-#ifndef CA_UNROLL_HIST
-#define CA_UNROLL_HIST 1
+#ifndef CA_BACKOFF_NS
+#define CA_BACKOFF_NS 200  // the producer's sleep between probes of a buffer that is still in use (tuning builds)
 #endif
-static constexpr int UNROLL_HIST = CA_UNROLL_HIST;  // partners per trip of the histogram loop (tuning builds)
 static constexpr unsigned FULL = 0xffffffffu;
 static constexpr int NC = TL_THREADS;       // consumer threads (a quad of cells each)
 static constexpr int NT = NC + 32;          // + the producer warp
@@ -121,7 +120,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (BACKOFF && !done) __nanosleep(200);  // the producer is usually far ahead: leave the issue slots to the consumers
+        if (BACKOFF && CA_BACKOFF_NS > 0 && !done) __nanosleep(CA_BACKOFF_NS);  // the producer is usually far ahead: leave the issue slots to the consumers
         if ((spin & 0xfffffu) == 0) {  // every ~0.1 s: a lost copy or arrive must fail loudly, never hang the GPU
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -129,6 +128,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             if (t - t0 > 120ull * 1000000000ull) __trap();  // 2 minutes: far beyond any legitimate phase
         }
     }
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 
 __device__ __forceinline__ uint4 ldg_u4(const uint16_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
@@ -462,15 +471,10 @@ __device__ __forceinline__ void plan_publish(const TileParams& P, uint32_t sbase
         if (pp.wide) bulk_g2s(bufaddr, P.zeros, pp.ttot, bar);
     }
     __syncwarp();
-    if (!pp.wide) {  // cnt partners x R rows: one bulk copy per (partner, row), spread over the lanes
-        const int ncopy = pp.cnt * pp.R;
-        for (int base = 0; base < ncopy; base += 32) {  // warp-uniform trip count: the shuffles need every lane
-            const int idx = base + lane;
-            const int t = min(idx / pp.R, pp.cnt - 1), r = idx - t * pp.R;
-            const uint32_t tbt = __shfl_sync(FULL, tb, t), rbt = __shfl_sync(FULL, pp.rowb, t);
-            if (idx < ncopy) bulk_g2s(tbt + (uint32_t)r * rbt, P.spack + (int64_t)(pl.j0 + pl.g0 + t) * P.kp, rbt, bar);
-        }
-    }
+    // one bulk copy per partner: R rows of the partner's table template (ca_pack.cu, table_template_kernel).  The copy
+    // instruction takes uniform operands, so the lanes' copies are issued one after the other: their number matters.
+    if (!pp.wide && lane < pp.cnt)
+        bulk_g2s(tb, reinterpret_cast<const char*>(P.tmpl) + (int64_t)(pl.j0 + pl.g0 + lane) * P.tmpl_bytes, pp.rowb * (uint32_t)pp.R, bar);
 }
 __device__ __forceinline__ void plan_terminal(uint32_t sbase, uint32_t buf, int lane) {
     if (lane == 0) {
@@ -520,14 +524,26 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
     if (warp == 0) {  // ---- producer ----
         Planner pl;
         planner_init(P, pl, lane, sbase);
+#ifdef CA_ABLATE
+        unsigned n_ahead = 0;  // phases for which the producer had to wait for its buffer (it was ahead of the consumers)
+        long long t_prod = clock64();
+#endif
         for (uint32_t p = 0;; p++) {
             const uint32_t b = p & 1u;
             const bool last = pl.w >= P.nwu;
             PhasePlan pp;
             if (!last) pp = plan_compute(P, sbase, half, lane, pl);
+#ifdef CA_ABLATE
+            if (p >= 2) n_ahead += mbar_test(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u) ? 0u : 1u;
+#endif
             if (p >= 2) mbar_wait<true>(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u);  // consumers are done with buffer b
             if (last) {
                 plan_terminal(sbase, b, lane);
+#ifdef CA_ABLATE
+                if ((blockIdx.x == 3 || blockIdx.x == 77) && lane == 0)
+                    printf("[kind %s] block %d producer: %u phases, had to wait for a free buffer in %u (%.1f %%), %lld cycles\n", STREAMING ? "streaming" : "resident",
+                           blockIdx.x, p, n_ahead, 100.0 * n_ahead / (p + 1.0), clock64() - t_prod);
+#endif
                 break;
             }
             plan_publish(P, sbase, b, sbase + SM_DYN + b * (uint32_t)half, lane, pl, pp);
@@ -564,12 +580,28 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
 
 #ifdef CA_ABLATE
     long long t_all = clock64(), u_all = 0;  // tuning builds: cycles and (padded) units of this block
+    unsigned n_late = 0;                      // phases whose buffer was not ready when this warp asked for it
+#endif
+#ifdef CA_TIMELINE                            // per-section cycle accounting (perturbs the kernel: spills)
+    long long t_sec[6] = {0, 0, 0, 0, 0, 0}, t_mark = clock64();  // wait full, WU start, histogram, barrier, gather, (unused)
+#define CA_SECTION(i)                 \
+    do {                              \
+        const long long t_ = clock64(); \
+        t_sec[i] += t_ - t_mark;      \
+        t_mark = t_;                  \
+    } while (0)
+#else
+#define CA_SECTION(i) do {} while (0)
 #endif
     uint32_t p = 0;
     for (;; p++) {
         const uint32_t b = p & 1u;
         const uint32_t meta = sbase + SM_META + b * META_BYTES, simacc = sbase + SM_SIMACC + b * 64u;
+#ifdef CA_ABLATE
+        n_late += !mbar_test(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);
+#endif
         mbar_wait(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);  // buffer b initialised, meta of phase p published
+        CA_SECTION(0);
         const uint2 hdr = lds_u64(meta + META_HDR);  // {cnt | g0 << 8 | first << 16 | big << 17, j0}
         Phase ph;
         ph.cnt = (int)(hdr.x & 0xffu);
@@ -600,6 +632,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
                 acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
             }
         }
+        CA_SECTION(1);
         // ---- histogram ----
         if (resident) {
             if (wactive) {
@@ -634,7 +667,9 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
                 if (cb + CAP < npos) hist_quad(P, meta, ph, Lh, 0u);
             }
         }
+        CA_SECTION(2);
         consumer_sync();  // the tables of phase p are complete; every consumer has left phase p-1
+        CA_SECTION(3);
         if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
         // ---- gather ----
         if (resident) {
@@ -665,6 +700,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         }
         prev = ph;
         prev_m = m;
+        CA_SECTION(4);
 #ifdef CA_ABLATE
         u_all += (long long)lds_u32(meta + META_NPOS) * ph.cnt;
 #endif
@@ -672,10 +708,16 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         if (lane == 0) mbar_arrive(sbase + SM_MBAR + 16 + b * 8u);  // this warp is done with buffer b (and its meta record)
     }
 #ifdef CA_ABLATE
-    if ((blockIdx.x == 3 || blockIdx.x == 77) && threadIdx.x == 64) {
+    if ((blockIdx.x == 3 || blockIdx.x == 77) && (threadIdx.x == 64 || threadIdx.x == 512)) {
         t_all = clock64() - t_all;
-        printf("[kind %s] block %d: %lld cycles, %lld padded units (%.3f cycles/unit), %u phases (%.0f units/phase)\n",
-               STREAMING ? "streaming" : "resident", blockIdx.x, t_all, u_all, (double)t_all / (double)(u_all + 1), p, (double)u_all / (p + 1.0));
+        printf("[kind %s] block %d warp %d: %lld cycles, %lld padded units (%.3f cycles/unit), %u phases (%.0f units/phase), buffer not ready in %u (%.1f %%)\n",
+               STREAMING ? "streaming" : "resident", blockIdx.x, warp, t_all, u_all, (double)t_all / (double)(u_all + 1), p, (double)u_all / (p + 1.0), n_late,
+               100.0 * n_late / (p + 1.0));
+#ifdef CA_TIMELINE
+        printf("[kind %s] block %d warp %d: %% of cycles: wait-full %.1f, WU start + label loads %.1f, histogram %.1f, barrier %.1f, gather %.1f\n",
+               STREAMING ? "streaming" : "resident", blockIdx.x, warp, 100.0 * t_sec[0] / t_all, 100.0 * t_sec[1] / t_all, 100.0 * t_sec[2] / t_all,
+               100.0 * t_sec[3] / t_all, 100.0 * t_sec[4] / t_all);
+#endif
     }
 #endif
     flush_acc();
@@ -687,7 +729,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
 
 // Shared memory one block asks for and the number of table rows a resident block may own so that at least one
 // partner with kmax clusters fits into one of the two buffers (R rows of kmax + 1 32-bit entries, rounded to 4).
-int tile_smem_budget(int32_t kmax, int32_t* max_rows_out) {
+int tile_smem_budget(int32_t kmax, int32_t* max_rows_out, int32_t* half_out) {
     Ctx& c = ctx();
     const size_t optin = c.smem_optin ? c.smem_optin : 227 * 1024;
     const int budget = TL_BLOCKS == 1 ? (int)optin : (int)(((optin + 1024) / TL_BLOCKS - 1024) & ~127);  // 1 KB per block is reserved by the system
@@ -702,6 +744,7 @@ int tile_smem_budget(int32_t kmax, int32_t* max_rows_out) {
     long long rows = half / rowb;
     if (rows > TL_MAX_ROWS) rows = TL_MAX_ROWS;
     if (max_rows_out) *max_rows_out = (int32_t)(rows < 0 ? 0 : rows);
+    if (half_out) *half_out = (int32_t)half;
     return budget_eff;
 }
 
