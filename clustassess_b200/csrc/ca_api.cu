@@ -359,7 +359,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
             }
             perm_stride = std::max(perm_stride, stride_t[t]);
         }
-        // Work unit = (item, super-tile of TL_SUPER partners), numbered super-tile-major.  With the items in the order
+        // Work unit = (item, span of TL_WU_SPAN partners), numbered span-major.  With the items in the order
         // of their first partner (`parts` is ascending, so slot order is that order), the items that reach into
         // super-tile s are a prefix of the list, and a work-unit number decodes with one prefix array.
         for (auto& v : items_s) total += v.size();
@@ -378,11 +378,11 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         pre.assign(1, 0);
         int32_t jmax = 0;
         for (const Item& it : v) jmax = std::max(jmax, it.jend);
-        const int32_t nsuper = (jmax + TL_SUPER - 1) / TL_SUPER;
+        const int32_t nsuper = (jmax + TL_WU_SPAN - 1) / TL_WU_SPAN;
         size_t k = 0;
         int64_t tot = 0;
         for (int32_t sp = 0; sp < nsuper; sp++) {
-            while (k < v.size() && v[k].jbeg < (sp + 1) * TL_SUPER) k++;
+            while (k < v.size() && v[k].jbeg < (sp + 1) * TL_WU_SPAN) k++;
             tot += (int64_t)k;
             if (tot > 0x7fffff00LL) {
                 set_error("too many work units (%lld)", (long long)tot);

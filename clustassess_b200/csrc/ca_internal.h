@@ -140,7 +140,12 @@ constexpr int TL_THREADS = CA_TL_THREADS;   // tuning builds (tools/build_varian
 constexpr int TL_BLOCKS = CA_TL_BLOCKS;     // persistent blocks per SM (they share the SM's shared memory)
 constexpr int TL_CAP = TL_CPT * TL_THREADS;  // positions per resident item
 constexpr int TL_MAX_ROWS = 1024;
-constexpr int TL_SUPER = 16;                 // partners per work unit: one 32-byte label sector per cell
+constexpr int TL_SUPER = 16;                 // partners per super-tile: one 32-byte label sector per cell
+#ifndef CA_TL_WU_SPAN
+#define CA_TL_WU_SPAN 32
+#endif
+constexpr int TL_WU_SPAN = CA_TL_WU_SPAN;    // partners per work unit: 1 or 2 super-tiles (cell ids, quad info and the ecc flush are per work unit)
+static_assert(TL_WU_SPAN == 16 || TL_WU_SPAN == 32, "a work unit spans one or two super-tiles");
 struct TileParams {
     const uint16_t* lab16;    // [mpad/16][n + 1][16] compact labels (cell n = the pad cell), see lab16_index()
     int64_t n;
@@ -154,7 +159,7 @@ struct TileParams {
     const uint16_t* crow;     // [m_slots][kp] row of a cluster inside its block
     const double* w;          // [mpad + 8] weights
     const Item* items;        // sorted by jbeg; nrows carries bit 30 = 32-bit counters, pad_ = perm slot
-    const int32_t* wu_prefix; // [nsuper + 1] work units before super-tile s (work unit = item x 16-partner super-tile)
+    const int32_t* wu_prefix; // [nsuper + 1] work units before span s (work unit = item x TL_WU_SPAN partners)
     uint32_t* qinfo;          // [m_slots][perm_stride / 4] x {row in block, cluster size} of every quad of positions
     double* ecc;              // [n] accumulated with atomics (may be null)
     double* sim;              // [m*m] accumulated with atomics (may be null)

@@ -69,7 +69,7 @@ static constexpr int META_HDR = 0, META_J0 = 4, META_M = 16, META_POS0 = 20, MET
                      META_KK = 128,  // [8] K_j | flags
                      META_W = 160;   // [8] double: weights
 static constexpr int SM_SIMACC = 480;   // [2][8] double: sum of ECS over the block's cells, per buffer and tile slot
-static constexpr int SM_PLAN = 608;     // at +112 K_j | flags, at +176 the weights of the current super-tile's 16 partners (producer's scratch)
+static constexpr int SM_PLAN = 608;     // [32] K_j | flags, at +128 [32] weights of the current span's partners (producer's scratch)
 static constexpr int SM_DYN = 1024;     // two table buffers
 static constexpr uint32_t KK_BIG = 1u << 30;  // partner has a cluster with >= 65535 cells
 
@@ -320,6 +320,7 @@ __device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, 
 // owner partition -- instead of one random HBM sector read per (cell, tile, owner), which is what bounds a
 // block-per-item schedule (measured: 42 G random sectors/s, tools/gatherbench.cu).
 static constexpr int SUPER = TL_SUPER;
+static constexpr int WSPAN = TL_WU_SPAN;  // partners per work unit (one or two super-tiles)
 #ifdef CA_ABLATE
 #define CA_DBG(P, bit) (((P).dbg >> (bit)) & 1)  // tuning builds: 0 no ecc flush, 1 no table fill, 2 no label loads, 3 no hist, 4 no gather
 #else
@@ -362,16 +363,16 @@ __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int
     pl.wend = pl.nwend;
     pl.it = pl.nit;
     if (pl.w < P.nwu) {
-        const int slo = pl.s * SUPER;
+        const int slo = pl.s * WSPAN;
         const int jlo = max(pl.it.jbeg, slo);
-        pl.jhi = min(pl.it.jend, slo + SUPER);
+        pl.jhi = min(pl.it.jend, slo + WSPAN);
         pl.j0 = jlo & ~7;
         pl.g0 = jlo - pl.j0;
         pl.first = 1;
         if (pl.s != olds) {  // a new super-tile: its partners' K | flags and weights
-            if (lane < SUPER) {
-                sts_u32(sbase + SM_PLAN + 112 + lane * 4, (uint32_t)__ldg(P.kinfo + slo + lane));
-                sts_f64(sbase + SM_PLAN + 176 + lane * 8, __ldg(P.w + slo + lane));
+            if (lane < WSPAN) {
+                sts_u32(sbase + SM_PLAN + lane * 4, (uint32_t)__ldg(P.kinfo + slo + lane));
+                sts_f64(sbase + SM_PLAN + 128 + lane * 8, __ldg(P.w + slo + lane));
             }
             __syncwarp();
         }
@@ -419,8 +420,8 @@ __device__ __forceinline__ PhasePlan plan_compute(const TileParams& P, uint32_t 
     pp.R = pl.it.npos <= CAP ? (int)(pl.it.nrows & 0xffff) : 1;
     const int thi = min(8, pl.jhi - pl.j0);
     const int q = pl.g0 + lane;                                 // tile slot served by meta entry `lane`
-    pp.sq = (((uint32_t)pl.j0 & (SUPER - 1)) + q) & (SUPER - 1);  // position inside the super-tile
-    pp.kk = lds_u32(sbase + SM_PLAN + 112 + pp.sq * 4);
+    pp.sq = (((uint32_t)pl.j0 & (WSPAN - 1)) + q) & (WSPAN - 1);  // position inside the work unit's span
+    pp.kk = lds_u32(sbase + SM_PLAN + pp.sq * 4);
     const bool ok = lane < 8 && q < thi;
     pp.rowb = ok ? (((pp.kk & 0xffffu) + 1u + 3u) & ~3u) * 4u : 0u;  // bytes of one table row: K_j entries + the pad column
     const uint32_t tbytes = pp.rowb * (uint32_t)pp.R;
@@ -447,7 +448,7 @@ __device__ __forceinline__ void plan_publish(const TileParams& P, uint32_t sbase
         sts_u32(meta + META_TR + slot * 8, tb);
         sts_u32(meta + META_TR + slot * 8 + 4, pp.rowb);
         sts_u32(meta + META_KK + slot * 4, pp.kk);
-        sts_f64(meta + META_W + slot * 8, lds_f64(sbase + SM_PLAN + 176 + pp.sq * 8));
+        sts_f64(meta + META_W + slot * 8, lds_f64(sbase + SM_PLAN + 128 + pp.sq * 8));
     }
     if (lane == 0) {
         sts_u32(meta + META_HDR, (uint32_t)pp.cnt | ((uint32_t)pl.g0 << 8) | ((uint32_t)pl.first << 16) | (bigm ? 1u << 17 : 0u));
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         if (resident) {
             if (wactive) {
                 if (ph.j0 != cur_j0) {
-                    if (cur_j0 < 0) {  // first phase of the WU: an L2 hit, the super-tile's sectors were fetched by the first block that needed them
+                    if (cur_j0 < 0 || ((ph.j0 ^ cur_j0) & ~(SUPER - 1)) != 0) {  // the WU's first phase or its second super-tile: L2 hits, the sectors were fetched by the first block that needed them
                         if (!CA_DBG(P, 2)) {
                             load_quad_super(P.lab16 + lab16_index(P.n, 0, ph.j0 & ~(SUPER - 1)), (uint32_t)P.n, cell, L, Lh);
                         } else {  // tuning builds: no label loads, every cell carries label 0
