@@ -312,7 +312,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     std::vector<Item> items;
     int64_t perm_stride = 4;
     {   // plan every owned partition; partitions are independent, so the host threads share them
-        const int nthreads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, nparts}));
+        const int nthreads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 32, (nparts + 7) / 8}));
         std::vector<std::vector<Item>> items_s(nparts);  // per slot, the long (streaming) items first
         std::vector<int64_t> stride_t(nthreads, 4);
         std::vector<int> rc_t(nthreads, CA_OK);

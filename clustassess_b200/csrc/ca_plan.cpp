@@ -33,61 +33,88 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
     out.sa.clear();
     out.total_pos = 0;
 
-    std::vector<int32_t> order(k);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return sizes[a] > sizes[b]; });
+    // Everything below is flat arrays reused across calls (one planner per host thread): the planner runs once per
+    // owned partition and sits between two GPU stages, so its allocations were what it spent its time on.
+    struct Scratch {
+        std::vector<uint64_t> keys;                    // (size << 32 | ~index) per cluster, sorted descending
+        std::vector<int32_t> head, next, bin_of, bin_rows, bin_start, member, big;
+        std::vector<int64_t> bin_used;
+        std::vector<uint64_t> nonempty;
+    };
+    static thread_local Scratch S;
 
     auto padded = [&](int32_t s) { return (int64_t)((s + align - 1) / align) * align; };
 
-    struct Bin {
-        std::vector<int32_t> members;
-        int64_t used = 0;
-    };
-    std::vector<Bin> bins;
-    // open bins by remaining capacity (in units of `align`): bucket lists + a bitmap of the non-empty buckets, so
-    // "smallest remaining capacity that still holds p" is a find-next-set-bit
+    // clusters by decreasing size, ties by increasing index (what a stable sort by size gives)
+    S.keys.resize(k);
+    for (int32_t c = 0; c < k; c++) {
+        if (sizes[c] <= 0) {
+            set_error("plan_blocks: cluster %d has size %d (must be > 0)", c, sizes[c]);
+            return CA_E_ARG;
+        }
+        S.keys[c] = ((uint64_t)(uint32_t)sizes[c] << 32) | (uint32_t)(0x7fffffff - c);
+    }
+    std::sort(S.keys.begin(), S.keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
+
+    // open bins by remaining capacity (in units of `align`): per-capacity LIFO lists threaded through `next` + a bitmap of
+    // the non-empty lists, so "smallest remaining capacity that still holds p" is a find-next-set-bit
     const int32_t nb = cap / align + 1;
-    std::vector<std::vector<int32_t>> bucket(nb);
-    std::vector<uint64_t> nonempty((nb + 63) / 64, 0);
-    auto find_from = [&](int32_t u) -> int32_t {  // first non-empty bucket >= u, or -1
-        for (int32_t w = u >> 6; w < (int32_t)nonempty.size(); w++) {
-            uint64_t bits = nonempty[w];
+    S.head.assign(nb, -1);
+    S.nonempty.assign((nb + 63) / 64, 0);
+    S.next.clear();
+    S.bin_used.clear();
+    S.bin_rows.clear();
+    S.bin_of.assign(k, -1);
+    S.big.clear();
+    auto find_from = [&](int32_t u) -> int32_t {  // first non-empty list >= u, or -1
+        for (int32_t w = u >> 6; w < (int32_t)S.nonempty.size(); w++) {
+            uint64_t bits = S.nonempty[w];
             if (w == (u >> 6)) bits &= ~0ULL << (u & 63);
             if (bits) return w * 64 + __builtin_ctzll(bits);
         }
         return -1;
     };
-    std::vector<int32_t> big;
 
     for (int32_t idx = 0; idx < k; idx++) {
-        int32_t c = order[idx];
-        if (sizes[c] <= 0) {
-            set_error("plan_blocks: cluster %d has size %d (must be > 0)", c, sizes[c]);
-            return CA_E_ARG;
-        }
-        int64_t p = padded(sizes[c]);
+        const int32_t c = 0x7fffffff - (int32_t)(uint32_t)(S.keys[idx] & 0xffffffffu);
+        const int64_t p = padded(sizes[c]);
         if (p > cap) {
-            big.push_back(c);
+            S.big.push_back(c);
             continue;
         }
         const int32_t u = find_from((int32_t)(p / align));  // best fit
         int32_t b;
         if (u < 0) {
-            b = (int32_t)bins.size();
-            bins.emplace_back();
+            b = (int32_t)S.bin_used.size();
+            S.bin_used.push_back(0);
+            S.bin_rows.push_back(0);
+            S.next.push_back(-1);
         } else {
-            b = bucket[u].back();
-            bucket[u].pop_back();
-            if (bucket[u].empty()) nonempty[u >> 6] &= ~(1ULL << (u & 63));
+            b = S.head[u];
+            S.head[u] = S.next[b];
+            if (S.head[u] < 0) S.nonempty[u >> 6] &= ~(1ULL << (u & 63));
         }
-        bins[b].members.push_back(c);
-        bins[b].used += p;
-        const int64_t rem = cap - bins[b].used;
-        if (rem >= align && (int32_t)bins[b].members.size() < max_rows) {
+        S.bin_of[c] = b;
+        S.bin_used[b] += p;
+        S.bin_rows[b]++;
+        const int64_t rem = cap - S.bin_used[b];
+        if (rem >= align && S.bin_rows[b] < max_rows) {
             const int32_t r = (int32_t)(rem / align);
-            bucket[r].push_back(b);
-            nonempty[r >> 6] |= 1ULL << (r & 63);
+            S.next[b] = S.head[r];
+            S.head[r] = b;
+            S.nonempty[r >> 6] |= 1ULL << (r & 63);
         }
+    }
+    // members of every bin in the order they were added (decreasing size)
+    const int32_t nbins = (int32_t)S.bin_used.size();
+    S.bin_start.assign(nbins + 1, 0);
+    for (int32_t b = 0; b < nbins; b++) S.bin_start[b + 1] = S.bin_start[b] + S.bin_rows[b];
+    S.member.resize(S.bin_start[nbins]);
+    for (int32_t b = 0; b < nbins; b++) S.bin_rows[b] = 0;  // reused as the fill cursor
+    for (int32_t idx = 0; idx < k; idx++) {
+        const int32_t c = 0x7fffffff - (int32_t)(uint32_t)(S.keys[idx] & 0xffffffffu);
+        const int32_t b = S.bin_of[c];
+        if (b >= 0) S.member[S.bin_start[b] + S.bin_rows[b]++] = c;
     }
 
     int64_t pos = 0;
@@ -98,22 +125,23 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
         out.wide.push_back(wide);
         out.sa.push_back(sa);
     };
-    for (int32_t c : big) {  // streaming items first: they are the long ones
+    for (int32_t c : S.big) {  // streaming items first: they are the long ones
         int64_t p = padded(sizes[c]);
         out.cstart[c] = (int32_t)pos;
         out.crow[c] = 0;
         push_item(pos, p, 1, sizes[c] > 65535 ? 1 : 0, sizes[c]);
         pos += p;
     }
-    for (const Bin& b : bins) {
+    for (int32_t b = 0; b < nbins; b++) {
         int64_t p0 = pos;
         int32_t r = 0;
-        for (int32_t c : b.members) {
+        for (int32_t t = S.bin_start[b]; t < S.bin_start[b + 1]; t++) {
+            const int32_t c = S.member[t];
             out.cstart[c] = (int32_t)pos;
             out.crow[c] = r++;
             pos += padded(sizes[c]);
         }
-        push_item(p0, pos - p0, r, 0, r == 1 ? sizes[b.members[0]] : 0);
+        push_item(p0, pos - p0, r, 0, r == 1 ? sizes[S.member[S.bin_start[b]]] : 0);
     }
     if (pos > 0x7fffff00LL) {
         set_error("plan_blocks: %lld padded positions exceed the int32 position range", (long long)pos);

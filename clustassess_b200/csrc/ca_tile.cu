@@ -59,18 +59,20 @@ static_assert(TL_CPT == 4, "a thread owns one quad of cells");
 
 // shared-memory map (byte offsets from the dynamic shared base)
 static constexpr int SM_MBAR = 0;       // four mbarriers: full[2] (tables initialised + meta published), empty[2] (buffer released)
-static constexpr int SM_META = 32;      // two Meta records
+static constexpr int SM_META = 32;      // two phase records
 static constexpr int META_BYTES = 224;
-// header word: cnt | g0 << 8 | first << 16 | big << 17 (read together with j0 by one 8-byte load); everything per partner
-// is indexed by TILE SLOT (partner j0 + slot), so the consumers' unrolled slot bodies address it with immediates
-static constexpr int META_HDR = 0, META_J0 = 4, META_M = 16, META_POS0 = 20, META_NPOS = 24, META_NROWS = 28, META_SA = 32,
-                     META_SLOT = 36, META_JHI = 40,
+// phase record.  Header word: cnt | g0 << 8 | first << 16 | big << 17 | WU-record parity << 18 (read together with j0 by one
+// 8-byte load); everything per partner is indexed by TILE SLOT (partner j0 + slot), so the consumers' unrolled slot bodies
+// address it with immediates
+static constexpr int META_HDR = 0, META_J0 = 4,
                      META_TR = 64,   // [8] {table base, row bytes}
-                     META_KK = 128,  // [8] K_j | flags
-                     META_W = 160;   // [8] double: weights
+                     META_W = 160;   // [8] double: weights (not written when every weight is 1)
 static constexpr int SM_SIMACC = 480;   // [2][8] double: sum of ECS over the block's cells, per buffer and tile slot
-static constexpr int SM_PLAN = 608;     // [32] K_j | flags, at +128 [32] weights of the current span's partners (producer's scratch)
-static constexpr int SM_DYN = 1024;     // two table buffers
+static constexpr int SM_WUREC = 608;    // two work-unit records (alternating), written once per work unit
+static constexpr int WU_M = 0, WU_POS0 = 4, WU_NPOS = 8, WU_NROWS = 12, WU_SA = 16, WU_SLOT = 20, WUREC_BYTES = 32;
+static constexpr int SM_PLAN = 672;     // producer's scratch for the current span: [32] {row bytes, inclusive prefix of the row
+static constexpr int SM_PLANW = 928;    //   bytes inside the 8-partner tile}; [32] weights
+static constexpr int SM_DYN = 1280;     // two table buffers
 static constexpr uint32_t KK_BIG = 1u << 30;  // partner has a cluster with >= 65535 cells
 
 // ---- shared-space accessors ---------------------------------------------------------------------------------
@@ -90,6 +92,7 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 // the immediate 1 matters: ptxas emits ATOMS.POPC.INC (same-address lanes merged in hardware) only for it
 __device__ __forceinline__ void red_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
@@ -322,7 +325,7 @@ __device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, 
 static constexpr int SUPER = TL_SUPER;
 static constexpr int WSPAN = TL_WU_SPAN;  // partners per work unit (one or two super-tiles)
 #ifdef CA_ABLATE
-#define CA_DBG(P, bit) (((P).dbg >> (bit)) & 1)  // tuning builds: 0 no ecc flush, 1 no table fill, 2 no label loads, 3 no hist, 4 no gather
+#define CA_DBG(P, bit) (((P).dbg >> (bit)) & 1)  // tuning builds: 0 no ecc flush, 1 no table fill, 2 no label loads, 3 no hist, 4 no gather, 5 no barrier between hist and gather
 #else
 #define CA_DBG(P, bit) 0
 #endif
@@ -336,6 +339,8 @@ struct Planner {          // the producer warp's registers (all values warp-unif
     int jhi;              // partners of this WU: [.., jhi)
     int j0, g0;           // cursor: tile and first tile slot of the next phase to plan
     int first;            // the next phase is the first of its WU
+    unsigned bigmask;     // partners of the current span that have a cluster with >= 65535 cells (bit = position in the span)
+    int wpar;             // parity of the WU record the current WU uses
     Item nit;             // item of the NEXT WU of this block (loaded one WU ahead), nw/ns/nwend its ids
     int nw, ns, nwend;
 };
@@ -369,10 +374,22 @@ __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int
         pl.j0 = jlo & ~7;
         pl.g0 = jlo - pl.j0;
         pl.first = 1;
-        if (pl.s != olds) {  // a new super-tile: its partners' K | flags and weights
+        pl.wpar ^= 1;
+        if (pl.s != olds) {  // a new span: row bytes of its partners' tables, their prefix sums inside each 8-partner tile, flags, weights
+            const uint32_t kk = lane < WSPAN ? (uint32_t)__ldg(P.kinfo + slo + lane) : 0u;
+            const uint32_t rowb = (((kk & 0xffffu) + 1u + 3u) & ~3u) * 4u;  // bytes of one table row: K_j entries + the pad column
+            uint32_t pre = rowb;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, pre, o);
+                if ((lane & 7) >= o) pre += v;
+            }
+            pl.bigmask = __ballot_sync(FULL, (kk & KK_BIG) != 0);
+            __syncwarp();  // every lane has finished reading the previous span's entries (plan_compute of the last phase)
             if (lane < WSPAN) {
-                sts_u32(sbase + SM_PLAN + lane * 4, (uint32_t)__ldg(P.kinfo + slo + lane));
-                sts_f64(sbase + SM_PLAN + 128 + lane * 8, __ldg(P.w + slo + lane));
+                sts_u32(sbase + SM_PLAN + lane * 8, rowb);
+                sts_u32(sbase + SM_PLAN + lane * 8 + 4, pre);
+                sts_f64(sbase + SM_PLANW + lane * 8, __ldg(P.w + slo + lane));
             }
             __syncwarp();
         }
@@ -394,6 +411,8 @@ __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int
 }
 __device__ __forceinline__ void planner_init(const TileParams& P, Planner& pl, int lane, uint32_t sbase) {
     pl.w = -1;
+    pl.wpar = 0;
+    pl.bigmask = 0;
     pl.nw = (int)blockIdx.x;
     pl.ns = 0;
     pl.nwend = __ldg(P.wu_prefix + 1);
@@ -410,56 +429,51 @@ __device__ __forceinline__ void planner_init(const TileParams& P, Planner& pl, i
 // initialise the tables.  After the last WU it publishes cnt = 0.  Everything written here is published by the
 // arrive on the buffer's `full` mbarrier.
 struct PhasePlan {
-    uint32_t kk, rowb, toff, ttot, sq;  // per lane (= tile slot g0 + lane): K | flags, row bytes, table offset; total bytes
+    uint32_t rowb, toff, ttot, sq;  // per lane (= tile slot g0 + lane): row bytes, table offset, position in the span; total bytes
     int cnt, R;
-    bool wide;
+    bool wide, big;
 };
 __device__ __forceinline__ PhasePlan plan_compute(const TileParams& P, uint32_t sbase, int half, int lane, const Planner& pl) {
     PhasePlan pp;
     pp.wide = (pl.it.nrows & NROWS_WIDE) != 0;
     pp.R = pl.it.npos <= CAP ? (int)(pl.it.nrows & 0xffff) : 1;
     const int thi = min(8, pl.jhi - pl.j0);
-    const int q = pl.g0 + lane;                                 // tile slot served by meta entry `lane`
-    pp.sq = (((uint32_t)pl.j0 & (WSPAN - 1)) + q) & (WSPAN - 1);  // position inside the work unit's span
-    pp.kk = lds_u32(sbase + SM_PLAN + pp.sq * 4);
+    const int q = pl.g0 + lane;                                   // tile slot served by this lane
+    const uint32_t sq0 = ((uint32_t)pl.j0 & (WSPAN - 1)) + (uint32_t)pl.g0;  // position of the phase's first partner inside the span
+    pp.sq = (sq0 + (uint32_t)lane) & (WSPAN - 1);
+    const uint2 rp = lds_u64(sbase + SM_PLAN + pp.sq * 8);        // {row bytes, inclusive prefix inside the tile}
+    const uint32_t base = pl.g0 ? lds_u32(sbase + SM_PLAN + (sq0 - 1u) * 8 + 4) : 0u;
     const bool ok = lane < 8 && q < thi;
-    pp.rowb = ok ? (((pp.kk & 0xffffu) + 1u + 3u) & ~3u) * 4u : 0u;  // bytes of one table row: K_j entries + the pad column
-    const uint32_t tbytes = pp.rowb * (uint32_t)pp.R;
-    uint32_t pre = tbytes;                                      // inclusive prefix of the bytes needed
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, pre, o);
-        if (lane >= o) pre += v;
-    }
-    const unsigned fm = __ballot_sync(FULL, ok && pre <= (uint32_t)half);
-    pp.cnt = __popc(fm & 0xffu);                                // >= 1: the host bounds R so that one partner always fits
-    if (pp.cnt == 0) __trap();                                  // cannot happen; never hang the GPU
+    pp.rowb = ok ? rp.x : 0u;
+    const uint32_t pre = (rp.y - base) * (uint32_t)pp.R;          // bytes of the tables of slots g0 .. g0 + lane
+    const unsigned fm = __ballot_sync(FULL, ok && pre <= (uint32_t)half);  // monotone: the set bits are a prefix
+    pp.cnt = __popc(fm & 0xffu);                                  // >= 1: the host bounds R so that one partner always fits
+    if (pp.cnt == 0) __trap();                                    // cannot happen; never hang the GPU
     pp.ttot = __shfl_sync(FULL, pre, pp.cnt - 1);
-    pp.toff = pre - tbytes;
+    pp.toff = pre - pp.rowb * (uint32_t)pp.R;
+    pp.big = ((pl.bigmask >> sq0) & ((1u << pp.cnt) - 1u)) != 0;
     return pp;
 }
+template <bool UNITW>
 __device__ __forceinline__ void plan_publish(const TileParams& P, uint32_t sbase, uint32_t buf, uint32_t bufaddr, int lane,
                                              const Planner& pl, const PhasePlan& pp) {
     const uint32_t meta = sbase + SM_META + buf * META_BYTES, bar = sbase + SM_MBAR + buf * 8u;
     const uint32_t tb = bufaddr + pp.toff;
-    const unsigned bigm = __ballot_sync(FULL, lane < pp.cnt && (pp.kk & KK_BIG) != 0);
     if (lane < pp.cnt) {
         const uint32_t slot = (uint32_t)(pl.g0 + lane);
-        sts_u32(meta + META_TR + slot * 8, tb);
-        sts_u32(meta + META_TR + slot * 8 + 4, pp.rowb);
-        sts_u32(meta + META_KK + slot * 4, pp.kk);
-        sts_f64(meta + META_W + slot * 8, lds_f64(sbase + SM_PLAN + 128 + pp.sq * 8));
+        sts_u64(meta + META_TR + slot * 8, tb, pp.rowb);
+        if (!UNITW) sts_f64(meta + META_W + slot * 8, lds_f64(sbase + SM_PLANW + pp.sq * 8));
     }
     if (lane == 0) {
-        sts_u32(meta + META_HDR, (uint32_t)pp.cnt | ((uint32_t)pl.g0 << 8) | ((uint32_t)pl.first << 16) | (bigm ? 1u << 17 : 0u));
-        sts_u32(meta + META_J0, (uint32_t)pl.j0);
-        sts_u32(meta + META_M, (uint32_t)pl.it.m);
-        sts_u32(meta + META_POS0, (uint32_t)pl.it.pos0);
-        sts_u32(meta + META_NPOS, (uint32_t)pl.it.npos);
-        sts_u32(meta + META_NROWS, (uint32_t)pl.it.nrows);
-        sts_u32(meta + META_SA, (uint32_t)pl.it.sa);
-        sts_u32(meta + META_SLOT, (uint32_t)pl.it.pad_);
-        sts_u32(meta + META_JHI, (uint32_t)pl.jhi);
+        sts_u64(meta + META_HDR,
+                (uint32_t)pp.cnt | ((uint32_t)pl.g0 << 8) | ((uint32_t)pl.first << 16) | (pp.big ? 1u << 17 : 0u) | ((uint32_t)pl.wpar << 18),
+                (uint32_t)pl.j0);
+        if (pl.first) {  // the work unit's record: read by the consumers at its first phase (every phase by the streaming kernel)
+            const uint32_t wr = sbase + SM_WUREC + (uint32_t)pl.wpar * WUREC_BYTES;
+            sts_u64(wr + WU_M, (uint32_t)pl.it.m, (uint32_t)pl.it.pos0);
+            sts_u64(wr + WU_NPOS, (uint32_t)pl.it.npos, (uint32_t)pl.it.nrows);
+            sts_u64(wr + WU_SA, (uint32_t)pl.it.sa, (uint32_t)pl.it.pad_);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the consumers' generic accesses before the async writes
     __syncwarp();
@@ -467,13 +481,12 @@ __device__ __forceinline__ void plan_publish(const TileParams& P, uint32_t sbase
         if (lane == 0) mbar_arrive(bar);
         return;
     }
+    // one bulk copy per partner: R rows of the partner's table template (ca_pack.cu, table_template_kernel).  The copy
+    // instruction takes uniform operands, so the lanes' copies are issued one after the other: their number matters.
     if (lane == 0) {
         mbar_expect_tx(bar, pp.ttot);
         if (pp.wide) bulk_g2s(bufaddr, P.zeros, pp.ttot, bar);
     }
-    __syncwarp();
-    // one bulk copy per partner: R rows of the partner's table template (ca_pack.cu, table_template_kernel).  The copy
-    // instruction takes uniform operands, so the lanes' copies are issued one after the other: their number matters.
     if (!pp.wide && lane < pp.cnt)
         bulk_g2s(tb, reinterpret_cast<const char*>(P.tmpl) + (int64_t)(pl.j0 + pl.g0 + lane) * P.tmpl_bytes, pp.rowb * (uint32_t)pp.R, bar);
 }
@@ -529,6 +542,9 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         unsigned n_ahead = 0;  // phases for which the producer had to wait for its buffer (it was ahead of the consumers)
         long long t_prod = clock64();
 #endif
+#ifdef CA_MEASURE_FILL
+        long long t_fill = 0, b_fill = 0;
+#endif
         for (uint32_t p = 0;; p++) {
             const uint32_t b = p & 1u;
             const bool last = pl.w >= P.nwu;
@@ -545,9 +561,22 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
                     printf("[kind %s] block %d producer: %u phases, had to wait for a free buffer in %u (%.1f %%), %lld cycles\n", STREAMING ? "streaming" : "resident",
                            blockIdx.x, p, n_ahead, 100.0 * n_ahead / (p + 1.0), clock64() - t_prod);
 #endif
+#ifdef CA_MEASURE_FILL
+                if ((blockIdx.x == 3 || blockIdx.x == 77) && lane == 0)
+                    printf("[kind %s] block %d fill: %.0f cycles and %.0f bytes per phase from issue to landing\n", STREAMING ? "streaming" : "resident", blockIdx.x,
+                           (double)t_fill / (p + 1.0), (double)b_fill / (p + 1.0));
+#endif
                 break;
             }
-            plan_publish(P, sbase, b, sbase + SM_DYN + b * (uint32_t)half, lane, pl, pp);
+            plan_publish<UNITW>(P, sbase, b, sbase + SM_DYN + b * (uint32_t)half, lane, pl, pp);
+#ifdef CA_MEASURE_FILL  // tuning builds: the producer waits for its own fill to land (this serialises it: only the latency is meaningful)
+            {
+                const long long t0 = clock64();
+                mbar_wait(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);
+                t_fill += clock64() - t0;
+                b_fill += pp.ttot;
+            }
+#endif
             plan_advance(P, pl, pp, lane, sbase);
         }
         return;
@@ -610,13 +639,15 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         ph.g0 = (int)((hdr.x >> 8) & 0xffu);
         ph.j0 = (int)hdr.y;
         const bool big = (hdr.x >> 17) & 1u;
+        const uint32_t wurec = sbase + SM_WUREC + ((hdr.x >> 18) & 1u) * WUREC_BYTES;
         if ((hdr.x >> 16) & 1u) {  // a new work unit: retire the old one, pick up the new item
             flush_acc();
-            m = (int)lds_u32(meta + META_M);
-            const int npos = (int)lds_u32(meta + META_NPOS);
-            const int64_t off = (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
+            const uint2 w0 = lds_u64(wurec + WU_M), w1 = lds_u64(wurec + WU_NPOS), w2 = lds_u64(wurec + WU_SA);
+            m = (int)w0.x;
+            const int npos = (int)w1.x;
+            const int64_t off = (int64_t)w2.y * P.perm_stride + (int)w0.y;
             const int32_t* perm = P.perm + off;
-            sa = lds_u32(meta + META_SA);
+            sa = w2.x;
             rowidx = 0;
             cur_j0 = -1;
             if (resident) {
@@ -655,8 +686,8 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
                 if (!CA_DBG(P, 3)) hist_quad(P, meta, ph, L, rowidx);
             }
         } else {
-            const int npos = (int)lds_u32(meta + META_NPOS);
-            const int32_t* perm = P.perm + (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
+            const int npos = (int)lds_u32(wurec + WU_NPOS);
+            const int32_t* perm = P.perm + (int64_t)lds_u32(wurec + WU_SLOT) * P.perm_stride + (int)lds_u32(wurec + WU_POS0);
             const uint16_t* labj = P.lab16 + lab16_index(P.n, 0, ph.j0);
             for (int cb = tid * 4; cb < npos; cb += 2 * CAP) {  // two chunks per trip: their loads are in flight together
                 const int4 none = make_int4(-1, -1, -1, -1);
@@ -669,16 +700,16 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
             }
         }
         CA_SECTION(2);
-        consumer_sync();  // the tables of phase p are complete; every consumer has left phase p-1
+        if (!CA_DBG(P, 5)) consumer_sync();  // the tables of phase p are complete; every consumer has left phase p-1
         CA_SECTION(3);
         if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
         // ---- gather ----
         if (resident) {
             if (wactive && !CA_DBG(P, 4)) gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, rowidx, sa, nvalid, lane, acc);
         } else {
-            const int npos = (int)lds_u32(meta + META_NPOS);
-            const bool wide = (lds_u32(meta + META_NROWS) & NROWS_WIDE) != 0;
-            const int32_t* perm = P.perm + (int64_t)lds_u32(meta + META_SLOT) * P.perm_stride + (int)lds_u32(meta + META_POS0);
+            const int npos = (int)lds_u32(wurec + WU_NPOS);
+            const bool wide = (lds_u32(wurec + WU_NROWS) & NROWS_WIDE) != 0;
+            const int32_t* perm = P.perm + (int64_t)lds_u32(wurec + WU_SLOT) * P.perm_stride + (int)lds_u32(wurec + WU_POS0);
             const double wscale = __ldg(P.w + m) * P.inv_norm;
             for (int cb0 = 0; cb0 < npos; cb0 += CAP) {  // warp-uniform trip count: gather_quad shuffles when WANT_SIM
                 const int cb = cb0 + tid * 4;
@@ -703,7 +734,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
         prev_m = m;
         CA_SECTION(4);
 #ifdef CA_ABLATE
-        u_all += (long long)lds_u32(meta + META_NPOS) * ph.cnt;
+        u_all += (long long)lds_u32(wurec + WU_NPOS) * ph.cnt;
 #endif
         __syncwarp();
         if (lane == 0) mbar_arrive(sbase + SM_MBAR + 16 + b * 8u);  // this warp is done with buffer b (and its meta record)
