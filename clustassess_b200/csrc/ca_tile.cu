@@ -588,6 +588,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
     int m = -1;
     constexpr bool resident = !STREAMING;  // a launch holds work units of one kind only: two register allocations
     int4 cell = make_int4(-1, -1, -1, -1);
+    int4 cell2 = cell;  // streaming kernel: the second chunk of an item of at most two chunks
     int nvalid = 0;
     bool wactive = false;
     uint32_t rowidx = 0, sa = 0;
@@ -689,6 +690,16 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
             const int npos = (int)lds_u32(wurec + WU_NPOS);
             const int32_t* perm = P.perm + (int64_t)lds_u32(wurec + WU_SLOT) * P.perm_stride + (int)lds_u32(wurec + WU_POS0);
             const uint16_t* labj = P.lab16 + lab16_index(P.n, 0, ph.j0);
+            if (npos <= 2 * CAP) {  // at most two chunks (most streaming items): their labels stay in registers for the gather
+                if ((hdr.x >> 16) & 1u) {
+                    cell = __ldg(reinterpret_cast<const int4*>(perm + tid * 4));
+                    cell2 = tid * 4 + CAP < npos ? __ldg(reinterpret_cast<const int4*>(perm + tid * 4 + CAP)) : make_int4(-1, -1, -1, -1);
+                }
+                load_quad(labj, (uint32_t)P.n, cell, L);
+                load_quad(labj, (uint32_t)P.n, cell2, Lh);
+                hist_quad(P, meta, ph, L, 0u);
+                hist_quad(P, meta, ph, Lh, 0u);  // padding positions count into the spare column
+            } else
             for (int cb = tid * 4; cb < npos; cb += 2 * CAP) {  // two chunks per trip: their loads are in flight together
                 const int4 none = make_int4(-1, -1, -1, -1);
                 const int4 ca = __ldg(reinterpret_cast<const int4*>(perm + cb));
@@ -711,6 +722,21 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
             const bool wide = (lds_u32(wurec + WU_NROWS) & NROWS_WIDE) != 0;
             const int32_t* perm = P.perm + (int64_t)lds_u32(wurec + WU_SLOT) * P.perm_stride + (int)lds_u32(wurec + WU_POS0);
             const double wscale = __ldg(P.w + m) * P.inv_norm;
+            if (npos <= 2 * CAP) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int4 cl = h ? cell2 : cell;
+                    const int nv = (cl.x >= 0) + (cl.y >= 0) + (cl.z >= 0) + (cl.w >= 0);
+                    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+                    gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, h ? Lh : L, 0u, sa, nv, lane, a4);
+                    if (WANT_ECC) {
+                        if (cl.x >= 0) atomicAdd(P.ecc + cl.x, a4[0] * wscale);
+                        if (cl.y >= 0) atomicAdd(P.ecc + cl.y, a4[1] * wscale);
+                        if (cl.z >= 0) atomicAdd(P.ecc + cl.z, a4[2] * wscale);
+                        if (cl.w >= 0) atomicAdd(P.ecc + cl.w, a4[3] * wscale);
+                    }
+                }
+            } else
             for (int cb0 = 0; cb0 < npos; cb0 += CAP) {  // warp-uniform trip count: gather_quad shuffles when WANT_SIM
                 const int cb = cb0 + tid * 4;
                 int4 cl = make_int4(-1, -1, -1, -1);
