@@ -696,9 +696,11 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
                     cell2 = tid * 4 + CAP < npos ? __ldg(reinterpret_cast<const int4*>(perm + tid * 4 + CAP)) : make_int4(-1, -1, -1, -1);
                 }
                 load_quad(labj, (uint32_t)P.n, cell, L);
-                load_quad(labj, (uint32_t)P.n, cell2, Lh);
                 hist_quad(P, meta, ph, L, 0u);
-                hist_quad(P, meta, ph, Lh, 0u);  // padding positions count into the spare column
+                if ((tid & ~31) * 4 + CAP < npos) {  // warp-uniform: the warp owns positions of the second chunk
+                    load_quad(labj, (uint32_t)P.n, cell2, Lh);
+                    hist_quad(P, meta, ph, Lh, 0u);
+                }
             } else
             for (int cb = tid * 4; cb < npos; cb += 2 * CAP) {  // two chunks per trip: their loads are in flight together
                 const int4 none = make_int4(-1, -1, -1, -1);
@@ -725,6 +727,7 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
             if (npos <= 2 * CAP) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
+                    if (h && !((tid & ~31) * 4 + CAP < npos)) break;  // warp-uniform
                     const int4 cl = h ? cell2 : cell;
                     const int nv = (cl.x >= 0) + (cl.y >= 0) + (cl.z >= 0) + (cl.w >= 0);
                     double a4[4] = {0.0, 0.0, 0.0, 0.0};
