@@ -127,7 +127,7 @@ def cpu_baseline(args, m, n, cores, seconds):
     impl = "reference" if oracle.have_ref() else "port"
     rng = np.random.default_rng(12345)
     # probe one pair to size the sample
-    parts = sorted(rng.choice(m, size=min(m, 16), replace=False).tolist())
+    parts = sorted(rng.choice(m, size=min(m, 48), replace=False).tolist())
     labels, _ = synth.config(args.config, family=args.family, m=m, n=n, parts=parts)
     t_probe = oracle.time_pairs(labels, [0], [1], nthreads=1, impl=impl)
     npairs = int(max(cores, min(len(parts) * (len(parts) - 1) // 2, seconds * cores / max(t_probe, 1e-6))))

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <numeric>
@@ -251,8 +252,7 @@ int prepare_labels(Labels& L) {
     CA_TRY(launch_relabel_transpose(L.d_raw, n, m, L.mpad, L.d_min.as<int32_t>(),
                                     L.identity ? nullptr : L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(),
                                     L.d_kcount.as<int32_t>(), L.d_lab16.as<uint16_t>(), s));
-    CA_CUDA(cudaEventRecord(c.ev[2], s));
-    CA_CUDA(cudaStreamSynchronize(s));
+    CA_CUDA(cudaEventRecord(c.ev[2], s));  // no synchronisation: the host goes on to plan while the transposition runs
     L.prepared = true;
     return CA_OK;
 }
@@ -310,58 +310,104 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     std::vector<int32_t> h_cstart((size_t)std::max(nparts, 1) * L.kp, 0);
     std::vector<uint16_t> h_crow((size_t)std::max(nparts, 1) * L.kp, 0);
     std::vector<Item> items;
-    int64_t perm_stride = 4;
-    {   // plan every owned partition; partitions are independent, so the host threads share them
+    // every cluster pads to a multiple of TL_CPT positions: an upper bound that does not wait for the planner
+    const int64_t perm_stride = ((int64_t)n + (int64_t)(TL_CPT - 1) * L.kmax + TL_CPT + 3) & ~3LL;
+    if (perm_stride > 0x7fffff00LL) {
+        set_error("%lld padded positions exceed the int32 position range", (long long)perm_stride);
+        return CA_E_UNSUPPORTED;
+    }
+    Workspace& W = ws();
+    CA_TRY(W.qinfo.ensure((size_t)std::max(nparts, 1) * perm_stride * 2));
+    CA_TRY(W.perm.ensure((size_t)std::max(nparts, 1) * perm_stride * 4));
+    CA_TRY(W.cstart.ensure(h_cstart.size() * 4));
+    CA_TRY(W.crow.ensure(h_crow.size() * 2));
+    CA_TRY(W.parts.ensure((size_t)std::max(nparts, 1) * 4));
+    if (nparts) CA_CUDA(cudaMemcpyAsync(W.parts.p, parts.data(), (size_t)nparts * 4, cudaMemcpyHostToDevice, s));
+    CA_CUDA(cudaEventRecord(c.ev[3], s));
+    {   // Plan every owned partition; partitions are independent, so the host threads share them.  The slots are cut
+        // into batches: as soon as a batch is planned its cluster starts go to the device and its counting sort is
+        // launched, so the GPU sorts batch b while the host plans batch b + 1.
         const int nthreads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 32, (nparts + 7) / 8}));
+        const int nbatch = nparts >= 64 && nthreads > 1 ? 4 : 1;
         std::vector<std::vector<Item>> items_s(nparts);  // per slot, the long (streaming) items first
-        std::vector<int64_t> stride_t(nthreads, 4);
-        std::vector<int> rc_t(nthreads, CA_OK);
-        auto work = [&](int tix) {
+        std::vector<int32_t> bnd(nbatch + 1);
+        for (int b = 0; b <= nbatch; b++) bnd[b] = (int32_t)((int64_t)b * nparts / nbatch);
+        std::vector<std::atomic<int>> left(nbatch);
+        for (int b = 0; b < nbatch; b++) left[b].store(bnd[b + 1] - bnd[b]);
+        std::atomic<int> next{0}, err{CA_OK};
+        auto work = [&]() {
             PlanOut po;
-            for (int32_t sl = tix; sl < nparts; sl += nthreads) {
-                const int32_t p = parts[sl];
-                int rc = plan_blocks(L.h_sizes.data() + (size_t)p * L.kp, L.h_k[p], TL_CPT, TL_CAP, max_rows, po);
-                if (rc != CA_OK) { rc_t[tix] = rc; return; }
-                stride_t[tix] = std::max<int64_t>(stride_t[tix], (po.total_pos + 3) & ~3LL);
-                for (int32_t k = 0; k < L.h_k[p]; k++) {
-                    h_cstart[(size_t)sl * L.kp + k] = po.cstart[k];
-                    h_crow[(size_t)sl * L.kp + k] = (uint16_t)po.crow[k];
+            for (;;) {
+                const int32_t sl = next.fetch_add(1);
+                if (sl >= nparts) break;
+                int b = 0;
+                while (sl >= bnd[b + 1]) b++;
+                if (err.load() == CA_OK) {
+                    const int32_t p = parts[sl];
+                    int rc = plan_blocks(L.h_sizes.data() + (size_t)p * L.kp, L.h_k[p], TL_CPT, TL_CAP, max_rows, po);
+                    if (rc == CA_OK && po.total_pos > perm_stride) rc = CA_E_UNSUPPORTED;
+                    if (rc != CA_OK) {
+                        err.store(rc);
+                    } else {
+                        for (int32_t k = 0; k < L.h_k[p]; k++) {
+                            h_cstart[(size_t)sl * L.kp + k] = po.cstart[k];
+                            h_crow[(size_t)sl * L.kp + k] = (uint16_t)po.crow[k];
+                        }
+                        std::vector<Item>& v = items_s[sl];
+                        v.reserve(po.pos0.size());
+                        for (size_t t = 0; t < po.pos0.size(); t++) {
+                            Item it;
+                            it.m = p;
+                            it.pos0 = po.pos0[t];
+                            it.npos = po.npos[t];
+                            it.nrows = po.nrows[t] | (po.wide[t] ? (1 << 30) : 0);  // bit 30: 32-bit counters
+                            it.jbeg = ref_only >= 0 ? 0 : p + 1;
+                            it.jend = ref_only >= 0 ? m_partners : m;
+                            it.sa = po.sa[t];
+                            it.pad_ = sl;  // perm slot
+                            v.push_back(it);
+                        }
+                        std::stable_sort(v.begin(), v.end(), [](const Item& a, const Item& b) { return a.npos > b.npos; });
+                    }
                 }
-                std::vector<Item>& v = items_s[sl];
-                v.reserve(po.pos0.size());
-                for (size_t t = 0; t < po.pos0.size(); t++) {
-                    Item it;
-                    it.m = p;
-                    it.pos0 = po.pos0[t];
-                    it.npos = po.npos[t];
-                    it.nrows = po.nrows[t] | (po.wide[t] ? (1 << 30) : 0);  // bit 30: 32-bit counters
-                    it.jbeg = ref_only >= 0 ? 0 : p + 1;
-                    it.jend = ref_only >= 0 ? m_partners : m;
-                    it.sa = po.sa[t];
-                    it.pad_ = sl;  // perm slot
-                    v.push_back(it);
-                }
-                std::stable_sort(v.begin(), v.end(), [](const Item& a, const Item& b) { return a.npos > b.npos; });
+                left[b].fetch_sub(1, std::memory_order_release);
             }
         };
-        if (nthreads == 1) {
-            work(0);
-        } else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
-            for (auto& t : th) t.join();
-        }
-        size_t total = 0;
-        for (int t = 0; t < nthreads; t++) {
-            if (rc_t[t] != CA_OK) {
-                set_error("item planning failed (code %d)", rc_t[t]);
-                return rc_t[t];
+        std::vector<std::thread> th;
+        if (nthreads > 1)
+            for (int t = 0; t < nthreads; t++) th.emplace_back(work);
+        else
+            work();
+        int launch_rc = CA_OK;
+        for (int b = 0; b < nbatch; b++) {
+            while (left[b].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+            const int32_t b0 = bnd[b], nb = bnd[b + 1] - bnd[b];
+            if (err.load() != CA_OK || launch_rc != CA_OK || nb == 0) continue;
+            cudaError_t e = cudaMemcpyAsync(W.cstart.as<int32_t>() + (size_t)b0 * L.kp, h_cstart.data() + (size_t)b0 * L.kp, (size_t)nb * L.kp * 4,
+                                            cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(W.crow.as<uint16_t>() + (size_t)b0 * L.kp, h_crow.data() + (size_t)b0 * L.kp, (size_t)nb * L.kp * 2,
+                                    cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) {
+                set_error("uploading the plan failed: %s", cudaGetErrorString(e));
+                launch_rc = CA_E_CUDA;
+                continue;
             }
-            perm_stride = std::max(perm_stride, stride_t[t]);
+            launch_rc = launch_sort(L.d_raw, n, L.d_min.as<int32_t>(), L.identity ? nullptr : L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(),
+                                    W.cstart.as<int32_t>() + (size_t)b0 * L.kp, L.kp, W.parts.as<int32_t>() + b0, nb,
+                                    W.perm.as<int32_t>() + (size_t)b0 * perm_stride, perm_stride, s);
         }
+        for (auto& t : th) t.join();
+        if (err.load() != CA_OK) {
+            set_error("item planning failed (code %d)", err.load());
+            return err.load();
+        }
+        CA_TRY(launch_rc);
+        CA_CUDA(cudaEventRecord(c.ev[4], s));
         // Work unit = (item, span of TL_WU_SPAN partners), numbered span-major.  With the items in the order
         // of their first partner (`parts` is ascending, so slot order is that order), the items that reach into
-        // super-tile s are a prefix of the list, and a work-unit number decodes with one prefix array.
+        // span s are a prefix of the list, and a work-unit number decodes with one prefix array.
+        size_t total = 0;
         for (auto& v : items_s) total += v.size();
         items.reserve(total);
         for (auto& v : items_s) items.insert(items.end(), v.begin(), v.end());
@@ -407,31 +453,17 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     }
     c.prof[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
 
-    // ---- upload plan, sort ------------------------------------------------------------------------
-    Workspace& W = ws();
+    // ---- upload the item lists (cluster starts and the sort went out batch by batch above) -----------------------
     const size_t npre0 = h_wu_prefix_kind[0].size(), npre1 = h_wu_prefix_kind[1].size();
     CA_TRY(W.wu_prefix.ensure((npre0 + npre1) * 4));
-    CA_TRY(W.qinfo.ensure((size_t)std::max(nparts, 1) * perm_stride * 2));
-    CA_TRY(W.perm.ensure((size_t)std::max(nparts, 1) * perm_stride * 4));
-    CA_TRY(W.cstart.ensure(h_cstart.size() * 4));
-    CA_TRY(W.crow.ensure(h_crow.size() * 2));
     CA_TRY(W.items.ensure(std::max<size_t>(items.size(), 1) * sizeof(Item)));
-    CA_TRY(W.parts.ensure((size_t)std::max(nparts, 1) * 4));
     CA_TRY(W.w.ensure(h_w.size() * 8));
     CA_CUDA(cudaMemcpyAsync(W.wu_prefix.p, h_wu_prefix_kind[0].data(), npre0 * 4, cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaMemcpyAsync(W.wu_prefix.as<int32_t>() + npre0, h_wu_prefix_kind[1].data(), npre1 * 4, cudaMemcpyHostToDevice, s));
-    CA_CUDA(cudaMemcpyAsync(W.cstart.p, h_cstart.data(), h_cstart.size() * 4, cudaMemcpyHostToDevice, s));
-    CA_CUDA(cudaMemcpyAsync(W.crow.p, h_crow.data(), h_crow.size() * 2, cudaMemcpyHostToDevice, s));
-    if (nparts) CA_CUDA(cudaMemcpyAsync(W.parts.p, parts.data(), (size_t)nparts * 4, cudaMemcpyHostToDevice, s));
     CA_CUDA(cudaMemcpyAsync(W.w.p, h_w.data(), h_w.size() * 8, cudaMemcpyHostToDevice, s));
     for (int kind = 0, off = 0; kind < 2; off += (int)items_kind[kind].size(), kind++)
         if (!items_kind[kind].empty())
             CA_CUDA(cudaMemcpyAsync(W.items.as<Item>() + off, items_kind[kind].data(), items_kind[kind].size() * sizeof(Item), cudaMemcpyHostToDevice, s));
-    CA_CUDA(cudaEventRecord(c.ev[3], s));
-    CA_TRY(launch_sort(L.d_raw, n, L.d_min.as<int32_t>(), L.identity ? nullptr : L.d_rank.as<uint32_t>(),
-                       L.d_roff.as<int64_t>(), W.cstart.as<int32_t>(), L.kp, W.parts.as<int32_t>(), nparts,
-                       W.perm.as<int32_t>(), perm_stride, s));
-    CA_CUDA(cudaEventRecord(c.ev[4], s));
 
     // ---- the wave kernel ----------------------------------------------------------------------------
     TileParams T;

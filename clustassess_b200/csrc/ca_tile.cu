@@ -9,11 +9,12 @@
 // sorted by cluster (perm_i, ca_pack.cu), so a block that works on an item owns whole ROWS of every contingency
 // table T_ij.  A consumer thread owns a quad of consecutive positions of one cluster.
 //
-// WORK UNIT = (item, super-tile of 16 partner partitions).  Work units are numbered super-tile-major and the
-// persistent blocks (one per SM) take them round-robin, so all SMs sweep the partner axis together and the labels
-// of the current super-tile -- a dense 32 N-byte slab of the super-tile-major uint16 label array, lab16_index() --
-// are fetched from HBM once and then served by L2 to every owner partition.  A thread fetches the 16 labels of a
-// cell with ONE 32-byte load (LDG.E.256) per work unit.
+// WORK UNIT = (item, span of 32 partner partitions = two 16-partner super-tiles).  Work units are numbered span-major
+// and the persistent blocks (one per SM) take them round-robin, so all SMs sweep the partner axis together and the
+// labels of the current super-tiles -- dense 32 (N+1)-byte slabs of the super-tile-major uint16 label array,
+// lab16_index() -- are fetched from HBM once and then served by L2 to every owner partition.  A thread fetches the 16
+// labels of a cell with ONE 32-byte load (LDG.E.256) per super-tile; cell ids, quad info and the flush of the
+// per-cell sums to ecc happen once per work unit.
 //
 // PHASE = as many partners of the current 8-partner tile as fit into one of the two shared-memory buffers:
 //   fill    the producer warp initialises the phase's tables with TMA bulk copies completing on the buffer's
@@ -29,13 +30,17 @@
 //   gather  one shared load per (cell, partner) returns count and partner cluster size together;
 //           ECS = T[a][b] / max(S_i[a], S_j[b])  (calculate_ecs.cpp:35) is accumulated in registers; the
 //           consumer warps then release the buffer through its `empty` mbarrier.
-// Tables are row-major per partner with row stride K_j (rounded to 4), so a table takes R * K_j entries whatever
-// the largest cluster count is.
+// Tables are row-major per partner with row stride K_j + 1 (rounded to 4), so a table takes R * (K_j + 1) entries
+// whatever the largest cluster count is.  Column K_j is the PAD COLUMN: padding positions of the cluster-sorted order
+// read the pad cell N, whose label in partition j is K_j, so the inner loops carry no validity tests.  The bodies of
+// histogram and gather are instantiated per tile slot (label word and half are compile-time, the slot's meta entries
+// sit at immediate offsets) and entered Duff-style at the phase's first slot.
 //
 // A work unit of a RESIDENT item (<= TL_CAP positions) adds its per-cell sums to ecc once, when the block moves on
-// to its next work unit; clusters larger than TL_CAP are "streaming" items: one row, both passes stream the cells
-// from global memory in chunks, sums are added per phase; with more than 65535 cells the entries are plain 32-bit
-// counts and the partner sizes come from global memory.
+// to its next work unit; clusters larger than TL_CAP are "streaming" items (their own launch, own register
+// allocation): one row; items of at most two chunks keep both chunks' labels in registers between histogram and
+// gather, longer ones stream the cells from global memory in both passes; sums are added per phase; with more than
+// 65535 cells the entries are plain 32-bit counts and the partner sizes come from global memory.
 //
 // The division is T * r with r = 1/max from rcp.approx.ftz.f64 + one Newton step (relative error < 1e-13);
 // the batched path has to meet 1e-9 absolute, the per-pair entry points (ca_pair.cu) keep the IEEE division.

@@ -316,10 +316,10 @@ def test_rank_sharding_sums_to_the_whole():
     dl.close()
 
 
-# ---- the wave engine's own structure (work units of 16 partners, phases, resident / streaming items) --------------
-@pytest.mark.parametrize("m", [2, 15, 16, 17, 31, 33, 49])
+# ---- the wave engine's own structure (work units of 32 partners, phases, resident / streaming items) --------------
+@pytest.mark.parametrize("m", [2, 15, 16, 17, 31, 33, 49, 64, 65, 97])
 def test_super_tile_boundaries_weights_and_matrix(m):
-    """Partition counts around the 16-partner super-tile and 8-partner tile boundaries, non-unit weights."""
+    """Partition counts around the 8-partner tile, 16-partner super-tile and 32-partner work-unit boundaries, non-unit weights."""
     rng = np.random.default_rng(100 + m)
     n = 6000
     base = rng.integers(0, 30, size=n)
@@ -350,6 +350,39 @@ def test_mixed_item_kinds_in_one_job():
     w = np.array([2.0, 1.0, 3.0, 1.0, 1.0])
     ecc, sim = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
     res = ecs.weighted_element_consistency(list(L), weights=w, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+
+
+@pytest.mark.parametrize("big", [3455, 3456, 3457, 3460, 5000, 6911, 6912, 6913, 6916, 20000])
+def test_streaming_chunk_boundaries(big):
+    """One cluster around the sizes where an item stops being resident (3456 positions = 864 threads x 4 cells), where
+    a streaming item has exactly two chunks (kept in registers) and where it has more (re-streamed in the gather);
+    partners with K % 4 == 0 (the pad column opens a new 16-byte group), K = 1 and K = 2."""
+    rng = np.random.default_rng(big)
+    n = big + 9000
+    own = np.concatenate([np.zeros(big, dtype=np.int64), 1 + rng.integers(0, 7, size=n - big)])   # K = 8
+    perm = rng.permutation(n)
+    L = np.stack([own[perm],
+                  rng.integers(0, 4, size=n),          # K = 4
+                  np.zeros(n, dtype=np.int64),          # K = 1
+                  (rng.random(n) < 0.5).astype(np.int64),  # K = 2
+                  np.where(rng.random(n) < 0.1, rng.integers(0, 12, size=n), own[perm]),  # a noisy copy: K = 12
+                  own[rng.permutation(n)]]).astype(np.int32)
+    w = np.array([1.0, 2.0, 1.0, 1.0, 3.0, 1.0])
+    ecc, sim = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), weights=w, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+    assert np.abs(ecs.weighted_element_consistency(list(L)) - oracle.weighted_element_consistency(L)).max() < TOL
+
+
+def test_many_rows_and_row_stride_remainders():
+    """Items with many table rows (small clusters) against partners whose cluster counts cover every remainder of the
+    4-entry row alignment, so that the pad column sits at every position of its 16-byte group."""
+    rng = np.random.default_rng(77)
+    n = 40_000
+    L = np.stack([rng.integers(0, k, size=n) for k in (900, 901, 902, 903, 37, 5, 1999, 2000)]).astype(np.int32)
+    ecc, sim = oracle.weighted_element_consistency(L, None, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
     assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
 
 
