@@ -44,6 +44,9 @@ SYMBOLS = {
     "ca_labels_device_ptr": (C.c_void_p, [C.c_void_p]),
     "ca_labels_invalidate": (C.c_int, [C.c_void_p]),
     "ca_labels_destroy": (C.c_int, [C.c_void_p]),
+    "ca_labels_select": (C.c_int, [C.c_void_p, _I32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ca_consistency_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, _F64, C.c_void_p]),
+    "ca_sim_matrix_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _F64]),
     "ca_shard_owner": (C.c_int, [C.c_int32, C.c_int32]),
     "ca_consistency_partial_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ca_consistency_finish_dev": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -123,6 +126,34 @@ class DeviceLabels:
 
     def invalidate(self):
         check(lib().ca_labels_invalidate(self._h))
+
+    def select(self, idx):
+        """A new resident set holding the partitions idx (device-to-device copies)."""
+        ix = np.ascontiguousarray(idx, dtype=np.int32)
+        h = C.c_void_p()
+        check(lib().ca_labels_select(self._h, ix, ix.size, C.byref(h)))
+        out = DeviceLabels.__new__(DeviceLabels)
+        out.n, out.m, out._h = self.n, int(ix.size), h
+        return out
+
+    def consistency(self, idx=None, weights=None, want_matrix=False):
+        """weighted_element_consistency of the resident partitions (all, or those named by idx) -> (ecc, matrix or None)."""
+        ix = None if idx is None else np.ascontiguousarray(idx, dtype=np.int32)
+        k = self.m if ix is None else int(ix.size)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        if w is not None and w.size != k:
+            raise ValueError("weights must have one entry per selected partition")
+        ecc = np.empty(self.n, dtype=np.float64)
+        sim = np.empty((k, k), dtype=np.float64) if want_matrix else None
+        check(lib().ca_consistency_resident(self._h, _opt(ix), k, _opt(w), ecc, _opt(sim)))
+        return ecc, sim
+
+    def sim_matrix(self, idx=None):
+        ix = None if idx is None else np.ascontiguousarray(idx, dtype=np.int32)
+        k = self.m if ix is None else int(ix.size)
+        sim = np.empty((k, k), dtype=np.float64)
+        check(lib().ca_sim_matrix_resident(self._h, _opt(ix), k, sim))
+        return sim
 
     def consistency_partial(self, weights, rank, world, ecc_ptr, sim_ptr):
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)

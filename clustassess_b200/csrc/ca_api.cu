@@ -761,6 +761,81 @@ static int host_allpairs(const int32_t* labels, const int32_t* const* cols, int6
     return rc;
 }
 
+// ---- resident label sets: the same job without the upload ----------------------------------------------------
+int ca_labels_select(ca_labels_t* src, const int32_t* idx, int32_t k, ca_labels_t** out) {
+    if (!src || !idx || !out || k < 1) { set_error("ca_labels_select: bad argument"); return CA_E_ARG; }
+    for (int32_t t = 0; t < k; t++)
+        if (idx[t] < 0 || idx[t] >= src->L.m) { set_error("ca_labels_select: index %d out of range [0, %d)", idx[t], src->L.m); return CA_E_ARG; }
+    CA_TRY(ensure_init());
+    ca_labels_t* h = nullptr;
+    CA_TRY(ca_labels_create(src->L.n, k, &h));
+    cudaStream_t s = ctx().stream;
+    const size_t row = (size_t)src->L.n * 4;
+    for (int32_t t = 0; t < k && row > 0;) {  // runs of consecutive indices go out as one copy
+        int32_t e = t + 1;
+        while (e < k && idx[e] == idx[e - 1] + 1) e++;
+        cudaError_t err = cudaMemcpyAsync(h->L.d_raw + (size_t)t * src->L.n, src->L.d_raw + (size_t)idx[t] * src->L.n, row * (size_t)(e - t),
+                                          cudaMemcpyDeviceToDevice, s);
+        if (err != cudaSuccess) {
+            set_error("device-to-device copy failed: %s", cudaGetErrorString(err));
+            ca_labels_destroy(h);
+            return CA_E_CUDA;
+        }
+        t = e;
+    }
+    *out = h;
+    return CA_OK;
+}
+
+static int resident_allpairs(ca_labels_t* h, const int32_t* idx, int32_t k, const double* weights, double* ecc_out, double* sim_out) {
+    if (!h || (idx && k < 1)) { set_error("bad arguments (NULL label set or empty index list)"); return CA_E_ARG; }
+    CA_TRY(ensure_init());
+    ca_labels_t* sub = nullptr;
+    if (idx) CA_TRY(ca_labels_select(h, idx, k, &sub));
+    ca_labels_t* use = sub ? sub : h;
+    const int64_t n = use->L.n;
+    const int32_t m = use->L.m;
+    int rc = CA_OK;
+    static DevBuf d_ecc, d_sim;
+    cudaStream_t s = ctx().stream;
+    do {
+        if (ecc_out && m < 2) { set_error("At least two clusterings are required to calculate the consistency."); rc = CA_E_ARG; break; }
+        if (n == 0) {
+            if (sim_out)
+                for (int32_t i = 0; i < m; i++)
+                    for (int32_t j = 0; j < m; j++) sim_out[(size_t)i * m + j] = i == j ? 1.0 : 0.0 / 0.0;
+            break;
+        }
+        if (ecc_out) { rc = d_ecc.ensure((size_t)n * 8); if (rc) break; }
+        if (sim_out) { rc = d_sim.ensure((size_t)m * m * 8); if (rc) break; }
+        cudaError_t e = cudaSuccess;
+        if (ecc_out) e = cudaMemsetAsync(d_ecc.p, 0, (size_t)n * 8, s);
+        if (e == cudaSuccess && sim_out) e = cudaMemsetAsync(d_sim.p, 0, (size_t)m * m * 8, s);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e)); rc = CA_E_CUDA; break; }
+        if (m >= 2) {
+            rc = run_allpairs(use->L, weights, 0, 1, ecc_out ? d_ecc.as<double>() : nullptr, sim_out ? d_sim.as<double>() : nullptr, -1, 0);
+            if (rc) break;
+        }
+        rc = ca_consistency_finish_dev(n, m, weights, ecc_out ? d_ecc.as<double>() : nullptr, sim_out ? d_sim.as<double>() : nullptr);
+        if (rc) break;
+        if (ecc_out) e = cudaMemcpyAsync(ecc_out, d_ecc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && sim_out) e = cudaMemcpyAsync(sim_out, d_sim.p, (size_t)m * m * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("device-to-host copy failed: %s", cudaGetErrorString(e)); rc = CA_E_CUDA; }
+    } while (0);
+    if (sub) ca_labels_destroy(sub);
+    return rc;
+}
+
+int ca_consistency_resident(ca_labels_t* h, const int32_t* idx, int32_t k, const double* weights, double* ecc_out, double* sim_out) {
+    if (!ecc_out) { set_error("ca_consistency_resident: ecc_out is NULL"); return CA_E_ARG; }
+    return resident_allpairs(h, idx, k, weights, ecc_out, sim_out);
+}
+int ca_sim_matrix_resident(ca_labels_t* h, const int32_t* idx, int32_t k, double* sim_out) {
+    if (!sim_out) { set_error("ca_sim_matrix_resident: sim_out is NULL"); return CA_E_ARG; }
+    return resident_allpairs(h, idx, k, nullptr, nullptr, sim_out);
+}
+
 int ca_consistency(const int32_t* labels, int64_t n, int32_t m, const double* weights, double* ecc_out, double* sim_out) {
     if (m < 2) { set_error("At least two clusterings are required to calculate the consistency."); return CA_E_ARG; }
     if (!ecc_out) { set_error("ca_consistency: ecc_out is NULL"); return CA_E_ARG; }

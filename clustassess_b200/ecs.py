@@ -21,7 +21,7 @@ from . import _capi
 __all__ = [
     "element_sim", "element_sim_elscore", "element_sim_matrix", "element_consistency",
     "weighted_element_consistency", "element_agreement", "merge_partitions", "merge_identical_partitions",
-    "contingency_table",
+    "contingency_table", "ResidentPartitions",
 ]
 
 
@@ -335,3 +335,45 @@ def element_agreement(reference_clustering, clustering_list, alpha=0.9, **_ignor
     out = np.zeros(n, dtype=np.float64)
     _capi.check(_capi.lib().ca_agreement(ref, lab.reshape(-1), n, m, out))
     return out
+
+
+# ---- pipeline glue: partitions kept on the device across calls ----------------
+class ResidentPartitions:
+    """The runs of one configuration, uploaded once and compared many times.
+
+    The stability pipeline hands the SAME membership vectors to the ECS routines up to three times: per number
+    of clusters k (R/stability-3-graph-clustering.R:271-300), per resolution (:25-69) and per k across
+    resolutions (:303-343).  This holds them as one device-resident label set (ca_labels_t); every comparison
+    names its partitions by index, nothing is uploaded again.  Results are the ones the list-taking functions of
+    this module return for `[clustering_list[i] for i in idx]`.
+    """
+
+    def __init__(self, clustering_list):
+        if len(clustering_list) < 1:
+            raise ValueError("At least one clustering is required.")
+        lab = _label_matrix(clustering_list)
+        self._like = clustering_list[0]
+        self._dev = _capi.DeviceLabels(lab.shape[1], lab.shape[0]).upload(lab)
+
+    def __len__(self):
+        return self._dev.m
+
+    def weighted_element_consistency(self, idx=None, weights=None, calculate_sim_matrix=False):
+        """weighted_element_consistency (R/ECS.R:1446-1500) of the partitions idx (default: all)."""
+        k = len(self) if idx is None else len(idx)
+        if k <= 1:
+            raise ValueError("At least two clusterings are required to calculate the consistency.")
+        ecc, sim = self._dev.consistency(idx, weights, calculate_sim_matrix)
+        ecc = _wrap(ecc, self._like)
+        return {"ecc": ecc, "ecs_matrix": sim} if calculate_sim_matrix else ecc
+
+    def element_consistency(self, idx=None):
+        """element_consistency (R/ECS.R:1350-1386) of distinct partitions: unit weights."""
+        return self.weighted_element_consistency(idx)
+
+    def element_sim_matrix(self, idx=None):
+        """element_sim_matrix, output_type = "matrix" (R/ECS.R:931-965)."""
+        return self._dev.sim_matrix(idx)
+
+    def close(self):
+        self._dev.close()

@@ -119,6 +119,20 @@ void *ca_labels_device_ptr(ca_labels_t *h);                    /* raw device mat
 int ca_labels_invalidate(ca_labels_t *h);                      /* call after writing through the ptr   */
 int ca_labels_destroy(ca_labels_t *h);
 
+/* Pipeline glue: the stability pipeline compares the SAME partitions several
+ * times -- per k (R/stability-3-graph-clustering.R:271-300: merge_partitions of the runs that gave k clusters),
+ * per resolution (:25-69: weighted_element_consistency of the merged partitions) and per k across resolutions
+ * (:303-343) -- and today re-walks the R vectors every time.  With a resident label set the runs of one
+ * configuration are uploaded once; every comparison names its partitions by index:
+ *   ca_labels_select     : a new device-resident set holding partitions idx[0..k) of src (device-to-device copies)
+ *   ca_consistency_resident : weighted_element_consistency (R/ECS.R:1446-1500) of a resident set, results to host;
+ *                          idx == NULL -> the whole set, else the partitions idx[0..k) (weights has k entries)
+ *   ca_sim_matrix_resident  : element_sim_matrix_flat_disjoint (R/ECS.R:931-981) likewise. */
+int ca_labels_select(ca_labels_t *src, const int32_t *idx, int32_t k, ca_labels_t **out);
+int ca_consistency_resident(ca_labels_t *h, const int32_t *idx, int32_t k, const double *weights, double *ecc_out,
+                            double *sim_out);
+int ca_sim_matrix_resident(ca_labels_t *h, const int32_t *idx, int32_t k, double *sim_out);
+
 /* One rank's share of the all-pairs job on a device-resident label set.
  *   rank/world : this process handles the partitions i with zigzag(i) == rank and all their pairs (i,j>i);
  *                world == 1 -> everything.

@@ -127,3 +127,60 @@ List ecsMergeIdentical(List mb_list, NumericVector freq) {
     }
     return List::create(Named("keep") = kept1, Named("freq") = f1);
 }
+
+// ---- pipeline glue: the runs of one configuration stay on the device -------------
+// R/stability-3-graph-clustering.R compares the same membership vectors per k (:271-300), per resolution (:25-69)
+// and per k across resolutions (:303-343).  ecsResident(mb_list) uploads them once and returns an external pointer;
+// ecsResidentConsistency(ptr, idx, weights, calculate_sim_matrix, n_cells) / ecsResidentSimMatrix(ptr, idx) run a
+// comparison of the partitions idx (1-based).  The finalizer releases the device memory with the R object.
+static void resident_finalizer(ca_labels_t *h) { ca_labels_destroy(h); }
+typedef XPtr<ca_labels_t, PreserveStorage, resident_finalizer, true> ResidentPtr;
+
+// [[Rcpp::export]]
+SEXP ecsResident(List mb_list) {
+    const int m = mb_list.size();
+    if (m < 1) stop("At least one clustering is required.");
+    std::vector<IntegerVector> keep;
+    R_xlen_t n;
+    std::vector<const int32_t *> cols = column_pointers(mb_list, keep, n);
+    ca_labels_t *h = NULL;
+    ca_check(ca_labels_create(n, m, &h));
+    for (int p = 0; p < m; p++) {
+        int rc = ca_labels_upload_col(h, p, cols[p]);
+        if (rc != CA_OK) {
+            ca_labels_destroy(h);
+            ca_check(rc);
+        }
+    }
+    return ResidentPtr(h, true);
+}
+
+// [[Rcpp::export]]
+List ecsResidentConsistency(SEXP resident, IntegerVector idx, Nullable<NumericVector> weights, bool calculate_sim_matrix, int n_cells) {
+    ResidentPtr h(resident);
+    const int k = idx.size();
+    if (k <= 1) stop("At least two clusterings are required to calculate the consistency.");
+    std::vector<int32_t> ix(idx.begin(), idx.end());
+    for (size_t t = 0; t < ix.size(); t++) ix[t] -= 1;  // R indices are 1-based
+    const double *w = NULL;
+    NumericVector wv;
+    if (weights.isNotNull()) {
+        wv = NumericVector(weights);
+        if (wv.size() != k) stop("weights must have one entry per clustering");
+        w = wv.begin();
+    }
+    NumericVector ecc(n_cells);
+    NumericMatrix sim(calculate_sim_matrix ? k : 0, calculate_sim_matrix ? k : 0);
+    ca_check(ca_consistency_resident(h.get(), ix.data(), k, w, ecc.begin(), calculate_sim_matrix ? sim.begin() : NULL));
+    return List::create(Named("ecc") = ecc, Named("ecs_matrix") = sim);
+}
+
+// [[Rcpp::export]]
+NumericMatrix ecsResidentSimMatrix(SEXP resident, IntegerVector idx) {
+    ResidentPtr h(resident);
+    std::vector<int32_t> ix(idx.begin(), idx.end());
+    for (size_t t = 0; t < ix.size(); t++) ix[t] -= 1;
+    NumericMatrix sim(ix.size(), ix.size());
+    ca_check(ca_sim_matrix_resident(h.get(), ix.data(), (int)ix.size(), sim.begin()));
+    return sim;
+}

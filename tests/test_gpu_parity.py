@@ -386,6 +386,28 @@ def test_many_rows_and_row_stride_remainders():
     assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
 
 
+def test_resident_partitions_subsets_without_reupload():
+    """Pipeline glue: a resident label set answers comparisons of arbitrary subsets -- contiguous
+    runs, scattered and repeated indices, with weights and with the matrix -- exactly like a fresh host-side call."""
+    L, w = synth.config("C3", m=23, n=25_000)
+    res = ecs.ResidentPartitions(list(L))
+    assert len(res) == 23
+    rng = np.random.default_rng(8)
+    for idx in ([0, 1], list(range(4, 15)), [22, 3, 17, 3, 9], sorted(rng.choice(23, 12, replace=False).tolist()), None):
+        sel = L if idx is None else L[idx]
+        wi = None if idx is None else w[idx]
+        want_ecc, want_sim = oracle.weighted_element_consistency(sel, wi, calculate_sim_matrix=True)
+        got = res.weighted_element_consistency(idx, weights=wi, calculate_sim_matrix=True)
+        assert np.abs(got["ecc"] - want_ecc).max() < TOL and np.abs(got["ecs_matrix"] - want_sim).max() < TOL
+        assert np.abs(res.element_sim_matrix(idx) - want_sim).max() < TOL
+        assert np.abs(res.element_consistency(idx) - oracle.weighted_element_consistency(sel)).max() < TOL
+    with pytest.raises(ValueError):
+        res.element_consistency([5])
+    with pytest.raises(_capi.ClustAssessError):
+        res.element_sim_matrix([0, 23])
+    res.close()
+
+
 def test_full_size_properties_config5_shape():
     """Size-independent properties at BASELINE.json's cell count (1M cells, K up to 2000): permuting the partitions
     and relabelling their clusters leaves ecc unchanged; duplicating the list leaves the weighted result unchanged
