@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <numeric>
 #include <thread>
@@ -257,13 +259,105 @@ int prepare_labels(Labels& L) {
     return CA_OK;
 }
 
+// ---- host worker pool -----------------------------------------------------------------------------------------
+// The item planner runs between two GPU stages of every batched call; creating its threads (and their thread-local
+// scratch) per call cost as much as the planning.  The pool's threads live until ca_shutdown / process exit.
+namespace {
+class WorkerPool {
+  public:
+    // runs job() on `n` pool threads and returns immediately; wait() blocks until all of them have returned
+    void start(int n, std::function<void()> job) {
+        std::unique_lock<std::mutex> g(mu_);
+        while ((int)threads_.size() < n) threads_.emplace_back([this, id = (int)threads_.size()] { loop(id); });
+        job_ = std::move(job);
+        want_ = n;
+        running_ = n;
+        generation_++;
+        cv_.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> g(mu_);
+        done_cv_.wait(g, [this] { return running_ == 0; });
+    }
+    void shutdown() {
+        {
+            std::unique_lock<std::mutex> g(mu_);
+            stop_ = true;
+            cv_.notify_all();
+        }
+        for (auto& t : threads_) t.join();
+        threads_.clear();
+        stop_ = false;
+    }
+    ~WorkerPool() { shutdown(); }
+
+  private:
+    void loop(int id) {
+        unsigned long seen = 0;
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return stop_ || (generation_ != seen && id < want_); });
+                if (stop_) return;
+                seen = generation_;
+                job = job_;
+            }
+            job();
+            std::unique_lock<std::mutex> g(mu_);
+            if (--running_ == 0) done_cv_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> threads_;
+    std::function<void()> job_;
+    unsigned long generation_ = 0;
+    int want_ = 0, running_ = 0;
+    bool stop_ = false;
+};
+WorkerPool& pool() {
+    static WorkerPool p;
+    return p;
+}
+}  // namespace
+
 // zigzag owner of partition i among `world` ranks: 0..w-1, w-1..0, ... (balances sum of M-1-i)
 static inline int owner_of(int32_t i, int32_t world) {
     int32_t r = i % (2 * world);
     return r < world ? r : 2 * world - 1 - r;
 }
 
+// grow-only pinned host buffer: cudaMemcpyAsync from pageable memory first synchronises with the stream's earlier work,
+// which would make the host wait for the previous batch's sort before it can hand over the next batch's plan
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return CA_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaHostAlloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            return CA_E_NOMEM;
+        }
+        cap = want;
+        return CA_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
 struct Workspace {
+    PinnedBuf h_cstart, h_crow, h_items, h_small;
     DevBuf perm, cstart, crow, items, parts, w, wu_prefix, qinfo;
 };
 static Workspace& ws() {
@@ -293,6 +387,10 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
 
     // ---- host planning ----------------------------------------------------------------------------
     auto t_plan0 = std::chrono::steady_clock::now();
+    const bool plan_dbg = getenv("CA_PLAN_DEBUG") != nullptr;
+    auto lap = [&](const char* what) {
+        if (plan_dbg) fprintf(stderr, "[plan] %-28s %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count());
+    };
     int32_t max_rows = 0;
     const int smem_bytes = tile_smem_budget(L.kmax, &max_rows);
     if (max_rows < 1) {
@@ -307,9 +405,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
             if (owner_of(i, world) == rank) parts.push_back(i);
     }
     const int32_t nparts = (int32_t)parts.size();
-    std::vector<int32_t> h_cstart((size_t)std::max(nparts, 1) * L.kp, 0);
-    std::vector<uint16_t> h_crow((size_t)std::max(nparts, 1) * L.kp, 0);
-    std::vector<Item> items;
+    Item* items_kind[2] = {nullptr, nullptr};  // [0] resident, [1] streaming: views into the pinned staging buffer, in slot order
+    size_t n_kind[2] = {0, 0};
     // every cluster pads to a multiple of TL_CPT positions: an upper bound that does not wait for the planner
     const int64_t perm_stride = ((int64_t)n + (int64_t)(TL_CPT - 1) * L.kmax + TL_CPT + 3) & ~3LL;
     if (perm_stride > 0x7fffff00LL) {
@@ -317,18 +414,32 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         return CA_E_UNSUPPORTED;
     }
     Workspace& W = ws();
+    // the previous call's copies out of the pinned staging buffers have completed: every batched call ends with a
+    // stream synchronisation.  Entries beyond a partition's K are never read, so the buffers are not cleared.
+    const size_t ncl = (size_t)std::max(nparts, 1) * L.kp;
+    CA_TRY(W.h_cstart.ensure(ncl * 4));
+    CA_TRY(W.h_crow.ensure(ncl * 2));
+    int32_t* const h_cstart = W.h_cstart.as<int32_t>();
+    uint16_t* const h_crow = W.h_crow.as<uint16_t>();
     CA_TRY(W.qinfo.ensure((size_t)std::max(nparts, 1) * perm_stride * 2));
     CA_TRY(W.perm.ensure((size_t)std::max(nparts, 1) * perm_stride * 4));
-    CA_TRY(W.cstart.ensure(h_cstart.size() * 4));
-    CA_TRY(W.crow.ensure(h_crow.size() * 2));
+    CA_TRY(W.cstart.ensure(ncl * 4));
+    CA_TRY(W.crow.ensure(ncl * 2));
     CA_TRY(W.parts.ensure((size_t)std::max(nparts, 1) * 4));
-    if (nparts) CA_CUDA(cudaMemcpyAsync(W.parts.p, parts.data(), (size_t)nparts * 4, cudaMemcpyHostToDevice, s));
+    // small host arrays go through one pinned block: [parts | wu_prefix of both kinds | weights]
+    const size_t small_bytes = (size_t)std::max(nparts, 1) * 4 + 2 * ((size_t)(m + TL_WU_SPAN) / TL_WU_SPAN + 2) * 4 + 64 + ((size_t)L.mpad + 8) * 8;
+    CA_TRY(W.h_small.ensure(small_bytes));
+    if (nparts) {
+        memcpy(W.h_small.p, parts.data(), (size_t)nparts * 4);
+        CA_CUDA(cudaMemcpyAsync(W.parts.p, W.h_small.p, (size_t)nparts * 4, cudaMemcpyHostToDevice, s));
+    }
     CA_CUDA(cudaEventRecord(c.ev[3], s));
+    lap("buffers ready");
     {   // Plan every owned partition; partitions are independent, so the host threads share them.  The slots are cut
         // into batches: as soon as a batch is planned its cluster starts go to the device and its counting sort is
         // launched, so the GPU sorts batch b while the host plans batch b + 1.
         const int nthreads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 32, (nparts + 7) / 8}));
-        const int nbatch = nparts >= 64 && nthreads > 1 ? 4 : 1;
+        const int nbatch = nthreads > 1 ? (nparts >= 256 ? 8 : nparts >= 64 ? 4 : 1) : 1;
         std::vector<std::vector<Item>> items_s(nparts);  // per slot, the long (streaming) items first
         std::vector<int32_t> bnd(nbatch + 1);
         for (int b = 0; b <= nbatch; b++) bnd[b] = (int32_t)((int64_t)b * nparts / nbatch);
@@ -373,9 +484,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                 left[b].fetch_sub(1, std::memory_order_release);
             }
         };
-        std::vector<std::thread> th;
         if (nthreads > 1)
-            for (int t = 0; t < nthreads; t++) th.emplace_back(work);
+            pool().start(nthreads, work);
         else
             work();
         int launch_rc = CA_OK;
@@ -383,10 +493,10 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
             while (left[b].load(std::memory_order_acquire) > 0) std::this_thread::yield();
             const int32_t b0 = bnd[b], nb = bnd[b + 1] - bnd[b];
             if (err.load() != CA_OK || launch_rc != CA_OK || nb == 0) continue;
-            cudaError_t e = cudaMemcpyAsync(W.cstart.as<int32_t>() + (size_t)b0 * L.kp, h_cstart.data() + (size_t)b0 * L.kp, (size_t)nb * L.kp * 4,
+            cudaError_t e = cudaMemcpyAsync(W.cstart.as<int32_t>() + (size_t)b0 * L.kp, h_cstart + (size_t)b0 * L.kp, (size_t)nb * L.kp * 4,
                                             cudaMemcpyHostToDevice, s);
             if (e == cudaSuccess)
-                e = cudaMemcpyAsync(W.crow.as<uint16_t>() + (size_t)b0 * L.kp, h_crow.data() + (size_t)b0 * L.kp, (size_t)nb * L.kp * 2,
+                e = cudaMemcpyAsync(W.crow.as<uint16_t>() + (size_t)b0 * L.kp, h_crow + (size_t)b0 * L.kp, (size_t)nb * L.kp * 2,
                                     cudaMemcpyHostToDevice, s);
             if (e != cudaSuccess) {
                 set_error("uploading the plan failed: %s", cudaGetErrorString(e));
@@ -397,7 +507,9 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                                     W.cstart.as<int32_t>() + (size_t)b0 * L.kp, L.kp, W.parts.as<int32_t>() + b0, nb,
                                     W.perm.as<int32_t>() + (size_t)b0 * perm_stride, perm_stride, s);
         }
-        for (auto& t : th) t.join();
+        lap("last batch launched");
+        if (nthreads > 1) pool().wait();
+        lap("threads joined");
         if (err.load() != CA_OK) {
             set_error("item planning failed (code %d)", err.load());
             return err.load();
@@ -407,28 +519,37 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         // Work unit = (item, span of TL_WU_SPAN partners), numbered span-major.  With the items in the order
         // of their first partner (`parts` is ascending, so slot order is that order), the items that reach into
         // span s are a prefix of the list, and a work-unit number decodes with one prefix array.
-        size_t total = 0;
-        for (auto& v : items_s) total += v.size();
-        items.reserve(total);
-        for (auto& v : items_s) items.insert(items.end(), v.begin(), v.end());
+        // Two kinds of items, two launches of the wave kernel (each kind gets its own register allocation): streaming
+        // items (one cluster with more than TL_CAP cells) first, resident items second.  Both lists keep the order of
+        // the first partner, so "the items that reach into span s" is a prefix of each.  They are written straight
+        // into the pinned staging buffer: [resident items][streaming items].
+        size_t cnt_kind[2] = {0, 0};
+        for (auto& v : items_s)
+            for (const Item& it : v) cnt_kind[it.npos > TL_CAP ? 1 : 0]++;
+        CA_TRY(W.h_items.ensure(std::max<size_t>(cnt_kind[0] + cnt_kind[1], 1) * sizeof(Item)));
+        items_kind[0] = W.h_items.as<Item>();
+        items_kind[1] = items_kind[0] + cnt_kind[0];
+        n_kind[0] = n_kind[1] = 0;
+        for (auto& v : items_s)
+            for (const Item& it : v) {
+                const int kind = it.npos > TL_CAP ? 1 : 0;
+                items_kind[kind][n_kind[kind]++] = it;
+            }
+        lap("items merged");
     }
-    // Two kinds of items, two launches of the wave kernel (each kind gets its own register allocation): streaming
-    // items (one cluster with more than TL_CAP cells) first, resident items second.  Both lists keep the order of
-    // the first partner, so "the items that reach into super-tile s" is a prefix of each.
-    std::vector<Item> items_kind[2];  // [0] resident, [1] streaming
-    for (const Item& it : items) items_kind[it.npos > TL_CAP ? 1 : 0].push_back(it);
     std::vector<int32_t> h_wu_prefix_kind[2];
     for (int kind = 0; kind < 2; kind++) {
         std::vector<int32_t>& pre = h_wu_prefix_kind[kind];
-        const std::vector<Item>& v = items_kind[kind];
+        const Item* v = items_kind[kind];
+        const size_t nv = n_kind[kind];
         pre.assign(1, 0);
         int32_t jmax = 0;
-        for (const Item& it : v) jmax = std::max(jmax, it.jend);
+        for (size_t t = 0; t < nv; t++) jmax = std::max(jmax, v[t].jend);
         const int32_t nsuper = (jmax + TL_WU_SPAN - 1) / TL_WU_SPAN;
         size_t k = 0;
         int64_t tot = 0;
         for (int32_t sp = 0; sp < nsuper; sp++) {
-            while (k < v.size() && v[k].jbeg < (sp + 1) * TL_WU_SPAN) k++;
+            while (k < nv && v[k].jbeg < (sp + 1) * TL_WU_SPAN) k++;
             tot += (int64_t)k;
             if (tot > 0x7fffff00LL) {
                 set_error("too many work units (%lld)", (long long)tot);
@@ -451,19 +572,29 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     } else {
         inv_norm = 1.0 / (wsum * (wsum - 1.0) / 2.0);  // R/ECS.R:1471-1472
     }
+    lap("kinds, prefixes, weights");
     c.prof[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
 
     // ---- upload the item lists (cluster starts and the sort went out batch by batch above) -----------------------
     const size_t npre0 = h_wu_prefix_kind[0].size(), npre1 = h_wu_prefix_kind[1].size();
     CA_TRY(W.wu_prefix.ensure((npre0 + npre1) * 4));
-    CA_TRY(W.items.ensure(std::max<size_t>(items.size(), 1) * sizeof(Item)));
+    CA_TRY(W.items.ensure(std::max<size_t>(n_kind[0] + n_kind[1], 1) * sizeof(Item)));
     CA_TRY(W.w.ensure(h_w.size() * 8));
-    CA_CUDA(cudaMemcpyAsync(W.wu_prefix.p, h_wu_prefix_kind[0].data(), npre0 * 4, cudaMemcpyHostToDevice, s));
-    CA_CUDA(cudaMemcpyAsync(W.wu_prefix.as<int32_t>() + npre0, h_wu_prefix_kind[1].data(), npre1 * 4, cudaMemcpyHostToDevice, s));
-    CA_CUDA(cudaMemcpyAsync(W.w.p, h_w.data(), h_w.size() * 8, cudaMemcpyHostToDevice, s));
-    for (int kind = 0, off = 0; kind < 2; off += (int)items_kind[kind].size(), kind++)
-        if (!items_kind[kind].empty())
-            CA_CUDA(cudaMemcpyAsync(W.items.as<Item>() + off, items_kind[kind].data(), items_kind[kind].size() * sizeof(Item), cudaMemcpyHostToDevice, s));
+    {
+        char* hs = static_cast<char*>(W.h_small.p) + (((size_t)std::max(nparts, 1) * 4 + 63) & ~(size_t)63);
+        if ((size_t)(hs - static_cast<char*>(W.h_small.p)) + (npre0 + npre1) * 4 + 64 + h_w.size() * 8 > W.h_small.cap) {
+            set_error("internal: pinned staging block too small");
+            return CA_E_ARG;
+        }
+        memcpy(hs, h_wu_prefix_kind[0].data(), npre0 * 4);
+        memcpy(hs + npre0 * 4, h_wu_prefix_kind[1].data(), npre1 * 4);
+        CA_CUDA(cudaMemcpyAsync(W.wu_prefix.p, hs, (npre0 + npre1) * 4, cudaMemcpyHostToDevice, s));
+        char* hw = hs + (((npre0 + npre1) * 4 + 63) & ~(size_t)63);
+        memcpy(hw, h_w.data(), h_w.size() * 8);
+        CA_CUDA(cudaMemcpyAsync(W.w.p, hw, h_w.size() * 8, cudaMemcpyHostToDevice, s));
+    }
+    if (n_kind[0] + n_kind[1])
+        CA_CUDA(cudaMemcpyAsync(W.items.p, W.h_items.p, (n_kind[0] + n_kind[1]) * sizeof(Item), cudaMemcpyHostToDevice, s));
 
     // ---- the wave kernel ----------------------------------------------------------------------------
     TileParams T;
@@ -507,7 +638,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         if (h_w[p] != 1.0) T.unit_w = 0;
     CA_TRY(launch_qinfo(T, W.parts.as<int32_t>(), nparts, s));
     for (int kind = 1; kind >= 0; kind--) {  // the long streaming items first
-        T.items = W.items.as<Item>() + (kind == 1 ? items_kind[0].size() : 0);
+        T.items = W.items.as<Item>() + (kind == 1 ? n_kind[0] : 0);
         T.wu_prefix = W.wu_prefix.as<int32_t>() + (kind == 1 ? npre0 : 0);
         T.nsuper = (int32_t)h_wu_prefix_kind[kind].size() - 1;
         T.nwu = h_wu_prefix_kind[kind].back();
@@ -573,7 +704,9 @@ void ca_shutdown(void) {
     cudaDeviceSynchronize();
     Workspace& W = ws();
     W.perm.release(); W.cstart.release(); W.crow.release(); W.items.release(); W.parts.release(); W.w.release(); W.wu_prefix.release(); W.qinfo.release();
+    W.h_cstart.release(); W.h_crow.release(); W.h_items.release(); W.h_small.release();
     dev_cache_release();
+    pool().shutdown();
     for (int i = 0; i < 8; i++)
         if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
     if (c.own_stream) { cudaStreamDestroy(c.own_stream); c.own_stream = nullptr; }

@@ -36,7 +36,7 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
     // Everything below is flat arrays reused across calls (one planner per host thread): the planner runs once per
     // owned partition and sits between two GPU stages, so its allocations were what it spent its time on.
     struct Scratch {
-        std::vector<uint64_t> keys;                    // (size << 32 | ~index) per cluster, sorted descending
+        std::vector<uint64_t> keys, tmp;               // cluster indices, sorted by decreasing size
         std::vector<int32_t> head, next, bin_of, bin_rows, bin_start, member, big;
         std::vector<int64_t> bin_used;
         std::vector<uint64_t> nonempty;
@@ -45,16 +45,29 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
 
     auto padded = [&](int32_t s) { return (int64_t)((s + align - 1) / align) * align; };
 
-    // clusters by decreasing size, ties by increasing index (what a stable sort by size gives)
-    S.keys.resize(k);
+    // clusters by decreasing size, ties by increasing index (what a stable sort by size gives): a stable LSD radix
+    // sort of the indices on the key (max size - size), 11 bits per pass, as many passes as the largest size needs
+    S.keys.resize(k);   // keys[c] = index permutation being sorted
+    S.tmp.resize(k);
+    int32_t smax = 0;
     for (int32_t c = 0; c < k; c++) {
         if (sizes[c] <= 0) {
             set_error("plan_blocks: cluster %d has size %d (must be > 0)", c, sizes[c]);
             return CA_E_ARG;
         }
-        S.keys[c] = ((uint64_t)(uint32_t)sizes[c] << 32) | (uint32_t)(0x7fffffff - c);
+        smax = std::max(smax, sizes[c]);
+        S.keys[c] = (uint64_t)c;
     }
-    std::sort(S.keys.begin(), S.keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
+    for (int shift = 0; shift < 32 && ((uint32_t)smax >> shift) != 0; shift += 11) {
+        uint32_t hist[2049] = {0};
+        for (int32_t t = 0; t < k; t++) hist[((((uint32_t)(smax - sizes[S.keys[t]])) >> shift) & 2047u) + 1]++;
+        for (int b = 0; b < 2048; b++) hist[b + 1] += hist[b];
+        for (int32_t t = 0; t < k; t++) {
+            const uint64_t c = S.keys[t];
+            S.tmp[hist[(((uint32_t)(smax - sizes[c])) >> shift) & 2047u]++] = c;
+        }
+        S.keys.swap(S.tmp);
+    }
 
     // open bins by remaining capacity (in units of `align`): per-capacity LIFO lists threaded through `next` + a bitmap of
     // the non-empty lists, so "smallest remaining capacity that still holds p" is a find-next-set-bit
@@ -76,7 +89,7 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
     };
 
     for (int32_t idx = 0; idx < k; idx++) {
-        const int32_t c = 0x7fffffff - (int32_t)(uint32_t)(S.keys[idx] & 0xffffffffu);
+        const int32_t c = (int32_t)S.keys[idx];
         const int64_t p = padded(sizes[c]);
         if (p > cap) {
             S.big.push_back(c);
@@ -112,7 +125,7 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
     S.member.resize(S.bin_start[nbins]);
     for (int32_t b = 0; b < nbins; b++) S.bin_rows[b] = 0;  // reused as the fill cursor
     for (int32_t idx = 0; idx < k; idx++) {
-        const int32_t c = 0x7fffffff - (int32_t)(uint32_t)(S.keys[idx] & 0xffffffffu);
+        const int32_t c = (int32_t)S.keys[idx];
         const int32_t b = S.bin_of[c];
         if (b >= 0) S.member[S.bin_start[b] + S.bin_rows[b]++] = c;
     }

@@ -273,6 +273,24 @@ def test_many_clusters_one_block_per_sm_configuration():
     assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
 
 
+def test_cluster_counts_up_to_the_table_row_limit():
+    """A partner with 24 000 clusters needs 96 KB per table row: one row per item, one partner per phase.  One with
+    30 000 does not fit a table buffer at all: the batched engine refuses it (CA_E_UNSUPPORTED), it never truncates."""
+    rng = np.random.default_rng(29)
+    n = 120_000
+    L = np.stack([rng.integers(0, 24_000, size=n), rng.integers(0, 7, size=n), rng.integers(0, 300, size=n)]).astype(np.int32)
+    ecc, sim = oracle.weighted_element_consistency(L, calculate_sim_matrix=True)
+    res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+    L[0] = rng.integers(0, 30_000, size=n)
+    L[0][:30_000] = np.arange(30_000)
+    with pytest.raises(_capi.ClustAssessError) as e:
+        ecs.weighted_element_consistency(list(L))
+    assert e.value.code == -6  # CA_E_UNSUPPORTED
+    # the per-pair entry points have no such limit
+    assert np.array_equal(ecs.element_sim_elscore(L[0], L[2]), oracle.disjoint_ecs(L[0], L[2]))
+
+
 def test_identical_partitions_and_m_not_multiple_of_tile():
     rng = np.random.default_rng(19)
     base = rng.integers(0, 12, size=4000).astype(np.int32)
