@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--n", type=int, default=None, help="override the number of cells")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=25.0, help="target CPU work of the cpu_baseline sample")
     return ap.parse_args()
 
 
