@@ -25,15 +25,43 @@ static constexpr unsigned FULL = 0xffffffffu;
 // ------------------------------------------------------------------------------------------------
 // per-partition min / max
 // ------------------------------------------------------------------------------------------------
+// A partition's label vector starts at raw + p n: 16-byte aligned only if p n is a multiple of 4.  vec_bounds() cuts it
+// into an unaligned head (< 4 elements), a body of int4 and a tail, so that the streaming kernels below read 16 bytes
+// per thread and load whatever n is.
+__device__ __forceinline__ void vec_bounds(const int32_t* x, int64_t n, int64_t& head, int64_t& nvec) {
+    head = (int64_t)((4 - ((reinterpret_cast<uintptr_t>(x) >> 2) & 3)) & 3);
+    if (head > n) head = n;
+    nvec = (n - head) >> 2;
+}
+
 __global__ void __launch_bounds__(256) minmax_kernel(const int32_t* __restrict__ raw, int64_t n, int32_t* __restrict__ d_min,
                                                      int32_t* __restrict__ d_max) {
     const int p = blockIdx.y;
     const int32_t* x = raw + (int64_t)p * n;
     int lo = INT32_MAX, hi = INT32_MIN;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int v = __ldg(x + i);
-        lo = min(lo, v);
-        hi = max(hi, v);
+    int64_t head, nvec;
+    vec_bounds(x, n, head, nvec);
+    const int4* xv = reinterpret_cast<const int4*>(x + head);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < nvec; i += 2 * stride) {  // two independent 16-byte loads in flight per thread
+        const int4 a = __ldg(xv + i), b = __ldg(xv + i + stride);
+        lo = min(min(min(lo, a.x), min(a.y, a.z)), min(min(a.w, b.x), min(min(b.y, b.z), b.w)));
+        hi = max(max(max(hi, a.x), max(a.y, a.z)), max(max(a.w, b.x), max(max(b.y, b.z), b.w)));
+    }
+    if (i < nvec) {
+        const int4 a = __ldg(xv + i);
+        lo = min(min(lo, a.x), min(min(a.y, a.z), a.w));
+        hi = max(max(hi, a.x), max(max(a.y, a.z), a.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) {  // head and tail: at most 3 elements each
+        const int64_t t = threadIdx.x < 4 ? (int64_t)threadIdx.x : head + 4 * nvec + (threadIdx.x - 4);
+        const bool ok = threadIdx.x < 4 ? t < head : t < n;
+        if (ok) {
+            const int v = __ldg(x + t);
+            lo = min(lo, v);
+            hi = max(hi, v);
+        }
     }
     lo = __reduce_min_sync(FULL, lo);
     hi = __reduce_max_sync(FULL, hi);
@@ -58,7 +86,7 @@ int launch_fill_i32(int32_t* x, int64_t n, int32_t v, cudaStream_t s) {
 int launch_minmax(const int32_t* raw, int64_t n, int32_t m, int32_t* d_min, int32_t* d_max, cudaStream_t s) {
     fill_i32_kernel<<<(m + 255) / 256, 256, 0, s>>>(d_min, m, INT32_MAX);
     fill_i32_kernel<<<(m + 255) / 256, 256, 0, s>>>(d_max, m, INT32_MIN);
-    int64_t nb = (n + 256 * 16 - 1) / (256 * 16);
+    int64_t nb = (n + 256 * 32 - 1) / (256 * 32);  // 32 elements (two 16-byte loads, four trips) per thread
     if (nb < 1) nb = 1;
     if (nb > 4096) nb = 4096;
     dim3 grid((unsigned)nb, (unsigned)m);
@@ -85,13 +113,27 @@ __global__ void __launch_bounds__(512) count_kernel(const int32_t* __restrict__ 
         for (int i = threadIdx.x; i < range; i += blockDim.x) sh[i] = 0;
         __syncthreads();
     }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int v = __ldg(x + i) - mn;
-        if (use_sh)
-            atomicAdd(sh + v, 1u);
-        else
-            atomicAdd(g + v, 1u);
-    }
+    int64_t head, nvec;
+    vec_bounds(x, n, head, nvec);
+    const int4* xv = reinterpret_cast<const int4*>(x + head);
+    auto body = [&](auto add) {  // instantiated once per address space, so that the shared-memory case stays ATOMS
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+            const int4 a = __ldg(xv + i);
+            add(a.x - mn);
+            add(a.y - mn);
+            add(a.z - mn);
+            add(a.w - mn);
+        }
+        if (blockIdx.x == 0 && threadIdx.x < 8) {  // head and tail: at most 3 elements each
+            const int64_t t = threadIdx.x < 4 ? (int64_t)threadIdx.x : head + 4 * nvec + (threadIdx.x - 4);
+            const bool ok = threadIdx.x < 4 ? t < head : t < n;
+            if (ok) add(__ldg(x + t) - mn);
+        }
+    };
+    if (use_sh)
+        body([&](int v) { atomicAdd(sh + v, 1u); });
+    else
+        body([&](int v) { atomicAdd(g + v, 1u); });
     if (use_sh) {
         __syncthreads();
         for (int i = threadIdx.x; i < range; i += blockDim.x) {
@@ -103,7 +145,7 @@ __global__ void __launch_bounds__(512) count_kernel(const int32_t* __restrict__ 
 
 int launch_count(const int32_t* raw, int64_t n, int32_t m, const int32_t* d_min, const int64_t* d_roff,
                  const int32_t* /*h_range*/, int32_t max_range, uint32_t* d_cnt, cudaStream_t s) {
-    int64_t nb = (n + 512 * 32 - 1) / (512 * 32);
+    int64_t nb = (n + 512 * 64 - 1) / (512 * 64);  // 64 elements (sixteen 16-byte loads) per thread
     if (nb < 1) nb = 1;
     if (nb > 1024) nb = 1024;
     dim3 grid((unsigned)nb, (unsigned)m);
@@ -233,27 +275,43 @@ __global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* _
                                                                 const int64_t* __restrict__ d_roff,
                                                                 const int32_t* __restrict__ d_kcount,
                                                                 uint16_t* __restrict__ lab16) {
-    __shared__ uint16_t tile[TP][TC + 2];
+    __shared__ __align__(16) uint16_t tile[TP][TC + 2];
     const int64_t c0 = (int64_t)blockIdx.x * TC;
     const int p0 = blockIdx.y * TP;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // every partition's row is 16-byte aligned and the tile is full
+    const bool vec = (n & 3) == 0 && c0 + TC <= n && (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
     for (int pp = wid; pp < TP; pp += 8) {
         const int p = p0 + pp;
         if (p < m) {
             const int32_t* x = raw + (int64_t)p * n;
             const int mn = d_min[p];
             const uint32_t* rk = d_rank ? d_rank + d_roff[p] : nullptr;
-#pragma unroll
-            for (int q = 0; q < TC / 32; q++) {
-                int64_t c = c0 + lane + 32 * q;
-                uint32_t v = 0;
-                if (c < n) {
-                    v = (uint32_t)(__ldg(x + c) - mn);
-                    if (rk) v = __ldg(rk + v);
-                } else if (c == n) {
-                    v = (uint32_t)d_kcount[p];  // the pad cell
+            if (vec) {  // one 16-byte load per lane: cells c0 + 4 lane .. + 3
+                const int4 a = __ldg(reinterpret_cast<const int4*>(x + c0) + lane);
+                uint32_t v0 = (uint32_t)(a.x - mn), v1 = (uint32_t)(a.y - mn), v2 = (uint32_t)(a.z - mn), v3 = (uint32_t)(a.w - mn);
+                if (rk) {
+                    v0 = __ldg(rk + v0);
+                    v1 = __ldg(rk + v1);
+                    v2 = __ldg(rk + v2);
+                    v3 = __ldg(rk + v3);
                 }
-                tile[pp][lane + 32 * q] = (uint16_t)v;
+                uint32_t* t32 = reinterpret_cast<uint32_t*>(&tile[pp][4 * lane]);  // row stride 130 uint16 = 260 bytes: 4-byte aligned
+                t32[0] = (v0 & 0xffffu) | (v1 << 16);
+                t32[1] = (v2 & 0xffffu) | (v3 << 16);
+            } else {
+#pragma unroll
+                for (int q = 0; q < TC / 32; q++) {
+                    int64_t c = c0 + lane + 32 * q;
+                    uint32_t v = 0;
+                    if (c < n) {
+                        v = (uint32_t)(__ldg(x + c) - mn);
+                        if (rk) v = __ldg(rk + v);
+                    } else if (c == n) {
+                        v = (uint32_t)d_kcount[p];  // the pad cell
+                    }
+                    tile[pp][lane + 32 * q] = (uint16_t)v;
+                }
             }
         } else {
 #pragma unroll
