@@ -504,7 +504,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                 continue;
             }
             launch_rc = launch_sort(L.d_raw, n, L.d_min.as<int32_t>(), L.identity ? nullptr : L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(),
-                                    W.cstart.as<int32_t>() + (size_t)b0 * L.kp, L.kp, W.parts.as<int32_t>() + b0, nb,
+                                    L.d_kcount.as<int32_t>(), W.cstart.as<int32_t>() + (size_t)b0 * L.kp, L.kp, W.parts.as<int32_t>() + b0, nb,
                                     W.perm.as<int32_t>() + (size_t)b0 * perm_stride, perm_stride, s);
         }
         lap("last batch launched");

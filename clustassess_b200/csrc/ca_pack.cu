@@ -427,12 +427,96 @@ __global__ void __launch_bounds__(512) sort_kernel(const int32_t* __restrict__ r
     }
 }
 
+// The same sort, one chunk of SC_CELLS cells per block, with the chunk sorted in shared memory first:
+//   1. every cell's label goes to shared memory and claims its rank inside (chunk, cluster) with a shared-memory atomic;
+//   2. an exclusive scan of the per-cluster counts gives the chunk-local start of every cluster, and ONE global atomic per
+//      non-empty (chunk, cluster) claims that many consecutive positions of the cluster's segment in perm;
+//   3. the cells are written to shared memory in cluster order, then out: adjacent threads write adjacent positions of a
+//      cluster's run, so a warp's store touches a handful of 32-byte sectors instead of 32 (the scattered 4-byte stores of
+//      sort_kernel are bound by the LSU's sector rate, like the label gather of the wave kernel).
+// No per-segment histogram / scan passes: the cursors start at cstart and move by atomics.
+constexpr int SC_CELLS = 16384, SC_THREADS = 1024;
+__global__ void __launch_bounds__(SC_THREADS, 2) sort_chunk_kernel(const int32_t* __restrict__ raw, int64_t n, const int32_t* __restrict__ d_min,
+                                                                const uint32_t* __restrict__ d_rank, const int64_t* __restrict__ d_roff,
+                                                                const int32_t* __restrict__ d_kcount, int32_t kp,
+                                                                const int32_t* __restrict__ d_parts, int32_t* __restrict__ d_perm,
+                                                                int64_t perm_stride, int32_t* __restrict__ d_cursor) {
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(sc_smem);                 // [kp] counts, then chunk-local starts
+    uint32_t* gbase = cnt + kp;                                           // [kp] first claimed position of the cluster's run
+    uint16_t* lab = reinterpret_cast<uint16_t*>(gbase + kp);              // [SC_CELLS] compact label of cell lo + i
+    uint16_t* rnk = lab + SC_CELLS;                                       // [SC_CELLS] rank inside (chunk, cluster)
+    uint16_t* sidx = rnk + SC_CELLS;                                      // [SC_CELLS] cell index at sorted position t
+    __shared__ uint32_t warp_tot[SC_THREADS / 32];
+    const int slot = blockIdx.y;
+    const int p = d_parts[slot];
+    const int32_t* x = raw + (int64_t)p * n;
+    const int mn = d_min[p];
+    const uint32_t* rk = d_rank ? d_rank + d_roff[p] : nullptr;
+    const int K = d_kcount[p];
+    const int64_t lo = (int64_t)blockIdx.x * SC_CELLS;
+    const int nloc = (int)((n - lo) < (int64_t)SC_CELLS ? (n - lo) : (int64_t)SC_CELLS);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int k = tid; k < K; k += SC_THREADS) cnt[k] = 0;
+    __syncthreads();
+    for (int i = tid; i < nloc; i += SC_THREADS) {
+        const uint32_t l = compact_of(x, lo + i, mn, rk);
+        lab[i] = (uint16_t)l;
+        rnk[i] = (uint16_t)atomicAdd(cnt + l, 1u);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..K): thread t owns the entries [t per, (t + 1) per)
+    const int per = (K + SC_THREADS - 1) / SC_THREADS;
+    const int k0 = min(K, tid * per), k1 = min(K, k0 + per);
+    uint32_t mine = 0;
+    for (int k = k0; k < k1; k++) mine += cnt[k];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t run = incl - mine;
+    for (int w = 0; w < wid; w++) run += warp_tot[w];
+    int32_t* cursor = d_cursor + (int64_t)slot * kp;
+    for (int k = k0; k < k1; k++) {
+        const uint32_t c = cnt[k];
+        cnt[k] = run;
+        gbase[k] = c ? (uint32_t)atomicAdd(cursor + k, (int32_t)c) : 0u;
+        run += c;
+    }
+    __syncthreads();
+    for (int i = tid; i < nloc; i += SC_THREADS) sidx[cnt[lab[i]] + rnk[i]] = (uint16_t)i;
+    __syncthreads();
+    int32_t* out = d_perm + (int64_t)slot * perm_stride;
+    for (int t = tid; t < nloc; t += SC_THREADS) {
+        const uint32_t i = sidx[t], l = lab[i];
+        out[gbase[l] + ((uint32_t)t - cnt[l])] = (int32_t)(lo + i);
+    }
+}
+
 int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
-                const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
+                const int32_t* d_kcount, const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
                 int64_t perm_stride, cudaStream_t s) {
     if (nparts == 0) return CA_OK;
     CA_CUDA(cudaMemsetAsync(d_perm, 0xff, (size_t)nparts * (size_t)perm_stride * sizeof(int32_t), s));
     static DevBuf segcur;
+    {   // chunk sort: counts + run bases ([kp] each) and three uint16 arrays of SC_CELLS entries in shared memory
+        const size_t smem = (size_t)kp * 8 + (size_t)SC_CELLS * 6;
+        if (smem <= 200 * 1024 && getenv("CA_SORT_LEGACY") == nullptr) {  // two blocks per SM up to ~2100 clusters, one beyond
+            CA_TRY(segcur.ensure((size_t)nparts * kp * 4));
+            CA_CUDA(cudaMemcpyAsync(segcur.p, d_cstart, (size_t)nparts * kp * 4, cudaMemcpyDeviceToDevice, s));
+            CA_CUDA(cudaFuncSetAttribute(sort_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const dim3 grid((unsigned)((n + SC_CELLS - 1) / SC_CELLS), (unsigned)nparts);
+            sort_chunk_kernel<<<grid, SC_THREADS, smem, s>>>(raw, n, d_min, d_rank, d_roff, d_kcount, kp, d_parts, d_perm, perm_stride,
+                                                             segcur.as<int32_t>());
+            CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+            return CA_OK;
+        }
+    }
+    // very large cluster counts: per-segment cursors, scattered stores
     const size_t per_warp = (size_t)kp * 4;
     const bool smem_ok = per_warp <= 200 * 1024;
     // segments: enough blocks to fill the machine, each at least 16k cells long; the shared-memory count
