@@ -405,6 +405,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
             if (owner_of(i, world) == rank) parts.push_back(i);
     }
     const int32_t nparts = (int32_t)parts.size();
+    bool qinfo_done = false;          // the sort wrote the quad info too (chunk sort)
+    std::vector<size_t> off_kind[2];  // items of each kind before slot sl
     Item* items_kind[2] = {nullptr, nullptr};  // [0] resident, [1] streaming: views into the pinned staging buffer, in slot order
     size_t n_kind[2] = {0, 0};
     // every cluster pads to a multiple of TL_CPT positions: an upper bound that does not wait for the planner
@@ -441,6 +443,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         const int nthreads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 32, (nparts + 7) / 8}));
         const int nbatch = nthreads > 1 ? (nparts >= 256 ? 8 : nparts >= 64 ? 4 : 1) : 1;
         std::vector<std::vector<Item>> items_s(nparts);  // per slot, the long (streaming) items first
+        std::vector<int32_t> nstream(std::max(nparts, 1), 0);  // per slot: how many of them are streaming items
         std::vector<int32_t> bnd(nbatch + 1);
         for (int b = 0; b <= nbatch; b++) bnd[b] = (int32_t)((int64_t)b * nparts / nbatch);
         std::vector<std::atomic<int>> left(nbatch);
@@ -479,6 +482,9 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                             v.push_back(it);
                         }
                         std::stable_sort(v.begin(), v.end(), [](const Item& a, const Item& b) { return a.npos > b.npos; });
+                        int32_t ns = 0;
+                        for (const Item& it : v) ns += it.npos > TL_CAP ? 1 : 0;
+                        nstream[sl] = ns;
                     }
                 }
                 left[b].fetch_sub(1, std::memory_order_release);
@@ -505,7 +511,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
             }
             launch_rc = launch_sort(L.d_raw, n, L.d_min.as<int32_t>(), L.identity ? nullptr : L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(),
                                     L.d_kcount.as<int32_t>(), W.cstart.as<int32_t>() + (size_t)b0 * L.kp, L.kp, W.parts.as<int32_t>() + b0, nb,
-                                    W.perm.as<int32_t>() + (size_t)b0 * perm_stride, perm_stride, s);
+                                    W.perm.as<int32_t>() + (size_t)b0 * perm_stride, perm_stride, W.crow.as<uint16_t>() + (size_t)b0 * L.kp,
+                                    L.d_sizes.as<int32_t>(), W.qinfo.as<uint32_t>() + (size_t)b0 * (perm_stride >> 2) * 2, &qinfo_done, s);
         }
         lap("last batch launched");
         if (nthreads > 1) pool().wait();
@@ -523,34 +530,53 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         // items (one cluster with more than TL_CAP cells) first, resident items second.  Both lists keep the order of
         // the first partner, so "the items that reach into span s" is a prefix of each.  They are written straight
         // into the pinned staging buffer: [resident items][streaming items].
-        size_t cnt_kind[2] = {0, 0};
-        for (auto& v : items_s)
-            for (const Item& it : v) cnt_kind[it.npos > TL_CAP ? 1 : 0]++;
-        CA_TRY(W.h_items.ensure(std::max<size_t>(cnt_kind[0] + cnt_kind[1], 1) * sizeof(Item)));
+        // per-slot offsets of both kinds (the workers counted their slots' streaming items), then the pool copies
+        off_kind[0].assign(nparts + 1, 0);
+        off_kind[1].assign(nparts + 1, 0);
+        for (int32_t sl = 0; sl < nparts; sl++) {
+            off_kind[1][sl + 1] = off_kind[1][sl] + (size_t)nstream[sl];
+            off_kind[0][sl + 1] = off_kind[0][sl] + (items_s[sl].size() - (size_t)nstream[sl]);
+        }
+        n_kind[0] = off_kind[0][nparts];
+        n_kind[1] = off_kind[1][nparts];
+        CA_TRY(W.h_items.ensure(std::max<size_t>(n_kind[0] + n_kind[1], 1) * sizeof(Item)));
         items_kind[0] = W.h_items.as<Item>();
-        items_kind[1] = items_kind[0] + cnt_kind[0];
-        n_kind[0] = n_kind[1] = 0;
-        for (auto& v : items_s)
-            for (const Item& it : v) {
-                const int kind = it.npos > TL_CAP ? 1 : 0;
-                items_kind[kind][n_kind[kind]++] = it;
+        items_kind[1] = items_kind[0] + n_kind[0];
+        std::atomic<int> next_slot{0};
+        auto fill = [&]() {
+            for (;;) {
+                const int32_t s0 = next_slot.fetch_add(16);
+                if (s0 >= nparts) break;
+                for (int32_t sl = s0; sl < std::min(nparts, s0 + 16); sl++) {
+                    size_t o[2] = {off_kind[0][sl], off_kind[1][sl]};
+                    for (const Item& it : items_s[sl]) {
+                        const int kind = it.npos > TL_CAP ? 1 : 0;
+                        items_kind[kind][o[kind]++] = it;
+                    }
+                }
             }
+        };
+        if (nthreads > 1 && nparts >= 64) {
+            pool().start(nthreads, fill);
+            pool().wait();
+        } else {
+            fill();
+        }
         lap("items merged");
     }
+    // work units before span sp = items whose first partner lies before the end of span sp, summed over the spans so far.
+    // All items of a slot share their partner range, so this walks the slots (off_kind = items before a slot), not the items.
     std::vector<int32_t> h_wu_prefix_kind[2];
     for (int kind = 0; kind < 2; kind++) {
         std::vector<int32_t>& pre = h_wu_prefix_kind[kind];
-        const Item* v = items_kind[kind];
-        const size_t nv = n_kind[kind];
         pre.assign(1, 0);
-        int32_t jmax = 0;
-        for (size_t t = 0; t < nv; t++) jmax = std::max(jmax, v[t].jend);
+        const int32_t jmax = n_kind[kind] ? (ref_only >= 0 ? m_partners : m) : 0;
         const int32_t nsuper = (jmax + TL_WU_SPAN - 1) / TL_WU_SPAN;
-        size_t k = 0;
+        int32_t t = 0;  // slots whose items have started
         int64_t tot = 0;
         for (int32_t sp = 0; sp < nsuper; sp++) {
-            while (k < nv && v[k].jbeg < (sp + 1) * TL_WU_SPAN) k++;
-            tot += (int64_t)k;
+            while (t < nparts && (ref_only >= 0 ? 0 : parts[t] + 1) < (sp + 1) * TL_WU_SPAN) t++;
+            tot += (int64_t)off_kind[kind][t];
             if (tot > 0x7fffff00LL) {
                 set_error("too many work units (%lld)", (long long)tot);
                 return CA_E_UNSUPPORTED;
@@ -636,7 +662,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
 #endif
     for (int32_t p = 0; p < mw; p++)
         if (h_w[p] != 1.0) T.unit_w = 0;
-    CA_TRY(launch_qinfo(T, W.parts.as<int32_t>(), nparts, s));
+    if (!qinfo_done) CA_TRY(launch_qinfo(T, W.parts.as<int32_t>(), nparts, s));
     for (int kind = 1; kind >= 0; kind--) {  // the long streaming items first
         T.items = W.items.as<Item>() + (kind == 1 ? n_kind[0] : 0);
         T.wu_prefix = W.wu_prefix.as<int32_t>() + (kind == 1 ? npre0 : 0);

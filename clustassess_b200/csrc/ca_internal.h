@@ -125,7 +125,7 @@ int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t m
                              const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_kcount, uint16_t* d_lab16, cudaStream_t s);
 int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
                 const int32_t* d_kcount, const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
-                int64_t perm_stride, cudaStream_t s);
+                int64_t perm_stride, const uint16_t* d_crow, const int32_t* d_sizes, uint32_t* d_qinfo, bool* qinfo_done, cudaStream_t s);
 
 // ca_tile.cu -- the all-pairs engine: persistent blocks of TL_THREADS consumer threads x 4 cells (+ 1 producer warp),
 // work units of 16 partners

@@ -440,7 +440,9 @@ __global__ void __launch_bounds__(SC_THREADS, 2) sort_chunk_kernel(const int32_t
                                                                 const uint32_t* __restrict__ d_rank, const int64_t* __restrict__ d_roff,
                                                                 const int32_t* __restrict__ d_kcount, int32_t kp,
                                                                 const int32_t* __restrict__ d_parts, int32_t* __restrict__ d_perm,
-                                                                int64_t perm_stride, int32_t* __restrict__ d_cursor) {
+                                                                int64_t perm_stride, int32_t* __restrict__ d_cursor,
+                                                                const uint16_t* __restrict__ d_crow, const int32_t* __restrict__ d_sizes,
+                                                                uint2* __restrict__ d_qinfo) {
     extern __shared__ __align__(16) unsigned char sc_smem[];
     uint32_t* cnt = reinterpret_cast<uint32_t*>(sc_smem);                 // [kp] counts, then chunk-local starts
     uint32_t* gbase = cnt + kp;                                           // [kp] first claimed position of the cluster's run
@@ -490,16 +492,25 @@ __global__ void __launch_bounds__(SC_THREADS, 2) sort_chunk_kernel(const int32_t
     __syncthreads();
     for (int i = tid; i < nloc; i += SC_THREADS) sidx[cnt[lab[i]] + rnk[i]] = (uint16_t)i;
     __syncthreads();
+    // The thread that writes the first position of a quad also writes the quad's info for the wave kernel: {row of the
+    // cluster inside its item, cluster size}.  A cluster's segment starts at a multiple of 4 and its padding sits at the
+    // tail, so the first position of every quad of the segment holds a real cell: exactly one writer per quad.
     int32_t* out = d_perm + (int64_t)slot * perm_stride;
+    uint2* qout = d_qinfo + (int64_t)slot * (perm_stride >> 2);
+    const uint16_t* crow = d_crow + (int64_t)slot * kp;
+    const int32_t* sizes = d_sizes + (int64_t)p * kp;
     for (int t = tid; t < nloc; t += SC_THREADS) {
         const uint32_t i = sidx[t], l = lab[i];
-        out[gbase[l] + ((uint32_t)t - cnt[l])] = (int32_t)(lo + i);
+        const uint32_t pos = gbase[l] + ((uint32_t)t - cnt[l]);
+        out[pos] = (int32_t)(lo + i);
+        if ((pos & 3u) == 0u) qout[pos >> 2] = make_uint2((uint32_t)__ldg(crow + l), (uint32_t)__ldg(sizes + l));
     }
 }
 
 int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
                 const int32_t* d_kcount, const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
-                int64_t perm_stride, cudaStream_t s) {
+                int64_t perm_stride, const uint16_t* d_crow, const int32_t* d_sizes, uint32_t* d_qinfo, bool* qinfo_done, cudaStream_t s) {
+    *qinfo_done = false;
     if (nparts == 0) return CA_OK;
     CA_CUDA(cudaMemsetAsync(d_perm, 0xff, (size_t)nparts * (size_t)perm_stride * sizeof(int32_t), s));
     static DevBuf segcur;
@@ -511,8 +522,9 @@ int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint3
             CA_CUDA(cudaFuncSetAttribute(sort_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const dim3 grid((unsigned)((n + SC_CELLS - 1) / SC_CELLS), (unsigned)nparts);
             sort_chunk_kernel<<<grid, SC_THREADS, smem, s>>>(raw, n, d_min, d_rank, d_roff, d_kcount, kp, d_parts, d_perm, perm_stride,
-                                                             segcur.as<int32_t>());
+                                                             segcur.as<int32_t>(), d_crow, d_sizes, reinterpret_cast<uint2*>(d_qinfo));
             CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+            *qinfo_done = true;
             return CA_OK;
         }
     }
