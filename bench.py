@@ -327,6 +327,33 @@ def run_b200(args):
                "entry": "ca_consistency (host buffers)" if world == 1 else "sharded upload + all_gather + ca_consistency_partial_dev + all_reduce + finish + D2H",
                "ecc_mean": float(np.mean(out))}
 
+    # ---- the same entry with PAGEABLE host buffers (what R's own vectors are): the library stages the upload through
+    # pinned slots on several host threads; CA_UPLOAD_DIRECT=1 is the plain cudaMemcpyAsync, timed beside it ---------
+    if e2e is not None and world == 1:
+        try:
+            pageable = np.array(host.numpy())  # ordinary malloc'ed memory
+            w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+            out = np.empty(n, dtype=np.float64)
+
+            def timed(reps):
+                _capi.check(lib.ca_consistency(pageable.reshape(-1), n, m, _capi._opt(w), out, None))  # warm-up
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    _capi.check(lib.ca_consistency(pageable.reshape(-1), n, m, _capi._opt(w), out, None))
+                return 1e3 * (time.perf_counter() - t0) / reps
+
+            staged_ms = timed(2)
+            os.environ["CA_UPLOAD_DIRECT"] = "1"
+            direct_ms = timed(2)
+            del os.environ["CA_UPLOAD_DIRECT"]
+            e2e["pageable"] = {"value": units / (staged_ms * 1e-3), "ms_per_step": staged_ms, "direct_memcpy_ms_per_step": direct_ms,
+                               "upload": "staged: 8 host threads x 2 pinned 4 MB slots (ca_api.cu upload_segments)",
+                               "ecc_mean": float(np.mean(out))}
+            del pageable
+        except Exception as ex:  # the headline numbers above do not depend on this leg
+            os.environ.pop("CA_UPLOAD_DIRECT", None)
+            e2e["pageable"] = {"error": str(ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

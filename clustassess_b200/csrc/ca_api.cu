@@ -365,6 +365,124 @@ static Workspace& ws() {
     return w;
 }
 
+// ---- host -> device upload ----------------------------------------------------------------------------
+// The R shim hands over R's own vectors, i.e. PAGEABLE memory.  cudaMemcpyAsync from pageable memory is staged by
+// the driver through one small pinned buffer on one thread and reaches a fraction of the PCIe rate; at config 5
+// (2 GB of labels) that copy would cost more than the whole computation.  Large pageable uploads are therefore
+// staged here: up to 8 host threads copy 4 MB chunks into their own pair of pinned slots and enqueue the
+// slot -> device DMA on the caller's stream, so the host memcpys of all threads overlap each other and the DMA.
+// Pinned / registered sources (bench.py's e2e buffers, torch pinned tensors) and small uploads go straight to
+// cudaMemcpyAsync.  CA_UPLOAD_DIRECT=1 forces the direct path (for A/B measurements).
+struct UploadSeg {
+    const void* src;
+    void* dst;
+    size_t bytes;
+};
+namespace {
+struct Stager {
+    static constexpr int MAXT = 8, SLOTS = 2;
+    static constexpr size_t CHUNK = 4u << 20;
+    char* pinned = nullptr;
+    cudaEvent_t ev[MAXT][SLOTS] = {};
+    bool used[MAXT][SLOTS] = {};
+    int ensure() {
+        if (pinned) return CA_OK;
+        cudaError_t e = cudaHostAlloc((void**)&pinned, (size_t)MAXT * SLOTS * CHUNK, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            pinned = nullptr;
+            (void)cudaGetLastError();
+            return CA_E_NOMEM;  // the caller falls back to the direct copy
+        }
+        for (int t = 0; t < MAXT; t++)
+            for (int k = 0; k < SLOTS; k++) {
+                if (cudaEventCreateWithFlags(&ev[t][k], cudaEventDisableTiming) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    release();
+                    return CA_E_CUDA;
+                }
+                used[t][k] = false;
+            }
+        return CA_OK;
+    }
+    void release() {
+        for (int t = 0; t < MAXT; t++)
+            for (int k = 0; k < SLOTS; k++) {
+                if (ev[t][k]) cudaEventDestroy(ev[t][k]);
+                ev[t][k] = nullptr;
+                used[t][k] = false;
+            }
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr;
+    }
+    char* slot(int t, int k) { return pinned + ((size_t)t * SLOTS + k) * CHUNK; }
+};
+Stager& stager() {
+    static Stager s;
+    return s;
+}
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+}  // namespace
+
+static int upload_segments(const UploadSeg* segs, size_t nseg, cudaStream_t s) {
+    size_t total = 0;
+    for (size_t i = 0; i < nseg; i++) total += segs[i].bytes;
+    if (total == 0) return CA_OK;
+    bool staged = total >= 2 * Stager::CHUNK && getenv("CA_UPLOAD_DIRECT") == nullptr;
+    for (size_t i = 0; staged && i < nseg; i++)
+        if (segs[i].bytes && !is_pageable(segs[i].src)) staged = false;
+    if (staged && stager().ensure() != CA_OK) staged = false;
+    if (!staged) {
+        for (size_t i = 0; i < nseg; i++)
+            if (segs[i].bytes) CA_CUDA(cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].bytes, cudaMemcpyHostToDevice, s));
+        return CA_OK;
+    }
+    Stager& S = stager();
+    std::vector<UploadSeg> chunks;
+    chunks.reserve(total / Stager::CHUNK + nseg);
+    for (size_t i = 0; i < nseg; i++)
+        for (size_t off = 0; off < segs[i].bytes; off += Stager::CHUNK)
+            chunks.push_back({(const char*)segs[i].src + off, (char*)segs[i].dst + off, std::min(Stager::CHUNK, segs[i].bytes - off)});
+    const int nthreads = (int)std::max<size_t>(1, std::min<size_t>({(size_t)Stager::MAXT, (size_t)std::thread::hardware_concurrency() / 2, chunks.size()}));
+    const int device = ctx().device;
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{(int)cudaSuccess};
+    auto work = [&](int t) {
+        if (cudaError_t e0 = cudaSetDevice(device)) { failed = (int)e0; return; }
+        int k = 0;
+        for (size_t c; (c = next.fetch_add(1)) < chunks.size() && failed == (int)cudaSuccess; k ^= 1) {
+            cudaError_t e = S.used[t][k] ? cudaEventSynchronize(S.ev[t][k]) : cudaSuccess;  // the slot's previous DMA has read it
+            if (e == cudaSuccess) {
+                memcpy(S.slot(t, k), chunks[c].src, chunks[c].bytes);
+                e = cudaMemcpyAsync(chunks[c].dst, S.slot(t, k), chunks[c].bytes, cudaMemcpyHostToDevice, s);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(S.ev[t][k], s);
+            if (e != cudaSuccess) { failed = (int)e; return; }
+            S.used[t][k] = true;
+        }
+    };
+    std::vector<std::thread> helpers;
+    helpers.reserve(nthreads);
+    try {
+        for (int t = 1; t < nthreads; t++) helpers.emplace_back(work, t);
+    } catch (...) {  // no more threads to be had: the ones that started (and this one) take all chunks
+    }
+    work(0);
+    for (auto& th : helpers) th.join();
+    if (failed != (int)cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("host-to-device copy failed: %s", cudaGetErrorString((cudaError_t)failed.load()));
+        return CA_E_CUDA;
+    }
+    return CA_OK;
+}
+
 // The all-pairs job (or one rank's share of it).  pairs: for every owned partition i, partners j in
 // (i, m) -- or, in agreement mode, partition `ref_only` against all j in [0, m_partners).
 static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int32_t world, double* d_ecc, double* d_sim,
@@ -731,6 +849,7 @@ void ca_shutdown(void) {
     Workspace& W = ws();
     W.perm.release(); W.cstart.release(); W.crow.release(); W.items.release(); W.parts.release(); W.w.release(); W.wu_prefix.release(); W.qinfo.release();
     W.h_cstart.release(); W.h_crow.release(); W.h_items.release(); W.h_small.release();
+    stager().release();
     dev_cache_release();
     pool().shutdown();
     for (int i = 0; i < 8; i++)
@@ -815,7 +934,8 @@ int ca_labels_upload(ca_labels_t* h, const int32_t* labels) {
     if (!h || !labels) { set_error("ca_labels_upload: NULL argument"); return CA_E_ARG; }
     CA_TRY(ensure_init());
     cudaStream_t s = ctx().stream;
-    CA_CUDA(cudaMemcpyAsync(h->L.d_raw, labels, (size_t)h->L.n * h->L.m * 4, cudaMemcpyHostToDevice, s));
+    const UploadSeg seg = {labels, h->L.d_raw, (size_t)h->L.n * h->L.m * 4};
+    CA_TRY(upload_segments(&seg, 1, s));
     CA_CUDA(cudaStreamSynchronize(s));
     h->L.prepared = h->L.ranked = false;
     return CA_OK;
@@ -825,7 +945,8 @@ int ca_labels_upload_col(ca_labels_t* h, int32_t p, const int32_t* col) {
     if (!h || !col || p < 0 || p >= h->L.m) { set_error("ca_labels_upload_col: bad argument"); return CA_E_ARG; }
     CA_TRY(ensure_init());
     cudaStream_t s = ctx().stream;
-    CA_CUDA(cudaMemcpyAsync(h->L.d_raw + (size_t)p * h->L.n, col, (size_t)h->L.n * 4, cudaMemcpyHostToDevice, s));
+    const UploadSeg seg = {col, h->L.d_raw + (size_t)p * h->L.n, (size_t)h->L.n * 4};
+    CA_TRY(upload_segments(&seg, 1, s));
     h->L.prepared = h->L.ranked = false;
     return CA_OK;
 }
@@ -893,10 +1014,12 @@ static int host_allpairs(const int32_t* labels, const int32_t* const* cols, int6
         if (labels) {
             rc = ca_labels_upload(h, labels);
         } else {
+            std::vector<UploadSeg> segs((size_t)m);  // all columns in one staged upload
             for (int32_t p = 0; p < m && rc == CA_OK; p++) {
                 if (!cols[p]) { set_error("NULL column pointer %d", p); rc = CA_E_ARG; break; }
-                rc = ca_labels_upload_col(h, p, cols[p]);
+                segs[p] = {cols[p], h->L.d_raw + (size_t)p * n, (size_t)n * 4};
             }
+            if (rc == CA_OK) rc = upload_segments(segs.data(), segs.size(), s);
         }
         if (rc != CA_OK) break;
         if (ecc_out) { rc = d_ecc.ensure((size_t)std::max<int64_t>(n, 1) * 8); if (rc) break; }
@@ -1024,9 +1147,10 @@ int ca_agreement(const int32_t* reference, const int32_t* labels, int64_t n, int
     int rc = CA_OK;
     static DevBuf d_out;
     do {
-        cudaError_t e = cudaMemcpyAsync(h->L.d_raw, labels, (size_t)n * m * 4, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h->L.d_raw + (size_t)n * m, reference, (size_t)n * 4, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) { set_error("host-to-device copy failed: %s", cudaGetErrorString(e)); rc = CA_E_CUDA; break; }
+        const UploadSeg segs[2] = {{labels, h->L.d_raw, (size_t)n * m * 4}, {reference, h->L.d_raw + (size_t)n * m, (size_t)n * 4}};
+        rc = upload_segments(segs, 2, s);
+        if (rc) break;
+        cudaError_t e = cudaSuccess;
         rc = d_out.ensure((size_t)std::max<int64_t>(n, 1) * 8);
         if (rc) break;
         e = cudaMemsetAsync(d_out.p, 0, (size_t)std::max<int64_t>(n, 1) * 8, s);
@@ -1055,8 +1179,8 @@ static int pair_upload(const int32_t* a, const int32_t* b, int64_t n, cudaStream
     CA_TRY(B.a.ensure((size_t)std::max<int64_t>(n, 1) * 4));
     CA_TRY(B.b.ensure((size_t)std::max<int64_t>(n, 1) * 4));
     if (n > 0) {
-        CA_CUDA(cudaMemcpyAsync(B.a.p, a, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-        CA_CUDA(cudaMemcpyAsync(B.b.p, b, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        const UploadSeg segs[2] = {{a, B.a.p, (size_t)n * 4}, {b, B.b.p, (size_t)n * 4}};
+        CA_TRY(upload_segments(segs, 2, s));
     }
     return CA_OK;
 }

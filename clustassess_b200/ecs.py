@@ -64,7 +64,7 @@ def _as_labels(x):
             raise ValueError("NA labels are not supported")
         return np.ascontiguousarray(np.trunc(a).astype(np.int32))
     if a.dtype.kind in "iub":
-        return np.ascontiguousarray(a.astype(np.int32))
+        return np.ascontiguousarray(a.astype(np.int32, copy=False))  # int32 input is passed on without a copy
     raise ValueError("unsupported label type %s" % a.dtype)
 
 
@@ -77,12 +77,21 @@ def _check_pair(c1, c2):
         raise ValueError("Not all elements of clustering1 and clustering2 are the same.")
 
 
-def _label_matrix(clustering_list):
+def _label_columns(clustering_list):
+    """The membership vectors as int32 columns plus the array of their addresses for the *_cols entry points --
+    what column_pointers() of r/calculate_ecs_b200.cpp hands over: R's list of vectors as it lies in memory, no
+    M x N copy on the host."""
     cols = [_as_labels(x) for x in clustering_list]
-    n = cols[0].size
+    n = cols[0].size if cols else 0
     for c in cols:
         if c.size != n:
             raise ValueError("The partitions do not have the same length")
+    ptrs = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    return cols, ptrs, len(cols), n
+
+
+def _label_matrix(clustering_list):
+    cols = _label_columns(clustering_list)[0]
     return np.ascontiguousarray(np.stack(cols)) if cols else np.zeros((0, 0), dtype=np.int32)
 
 
@@ -144,8 +153,7 @@ def weighted_element_consistency(clustering_list, weights=None, calculate_sim_ma
     """Weighted element-wise consistency (R/ECS.R:1446-1500)."""
     if len(clustering_list) <= 1:
         raise ValueError("At least two clusterings are required to calculate the consistency.")
-    lab = _label_matrix(clustering_list)
-    m, n = lab.shape
+    cols, ptrs, m, n = _label_columns(clustering_list)
     w = None
     if weights is not None:
         w = np.ascontiguousarray(weights, dtype=np.float64)
@@ -153,7 +161,7 @@ def weighted_element_consistency(clustering_list, weights=None, calculate_sim_ma
             raise ValueError("weights must have one entry per clustering")
     ecc = np.zeros(n, dtype=np.float64)
     sim = np.zeros((m, m), dtype=np.float64) if calculate_sim_matrix else None
-    _capi.check(_capi.lib().ca_consistency(lab.reshape(-1), n, m, _capi._opt(w), ecc, _capi._opt(sim)))
+    _capi.check(_capi.lib().ca_consistency_cols(ptrs, n, m, _capi._opt(w), ecc, _capi._opt(sim)))
     ecc = _wrap(ecc, clustering_list[0])
     return {"ecc": ecc, "ecs_matrix": sim} if calculate_sim_matrix else ecc
 
@@ -162,10 +170,9 @@ def element_sim_matrix(clustering_list, output_type="matrix", alpha=0.9, **_igno
     """Pairwise mean-ECS matrix (R/ECS.R:849-882 -> element_sim_matrix_flat_disjoint R/ECS.R:931-981)."""
     if output_type not in ("data.frame", "matrix"):
         raise ValueError("output_type must be data.frame or matrix.")
-    lab = _label_matrix(clustering_list)
-    m, n = lab.shape
+    cols, ptrs, m, n = _label_columns(clustering_list)
     sim = np.zeros((m, m), dtype=np.float64)
-    _capi.check(_capi.lib().ca_sim_matrix(lab.reshape(-1), n, m, sim))
+    _capi.check(_capi.lib().ca_sim_matrix_cols(ptrs, n, m, sim))
     if output_type == "matrix":
         return sim
     # data.frame(i.clustering = rep(1:m, m), j.clustering = rep(1:m, each = m), element_sim = c(sim))

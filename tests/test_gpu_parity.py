@@ -448,3 +448,61 @@ def test_full_size_properties_config5_shape():
         for j in range(i + 1, 12):
             acc += oracle.disjoint_ecs(L[i], L[j])[idx]
     assert np.abs(ecc[idx] - acc / 66.0).max() < TOL
+
+
+def _matrix_entry(L, w=None, want_sim=True):
+    """ca_consistency with the partition-major M x N matrix (the entry bench.py's e2e leg times)."""
+    m, n = L.shape
+    ecc = np.zeros(n)
+    sim = np.zeros((m, m)) if want_sim else None
+    lab = np.ascontiguousarray(L, dtype=np.int32)
+    _capi.check(_capi.lib().ca_consistency(lab.reshape(-1), n, m, _capi._opt(w), ecc, _capi._opt(sim)))
+    return ecc, sim
+
+
+def test_matrix_and_column_entry_points_agree():
+    """ca_consistency / ca_sim_matrix (one M x N matrix) and ca_consistency_cols / ca_sim_matrix_cols (M column
+    pointers, what the Rcpp glue passes) are the same job; both against the oracle."""
+    L, w = synth.config("C3", m=9, n=20_011)
+    ecc_m, sim_m = _matrix_entry(L, w)
+    cols = [np.array(L[p]) for p in range(9)]  # separately allocated columns
+    res = ecs.weighted_element_consistency(cols, weights=w, calculate_sim_matrix=True)
+    exp = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+    assert np.abs(ecc_m - exp[0]).max() < TOL and np.abs(sim_m - exp[1]).max() < TOL
+    assert np.abs(res["ecc"] - exp[0]).max() < TOL and np.abs(res["ecs_matrix"] - exp[1]).max() < TOL
+    sim2 = np.zeros((9, 9))
+    _capi.check(_capi.lib().ca_sim_matrix(np.ascontiguousarray(L).reshape(-1), L.shape[1], 9, sim2))
+    assert np.abs(sim2 - ecs.element_sim_matrix(cols)).max() < TOL and np.abs(sim2 - exp[1]).max() < TOL
+
+
+@pytest.mark.parametrize("n", [700_001, 2_300_003])
+def test_staged_upload_of_pageable_buffers(n, monkeypatch):
+    """Uploads of 8 MB and more from pageable memory (numpy arrays here, R vectors in the package) are staged through
+    pinned slots by several host threads; CA_UPLOAD_DIRECT=1 is the plain cudaMemcpyAsync.  Both must give the same
+    job: columns smaller than a 4 MB slot (n = 700 001), columns of several slots with a ragged tail (n = 2 300 003),
+    the matrix form (one segment of many slots), the agreement entry and the per-pair entry."""
+    L, _ = synth.config("C5", m=5, n=n)
+    cols = [np.array(L[p]) for p in range(5)]
+    staged_cols = ecs.weighted_element_consistency(cols, calculate_sim_matrix=True)
+    staged_mat = _matrix_entry(L)
+    staged_agr = ecs.element_agreement(cols[0], cols[1:])
+    staged_pair = ecs.element_sim_elscore(cols[0], cols[1])
+    monkeypatch.setenv("CA_UPLOAD_DIRECT", "1")
+    direct_cols = ecs.weighted_element_consistency(cols, calculate_sim_matrix=True)
+    direct_mat = _matrix_entry(L)
+    direct_agr = ecs.element_agreement(cols[0], cols[1:])
+    direct_pair = ecs.element_sim_elscore(cols[0], cols[1])
+    monkeypatch.delenv("CA_UPLOAD_DIRECT")
+    # the sim matrix is a sum of exact per-cell ratios in a run-dependent order; ecc likewise: 1e-9, not bit-equality
+    for a, b in ((staged_cols["ecc"], direct_cols["ecc"]), (staged_cols["ecs_matrix"], direct_cols["ecs_matrix"]),
+                 (staged_mat[0], direct_mat[0]), (staged_mat[1], direct_mat[1]), (staged_cols["ecc"], staged_mat[0]),
+                 (staged_agr, direct_agr)):
+        assert np.abs(np.asarray(a) - np.asarray(b)).max() < TOL
+    assert np.array_equal(staged_pair, direct_pair)
+    assert np.array_equal(staged_pair, oracle.disjoint_ecs(L[0], L[1]))
+    idx = np.random.default_rng(n).choice(n, size=500, replace=False)
+    acc = np.zeros(500)
+    for i in range(5):
+        for j in range(i + 1, 5):
+            acc += oracle.disjoint_ecs(L[i], L[j])[idx]
+    assert np.abs(np.asarray(staged_cols["ecc"])[idx] - acc / 10.0).max() < TOL
