@@ -36,11 +36,14 @@ SYMBOLS = {
     "ca_sim_matrix": (C.c_int, [_I32, C.c_int64, C.c_int32, _F64]),
     "ca_sim_matrix_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _F64]),
     "ca_agreement": (C.c_int, [_I32, _I32, C.c_int64, C.c_int32, _F64]),
+    "ca_agreement_cols": (C.c_int, [_I32, C.c_void_p, C.c_int64, C.c_int32, _F64]),
     "ca_merge_identical": (C.c_int, [_I32, C.c_int64, C.c_int32, C.c_void_p, _I32, _F64, C.POINTER(C.c_int32)]),
+    "ca_merge_identical_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, _I32, _F64, C.POINTER(C.c_int32)]),
     "ca_labels_create": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
     "ca_labels_wrap": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ca_labels_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ca_labels_upload_col": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "ca_labels_upload_cols": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ca_labels_device_ptr": (C.c_void_p, [C.c_void_p]),
     "ca_labels_invalidate": (C.c_int, [C.c_void_p]),
     "ca_labels_destroy": (C.c_int, [C.c_void_p]),
@@ -114,6 +117,13 @@ class DeviceLabels:
         a = np.ascontiguousarray(labels, dtype=np.int32)
         assert a.shape == (self.m, self.n)
         check(lib().ca_labels_upload(self._h, a.ctypes.data))
+        return self
+
+    def upload_columns(self, cols):
+        """M separately allocated int32 vectors (R's list of vectors) in one staged upload, no host-side M x N copy."""
+        assert len(cols) == self.m and all(c.dtype == np.int32 and c.size == self.n and c.flags.c_contiguous for c in cols)
+        ptrs = (C.c_void_p * self.m)(*[c.ctypes.data for c in cols])
+        check(lib().ca_labels_upload_cols(self._h, ptrs))
         return self
 
     def upload_pinned(self, ptr):

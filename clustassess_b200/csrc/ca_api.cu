@@ -951,6 +951,21 @@ int ca_labels_upload_col(ca_labels_t* h, int32_t p, const int32_t* col) {
     return CA_OK;
 }
 
+int ca_labels_upload_cols(ca_labels_t* h, const int32_t* const* cols) {
+    if (!h || !cols) { set_error("ca_labels_upload_cols: NULL argument"); return CA_E_ARG; }
+    CA_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    std::vector<UploadSeg> segs((size_t)h->L.m);
+    for (int32_t p = 0; p < h->L.m; p++) {
+        if (!cols[p]) { set_error("NULL column pointer %d", p); return CA_E_ARG; }
+        segs[p] = {cols[p], h->L.d_raw + (size_t)p * h->L.n, (size_t)h->L.n * 4};
+    }
+    CA_TRY(upload_segments(segs.data(), segs.size(), s));
+    CA_CUDA(cudaStreamSynchronize(s));
+    h->L.prepared = h->L.ranked = false;
+    return CA_OK;
+}
+
 void* ca_labels_device_ptr(ca_labels_t* h) { return h ? (void*)h->L.d_raw : nullptr; }
 
 int ca_labels_invalidate(ca_labels_t* h) {
@@ -1014,12 +1029,7 @@ static int host_allpairs(const int32_t* labels, const int32_t* const* cols, int6
         if (labels) {
             rc = ca_labels_upload(h, labels);
         } else {
-            std::vector<UploadSeg> segs((size_t)m);  // all columns in one staged upload
-            for (int32_t p = 0; p < m && rc == CA_OK; p++) {
-                if (!cols[p]) { set_error("NULL column pointer %d", p); rc = CA_E_ARG; break; }
-                segs[p] = {cols[p], h->L.d_raw + (size_t)p * n, (size_t)n * 4};
-            }
-            if (rc == CA_OK) rc = upload_segments(segs.data(), segs.size(), s);
+            rc = ca_labels_upload_cols(h, cols);  // all columns in one staged upload
         }
         if (rc != CA_OK) break;
         if (ecc_out) { rc = d_ecc.ensure((size_t)std::max<int64_t>(n, 1) * 8); if (rc) break; }
@@ -1137,8 +1147,9 @@ int ca_sim_matrix_cols(const int32_t* const* cols, int64_t n, int32_t m, double*
     return host_allpairs(nullptr, cols, n, m, nullptr, nullptr, sim_out);
 }
 
-int ca_agreement(const int32_t* reference, const int32_t* labels, int64_t n, int32_t m, double* agr_out) {
-    if (!reference || !labels || !agr_out || n < 0 || m < 1) { set_error("ca_agreement: bad argument"); return CA_E_ARG; }
+static int agreement_impl(const int32_t* reference, const int32_t* labels, const int32_t* const* cols, int64_t n, int32_t m,
+                          double* agr_out) {
+    if (!reference || (!labels && !cols) || !agr_out || n < 0 || m < 1) { set_error("ca_agreement: bad argument"); return CA_E_ARG; }
     CA_TRY(ensure_init());
     if (n == 0) return CA_OK;
     cudaStream_t s = ctx().stream;
@@ -1147,8 +1158,14 @@ int ca_agreement(const int32_t* reference, const int32_t* labels, int64_t n, int
     int rc = CA_OK;
     static DevBuf d_out;
     do {
-        const UploadSeg segs[2] = {{labels, h->L.d_raw, (size_t)n * m * 4}, {reference, h->L.d_raw + (size_t)n * m, (size_t)n * 4}};
-        rc = upload_segments(segs, 2, s);
+        if (labels) {
+            const UploadSeg segs[2] = {{labels, h->L.d_raw, (size_t)n * m * 4}, {reference, h->L.d_raw + (size_t)n * m, (size_t)n * 4}};
+            rc = upload_segments(segs, 2, s);
+        } else {
+            std::vector<const int32_t*> all(cols, cols + m);
+            all.push_back(reference);
+            rc = ca_labels_upload_cols(h, all.data());
+        }
         if (rc) break;
         cudaError_t e = cudaSuccess;
         rc = d_out.ensure((size_t)std::max<int64_t>(n, 1) * 8);
@@ -1163,6 +1180,13 @@ int ca_agreement(const int32_t* reference, const int32_t* labels, int64_t n, int
     } while (0);
     ca_labels_destroy(h);
     return rc;
+}
+
+int ca_agreement(const int32_t* reference, const int32_t* labels, int64_t n, int32_t m, double* agr_out) {
+    return agreement_impl(reference, labels, nullptr, n, m, agr_out);
+}
+int ca_agreement_cols(const int32_t* reference, const int32_t* const* cols, int64_t n, int32_t m, double* agr_out) {
+    return agreement_impl(reference, nullptr, cols, n, m, agr_out);
 }
 
 // ---- legacy per-pair entry points ------------------------------------------------------------------------
@@ -1277,5 +1301,7 @@ int ca_ecs_pair_mean(const int32_t* a, const int32_t* b, int64_t n, double* mean
 
 int ca_merge_identical(const int32_t* labels, int64_t n, int32_t m, const double* freq_in, int32_t* keep_out, double* freq_out,
                        int32_t* u_out);  // defined in ca_dedup.cu
+int ca_merge_identical_cols(const int32_t* const* cols, int64_t n, int32_t m, const double* freq_in, int32_t* keep_out,
+                            double* freq_out, int32_t* u_out);  // defined in ca_dedup.cu
 
 }  // extern "C"

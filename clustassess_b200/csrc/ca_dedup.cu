@@ -151,9 +151,9 @@ namespace ca {
 Labels& labels_of(ca_labels_t* h);
 }
 
-extern "C" int ca_merge_identical(const int32_t* labels, int64_t n, int32_t m, const double* freq_in, int32_t* keep_out,
-                                  double* freq_out, int32_t* u_out) {
-    if (!labels || !keep_out || !freq_out || !u_out || n < 1 || m < 1) {
+static int merge_identical_impl(const int32_t* labels, const int32_t* const* cols, int64_t n, int32_t m, const double* freq_in,
+                               int32_t* keep_out, double* freq_out, int32_t* u_out) {
+    if ((!labels && !cols) || !keep_out || !freq_out || !u_out || n < 1 || m < 1) {
         set_error("ca_merge_identical: bad argument");
         return CA_E_ARG;
     }
@@ -161,7 +161,7 @@ extern "C" int ca_merge_identical(const int32_t* labels, int64_t n, int32_t m, c
     cudaStream_t s = ctx().stream;
     ca_labels_t* h = nullptr;
     CA_TRY(ca_labels_create(n, m, &h));
-    int rc = ca_labels_upload(h, labels);
+    int rc = labels ? ca_labels_upload(h, labels) : ca_labels_upload_cols(h, cols);
     static DevBuf d_first;
     std::vector<uint64_t> lo, hi;
     Labels& L = labels_of(h);
@@ -202,4 +202,13 @@ extern "C" int ca_merge_identical(const int32_t* labels, int64_t n, int32_t m, c
     ca_labels_destroy(h);
     if (rc == CA_OK) *u_out = u;
     return rc;
+}
+
+extern "C" int ca_merge_identical(const int32_t* labels, int64_t n, int32_t m, const double* freq_in, int32_t* keep_out,
+                                  double* freq_out, int32_t* u_out) {
+    return merge_identical_impl(labels, nullptr, n, m, freq_in, keep_out, freq_out, u_out);
+}
+extern "C" int ca_merge_identical_cols(const int32_t* const* cols, int64_t n, int32_t m, const double* freq_in, int32_t* keep_out,
+                                       double* freq_out, int32_t* u_out) {
+    return merge_identical_impl(nullptr, cols, n, m, freq_in, keep_out, freq_out, u_out);
 }

@@ -90,11 +90,6 @@ def _label_columns(clustering_list):
     return cols, ptrs, len(cols), n
 
 
-def _label_matrix(clustering_list):
-    cols = _label_columns(clustering_list)[0]
-    return np.ascontiguousarray(np.stack(cols)) if cols else np.zeros((0, 0), dtype=np.int32)
-
-
 def _wrap(values, like):
     names = _names(like)
     if names is None:
@@ -194,13 +189,12 @@ def merge_identical_partitions(clustering_list):
     recs = [dict(r) for r in clustering_list]
     if len(recs) == 1:
         return recs
-    lab = _label_matrix([r["mb"] for r in recs])
-    m, n = lab.shape
+    cols, ptrs, m, n = _label_columns([r["mb"] for r in recs])
     freq = np.ascontiguousarray([float(r["freq"]) for r in recs], dtype=np.float64)
     keep = np.zeros(m, dtype=np.int32)
     fout = np.zeros(m, dtype=np.float64)
     u = C.c_int32()
-    _capi.check(_capi.lib().ca_merge_identical(lab.reshape(-1), n, m, freq.ctypes.data, keep, fout, C.byref(u)))
+    _capi.check(_capi.lib().ca_merge_identical_cols(ptrs, n, m, freq.ctypes.data, keep, fout, C.byref(u)))
     out = []
     for t in range(u.value):
         r = dict(recs[int(keep[t])])
@@ -335,12 +329,11 @@ def element_agreement(reference_clustering, clustering_list, alpha=0.9, **_ignor
     """Mean ECS of every clustering of a list against a reference (R/ECS.R:1544-1648, flat route
     element_agreement_flat_disjoint R/ECS.R:1625-1648)."""
     ref = _as_labels(reference_clustering)
-    lab = _label_matrix(clustering_list)
-    m, n = lab.shape
+    cols, ptrs, m, n = _label_columns(clustering_list)
     if n != ref.size:
         raise ValueError("The partitions do not have the same length")
     out = np.zeros(n, dtype=np.float64)
-    _capi.check(_capi.lib().ca_agreement(ref, lab.reshape(-1), n, m, out))
+    _capi.check(_capi.lib().ca_agreement_cols(ref, ptrs, n, m, out))
     return out
 
 
@@ -358,9 +351,9 @@ class ResidentPartitions:
     def __init__(self, clustering_list):
         if len(clustering_list) < 1:
             raise ValueError("At least one clustering is required.")
-        lab = _label_matrix(clustering_list)
+        cols, _, m, n = _label_columns(clustering_list)
         self._like = clustering_list[0]
-        self._dev = _capi.DeviceLabels(lab.shape[1], lab.shape[0]).upload(lab)
+        self._dev = _capi.DeviceLabels(n, m).upload_columns(cols)
 
     def __len__(self):
         return self._dev.m

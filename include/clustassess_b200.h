@@ -16,6 +16,9 @@
  *     CA_E_NA_LABEL (the reference has undefined behaviour there).
  *   - A "label matrix" is partition-major M x N: partition p occupies labels[p*n .. p*n+n), which is
  *     R's list-of-vectors layout.  The *_cols variants take M separate column pointers instead.
+ *   - Host buffers may be pageable (R vectors are): uploads of 8 MB and more from pageable memory are staged
+ *     through pinned slots by several host threads (near the PCIe rate); pinned or registered buffers are copied
+ *     directly.
  *   - Inputs are never written.  Outputs are caller-allocated; "host" pointers unless the name ends in
  *     _dev.  There is NO CPU fallback: without a CUDA device every compute entry returns CA_E_NO_DEVICE.
  *   - fp64 throughout; per-pair ECS is one IEEE division (bit-identical to the reference), set-level
@@ -97,6 +100,7 @@ int ca_sim_matrix_cols(const int32_t *const *cols, int64_t n, int32_t m, double 
 /* element_agreement_flat_disjoint(reference, list) -- R/ECS.R:1625-1648:
  * agr_out[n] = mean_p ECS(reference, labels[p])[n].   */
 int ca_agreement(const int32_t *reference, const int32_t *labels, int64_t n, int32_t m, double *agr_out);
+int ca_agreement_cols(const int32_t *reference, const int32_t *const *cols, int64_t n, int32_t m, double *agr_out);
 
 /* merge_identical_partitions(list) -- R/ECS.R:1021-1054 with are_identical_memberships R/ECS.R:984-1016:
  * greedy first-match dedup.  keep_out[u] = index of the u-th kept partition, freq_out[u] = summed
@@ -105,6 +109,8 @@ int ca_agreement(const int32_t *reference, const int32_t *labels, int64_t n, int
  *  */
 int ca_merge_identical(const int32_t *labels, int64_t n, int32_t m, const double *freq_in, int32_t *keep_out,
                        double *freq_out, int32_t *u_out);
+int ca_merge_identical_cols(const int32_t *const *cols, int64_t n, int32_t m, const double *freq_in,
+                            int32_t *keep_out, double *freq_out, int32_t *u_out);
 
 /* ---- device-resident label sets (pipeline glue; also what bench.py times as "value") --------------- */
 
@@ -115,6 +121,7 @@ int ca_labels_wrap(int64_t n, int32_t m, void *device_matrix, ca_labels_t **out)
                                                                   (e.g. filled by an NCCL all-gather)  */
 int ca_labels_upload(ca_labels_t *h, const int32_t *labels);   /* host -> device, whole matrix         */
 int ca_labels_upload_col(ca_labels_t *h, int32_t p, const int32_t *col);
+int ca_labels_upload_cols(ca_labels_t *h, const int32_t *const *cols); /* all M columns, one staged upload     */
 void *ca_labels_device_ptr(ca_labels_t *h);                    /* raw device matrix (int32 M x N)      */
 int ca_labels_invalidate(ca_labels_t *h);                      /* call after writing through the ptr   */
 int ca_labels_destroy(ca_labels_t *h);

@@ -100,10 +100,8 @@ NumericVector ecsAgreement(IntegerVector reference, List mb_list) {
     R_xlen_t n;
     std::vector<const int32_t *> cols = column_pointers(mb_list, keep, n);
     if (reference.size() != n) stop("The partitions do not have the same length");
-    IntegerMatrix packed(n, m);  // ca_agreement takes one partition-major matrix
-    for (int p = 0; p < m; p++) std::copy(cols[p], cols[p] + n, packed.begin() + (R_xlen_t)p * n);
     NumericVector out(n);
-    ca_check(ca_agreement(reference.begin(), packed.begin(), n, m, out.begin()));
+    ca_check(ca_agreement_cols(reference.begin(), cols.data(), n, m, out.begin()));
     return out;
 }
 
@@ -113,12 +111,10 @@ List ecsMergeIdentical(List mb_list, NumericVector freq) {
     std::vector<IntegerVector> keep;
     R_xlen_t n;
     std::vector<const int32_t *> cols = column_pointers(mb_list, keep, n);
-    IntegerMatrix packed(n, m);
-    for (int p = 0; p < m; p++) std::copy(cols[p], cols[p] + n, packed.begin() + (R_xlen_t)p * n);
     IntegerVector kept(m);
     NumericVector fout(m);
     int u = 0;
-    ca_check(ca_merge_identical(packed.begin(), n, m, freq.begin(), kept.begin(), fout.begin(), &u));
+    ca_check(ca_merge_identical_cols(cols.data(), n, m, freq.begin(), kept.begin(), fout.begin(), &u));
     IntegerVector kept1(u);
     NumericVector f1(u);
     for (int t = 0; t < u; t++) {
@@ -145,12 +141,10 @@ SEXP ecsResident(List mb_list) {
     std::vector<const int32_t *> cols = column_pointers(mb_list, keep, n);
     ca_labels_t *h = NULL;
     ca_check(ca_labels_create(n, m, &h));
-    for (int p = 0; p < m; p++) {
-        int rc = ca_labels_upload_col(h, p, cols[p]);
-        if (rc != CA_OK) {
-            ca_labels_destroy(h);
-            ca_check(rc);
-        }
+    int rc = ca_labels_upload_cols(h, cols.data());  // one staged upload of R's (pageable) vectors
+    if (rc != CA_OK) {
+        ca_labels_destroy(h);
+        ca_check(rc);
     }
     return ResidentPtr(h, true);
 }

@@ -473,6 +473,19 @@ def test_matrix_and_column_entry_points_agree():
     sim2 = np.zeros((9, 9))
     _capi.check(_capi.lib().ca_sim_matrix(np.ascontiguousarray(L).reshape(-1), L.shape[1], 9, sim2))
     assert np.abs(sim2 - ecs.element_sim_matrix(cols)).max() < TOL and np.abs(sim2 - exp[1]).max() < TOL
+    # agreement and identical-partition merging: matrix form against the column form the Python mirror uses
+    lab = np.ascontiguousarray(L[1:]).reshape(-1)
+    agr = np.zeros(L.shape[1])
+    _capi.check(_capi.lib().ca_agreement(np.ascontiguousarray(L[0]), lab, L.shape[1], 8, agr))
+    assert np.abs(agr - ecs.element_agreement(cols[0], cols[1:])).max() < TOL
+    want = np.mean([oracle.corrected_l1_mb(L[0], L[p]) for p in range(1, 9)], axis=0)  # R/ECS.R:1639-1647
+    assert np.abs(agr - want).max() < TOL
+    dup = np.ascontiguousarray(np.stack([L[0], L[1], L[0].max() + 1 - L[0], L[2], L[1]]), dtype=np.int32)  # 0 == 2, 1 == 4
+    keep, fout, u = np.zeros(5, np.int32), np.zeros(5), C.c_int32()
+    _capi.check(_capi.lib().ca_merge_identical(dup.reshape(-1), dup.shape[1], 5, None, keep, fout, C.byref(u)))
+    got = ecs.merge_identical_partitions([{"mb": np.array(r), "freq": 1} for r in dup])
+    assert u.value == 3 and keep[:3].tolist() == [0, 1, 3] and fout[:3].tolist() == [2.0, 2.0, 1.0]
+    assert [r["freq"] for r in got] == [2, 2, 1] and all(np.array_equal(g["mb"], dup[k]) for g, k in zip(got, (0, 1, 3)))
 
 
 @pytest.mark.parametrize("n", [700_001, 2_300_003])
