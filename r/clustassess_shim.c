@@ -6,7 +6,9 @@
  *
  * Rules kept: inputs are never written; outputs are allocated here under PROTECT and
  * only filled by the library; Rf_error (a longjmp) is raised only after the library call has returned.
- * NOT compiled in this repository (no R headers in the build container). */
+ * The build container has no R headers; tests/test_r_shim.py compiles this file against a miniature of R's C runtime
+ * (tests/r_standin/) and drives every entry below the way .Call would, on the CPU (argument errors, no-device error,
+ * registration table) and on the B200 (results against the oracle, PROTECT balance, inputs untouched). */
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
