@@ -5,8 +5,9 @@
 // (include/clustassess_b200.h) instead of computing on the CPU.  Four batched routines are added for the
 // set-level R functions.  Link with  PKG_LIBS = -L$(CLUSTASSESS_B200_HOME) -lclustassess_b200  in src/Makevars.
 //
-// NOT compiled in this repository (the build container has neither R nor Rcpp); the Python twin of this
-// file, clustassess_b200/_capi.py, drives exactly the same entry points in the tests.
+// The build container has neither R nor Rcpp: tests/test_r_glue.py compiles this file UNMODIFIED against a stand-in
+// Rcpp.h (tests/rcpp_standin/) and calls every exported routine -- argument errors and the no-device error on the CPU,
+// results against the oracle on the B200.  clustassess_b200/_capi.py is the Python twin over the same entry points.
 #include <Rcpp.h>
 #include "clustassess_b200.h"
 
