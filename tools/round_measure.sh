@@ -10,5 +10,6 @@ python bench.py --family uniform --steps 3 --warmup 2 --no-cpu-baseline > gpurun
 python bench.py --config C4 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/${tag}_bench_c4shape.json 2>/dev/null
 python bench.py --config C3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_c3shape.json 2>/dev/null
 python tools/run_c3_c4.py > gpurun_out/${tag}_c3_c4.txt 2>&1
+python tools/run_c1_c2_dedup.py > gpurun_out/${tag}_c1_c2_dedup.txt 2>&1
 nproc > gpurun_out/${tag}_nproc.txt
 ls gpurun_out | grep $tag
