@@ -260,7 +260,7 @@ def run_b200(args):
         launches[0] += 1
 
     def step_resident():
-        ecc, _ = consistency_sharded(n, m, weights, partial, finish, device="cuda")
+        ecc, _ = consistency_sharded(n, m, weights, partial, finish, device="cuda", fixed_point=True)
         return ecc
 
     def step_e2e():
@@ -271,7 +271,7 @@ def run_b200(args):
             return out
         upload_sharded(host, dev_labels)   # 1/world of the matrix over PCIe per rank + one NCCL all-gather
         torch.cuda.current_stream().synchronize()
-        ecc, _ = consistency_sharded(n, m, weights, partial, finish, device="cuda")
+        ecc, _ = consistency_sharded(n, m, weights, partial, finish, device="cuda", fixed_point=True)
         return ecc.cpu().numpy()
 
     def barrier():

@@ -26,7 +26,9 @@ SYMBOLS = {
     "ca_shutdown": (None, []),
     "ca_last_error": (C.c_char_p, []),
     "ca_version": (C.c_int, []),
+    "ca_device_count": (C.c_int, []),
     "ca_set_stream": (C.c_int, [C.c_void_p]),
+    "ca_use_stream": (C.c_int, [C.c_void_p, C.c_int]),
     "ca_label_range": (C.c_int, [_I32, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ca_contingency": (C.c_int, [_I32, _I32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, C.c_void_p, C.c_void_p]),
     "ca_ecs_pair": (C.c_int, [_I32, _I32, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -40,6 +42,9 @@ SYMBOLS = {
     "ca_merge_identical": (C.c_int, [_I32, C.c_int64, C.c_int32, C.c_void_p, _I32, _F64, C.POINTER(C.c_int32)]),
     "ca_merge_identical_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, _I32, _F64, C.POINTER(C.c_int32)]),
     "ca_labels_create": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ca_labels_create_on_primary": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ca_labels_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "ca_labels_is_sharded": (C.c_int, [C.c_void_p]),
     "ca_labels_wrap": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ca_labels_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ca_labels_upload_col": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
@@ -50,10 +55,12 @@ SYMBOLS = {
     "ca_labels_select": (C.c_int, [C.c_void_p, _I32, C.c_int32, C.POINTER(C.c_void_p)]),
     "ca_consistency_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, _F64, C.c_void_p]),
     "ca_sim_matrix_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _F64]),
+    "ca_merge_identical_resident": (C.c_int, [C.c_void_p, C.c_void_p, _I32, _F64, C.POINTER(C.c_int32)]),
     "ca_shard_owner": (C.c_int, [C.c_int32, C.c_int32]),
     "ca_consistency_partial_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ca_consistency_finish_dev": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ca_get_profile": (C.c_int, [_F64, C.c_int]),
+    "ca_get_profile_dev": (C.c_int, [C.c_int, _F64, C.c_int]),
     "ca_plan_blocks": (C.c_int, [_I32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _I32, _I32, C.c_int32,
                                  C.POINTER(C.c_int64)]),
 }
@@ -93,22 +100,40 @@ def _opt(a):
     return None if a is None else a.ctypes.data
 
 
-def profile():
-    out = np.zeros(8, dtype=np.float64)
-    lib().ca_get_profile(out, 8)
-    keys = ["pack_ms", "transpose_ms", "plan_ms", "sort_ms", "engine_ms", "finish_ms", "call_ms", "launches"]
-    return dict(zip(keys, out.tolist()))
+_PROFILE_KEYS = ["pack_ms", "transpose_ms", "plan_ms", "sort_ms", "engine_ms", "finish_ms", "call_ms", "launches", "streaming_ms", "resident_ms"]
+
+
+def profile(device_index=None):
+    """Stage timings of the last batched call: of the primary device, or of the index-th selected device of a multi-GPU job."""
+    out = np.zeros(10, dtype=np.float64)
+    if device_index is None:
+        lib().ca_get_profile(out, 10)
+    else:
+        lib().ca_get_profile_dev(int(device_index), out, 10)
+    return dict(zip(_PROFILE_KEYS, out.tolist()))
+
+
+def init(devices=None):
+    """ca_init: select the device(s) this process computes on (None = device 0)."""
+    if devices is None:
+        check(lib().ca_init(None, 0))
+    else:
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        check(lib().ca_init(arr, len(devices)))
+    return lib().ca_device_count()
 
 
 class DeviceLabels:
     """A device-resident M x N int32 label matrix (ca_labels_t)."""
 
-    def __init__(self, n, m, device_ptr=None):
-        """device_ptr: wrap caller-owned device memory (M x N int32) instead of allocating."""
+    def __init__(self, n, m, device_ptr=None, primary=False):
+        """device_ptr: wrap caller-owned device memory (M x N int32) instead of allocating.  primary: a single-device set
+        even when several devices are selected (what the dedup pre-pass and the rank-sharded entries need)."""
         self.n, self.m = int(n), int(m)
         h = C.c_void_p()
         if device_ptr is None:
-            check(lib().ca_labels_create(self.n, self.m, C.byref(h)))
+            fn = lib().ca_labels_create_on_primary if primary else lib().ca_labels_create
+            check(fn(self.n, self.m, C.byref(h)))
         else:
             check(lib().ca_labels_wrap(self.n, self.m, C.c_void_p(device_ptr), C.byref(h)))
         self._h = h
@@ -136,6 +161,19 @@ class DeviceLabels:
 
     def invalidate(self):
         check(lib().ca_labels_invalidate(self._h))
+
+    @property
+    def sharded(self):
+        return bool(lib().ca_labels_is_sharded(self._h))
+
+    def merge_identical(self, freq=None):
+        """merge_identical_partitions (R/ECS.R:1021-1054) of this resident (single-device) set -> (kept indices, summed freq)."""
+        f = None if freq is None else np.ascontiguousarray(freq, dtype=np.float64)
+        keep = np.zeros(self.m, dtype=np.int32)
+        fout = np.zeros(self.m, dtype=np.float64)
+        u = C.c_int32()
+        check(lib().ca_merge_identical_resident(self._h, _opt(f), keep, fout, C.byref(u)))
+        return keep[:u.value].copy(), fout[:u.value].copy()
 
     def select(self, idx):
         """A new resident set holding the partitions idx (device-to-device copies)."""

@@ -15,6 +15,8 @@
 // where range = max - min + 1 (calculate_ecs.cpp:8-10: unused labels inside the range are table rows).
 #include <algorithm>
 
+#include <string>
+
 #include "ca_internal.h"
 
 namespace ca {
@@ -94,13 +96,13 @@ __global__ void __launch_bounds__(256) compare_kernel(const int32_t* __restrict_
     if (__any_sync(FULL, bad) && (threadIdx.x & 31) == 0) *differ = 1;
 }
 
-static DevBuf g_sig, g_flag;
 
 int dedup_signatures(Labels& L, std::vector<uint64_t>& sig_lo, std::vector<uint64_t>& sig_hi, DevBuf& d_first, cudaStream_t s) {
     const int32_t m = L.m;
     const int64_t n = L.n;
     CA_TRY(prepare_ranks(L));
     CA_TRY(d_first.ensure((size_t)m * L.kp * 4));
+    DevBuf& g_sig = scratch(SCR_SIG);
     CA_TRY(g_sig.ensure((size_t)m * 16));
     CA_TRY(launch_fill_i32(d_first.as<int32_t>(), (int64_t)m * L.kp, INT32_MAX, s));
     CA_CUDA(cudaMemsetAsync(g_sig.p, 0, (size_t)m * 16, s));
@@ -125,6 +127,7 @@ int dedup_signatures(Labels& L, std::vector<uint64_t>& sig_lo, std::vector<uint6
 }
 
 int dedup_same_partition(Labels& L, const DevBuf& d_first, int32_t p, int32_t q, bool* same, cudaStream_t s) {
+    DevBuf& g_flag = scratch(SCR_FLAG);
     CA_TRY(g_flag.ensure(4));
     CA_CUDA(cudaMemsetAsync(g_flag.p, 0, 4, s));
     int64_t nb = (L.n + 256 * 8 - 1) / (256 * 8);
@@ -144,28 +147,24 @@ int dedup_same_partition(Labels& L, const DevBuf& d_first, int32_t p, int32_t q,
 
 using namespace ca;
 
-extern "C" int ca_labels_create(int64_t n, int32_t m, ca_labels_t** out);
+extern "C" int ca_labels_create_on_primary(int64_t n, int32_t m, ca_labels_t** out);
 extern "C" int ca_labels_upload(ca_labels_t* h, const int32_t* labels);
+extern "C" int ca_labels_upload_cols(ca_labels_t* h, const int32_t* const* cols);
 extern "C" int ca_labels_destroy(ca_labels_t* h);
+extern "C" int ca_labels_is_sharded(ca_labels_t* h);
 namespace ca {
 Labels& labels_of(ca_labels_t* h);
 }
 
-static int merge_identical_impl(const int32_t* labels, const int32_t* const* cols, int64_t n, int32_t m, const double* freq_in,
-                               int32_t* keep_out, double* freq_out, int32_t* u_out) {
-    if ((!labels && !cols) || !keep_out || !freq_out || !u_out || n < 1 || m < 1) {
-        set_error("ca_merge_identical: bad argument");
-        return CA_E_ARG;
-    }
-    CA_TRY(ensure_init());
+// greedy first-match dedup of a label set that is already on the device: exactly the loop of R/ECS.R:1030-1050, with the
+// contingency-table test of are_identical_memberships (R/ECS.R:984-1016) replaced by canonical labelling + signature + exact compare
+static int merge_identical_on(Labels& L, const double* freq_in, int32_t* keep_out, double* freq_out, int32_t* u_out) {
     cudaStream_t s = ctx().stream;
-    ca_labels_t* h = nullptr;
-    CA_TRY(ca_labels_create(n, m, &h));
-    int rc = labels ? ca_labels_upload(h, labels) : ca_labels_upload_cols(h, cols);
-    static DevBuf d_first;
+    const int32_t m = L.m;
+    const int64_t n = L.n;
+    DevBuf& d_first = scratch(SCR_FIRST);
     std::vector<uint64_t> lo, hi;
-    Labels& L = labels_of(h);
-    if (rc == CA_OK) rc = dedup_signatures(L, lo, hi, d_first, s);
+    int rc = dedup_signatures(L, lo, hi, d_first, s);
     int32_t u = 0;
     if (rc == CA_OK) {
         std::vector<int64_t> range(m);
@@ -174,7 +173,6 @@ static int merge_identical_impl(const int32_t* labels, const int32_t* const* col
             range[p] = L.h_roff[p + 1] - L.h_roff[p];
             gapless[p] = (int64_t)L.h_k[p] == range[p];
         }
-        // greedy first-match, exactly the loop of R/ECS.R:1030-1050
         for (int32_t i = 0; i < m && rc == CA_OK; i++) {
             int32_t assigned = -1;
             for (int32_t t = 0; t < u && rc == CA_OK; t++) {
@@ -199,8 +197,24 @@ static int merge_identical_impl(const int32_t* labels, const int32_t* const* col
             }
         }
     }
-    ca_labels_destroy(h);
     if (rc == CA_OK) *u_out = u;
+    return rc;
+}
+
+static int merge_identical_impl(const int32_t* labels, const int32_t* const* cols, int64_t n, int32_t m, const double* freq_in,
+                               int32_t* keep_out, double* freq_out, int32_t* u_out) {
+    if ((!labels && !cols) || !keep_out || !freq_out || !u_out || n < 1 || m < 1) {
+        set_error("ca_merge_identical: bad argument");
+        return CA_E_ARG;
+    }
+    CA_TRY(ensure_init());
+    ca_labels_t* h = nullptr;
+    CA_TRY(ca_labels_create_on_primary(n, m, &h));  // the pre-pass is O(M N) streaming work: one device
+    int rc = labels ? ca_labels_upload(h, labels) : ca_labels_upload_cols(h, cols);
+    if (rc == CA_OK) rc = merge_identical_on(labels_of(h), freq_in, keep_out, freq_out, u_out);
+    std::string msg = ca_last_error();
+    ca_labels_destroy(h);
+    if (rc != CA_OK) set_error("%s", msg.c_str());
     return rc;
 }
 
@@ -211,4 +225,22 @@ extern "C" int ca_merge_identical(const int32_t* labels, int64_t n, int32_t m, c
 extern "C" int ca_merge_identical_cols(const int32_t* const* cols, int64_t n, int32_t m, const double* freq_in, int32_t* keep_out,
                                        double* freq_out, int32_t* u_out) {
     return merge_identical_impl(nullptr, cols, n, m, freq_in, keep_out, freq_out, u_out);
+}
+// the same on a resident single-device label set: merge_partitions / element_consistency upload their partitions ONCE, dedup
+// them here and run the consistency of the kept ones (ca_consistency_resident with their indices) on the same device memory
+extern "C" int ca_merge_identical_resident(ca_labels_t* h, const double* freq_in, int32_t* keep_out, double* freq_out, int32_t* u_out) {
+    if (!h || !keep_out || !freq_out || !u_out) {
+        set_error("ca_merge_identical_resident: NULL argument");
+        return CA_E_ARG;
+    }
+    if (ca_labels_is_sharded(h)) {
+        set_error("ca_merge_identical_resident needs a single-device label set (ca_labels_create_on_primary)");
+        return CA_E_UNSUPPORTED;
+    }
+    CA_TRY(ensure_init());
+    if (labels_of(h).n < 1) {
+        set_error("ca_merge_identical_resident: empty label set");
+        return CA_E_ARG;
+    }
+    return merge_identical_on(labels_of(h), freq_in, keep_out, freq_out, u_out);
 }

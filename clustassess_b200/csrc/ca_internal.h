@@ -34,12 +34,18 @@ struct Ctx {
     size_t smem_optin = 0;        // max dynamic shared memory per block (opt-in)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // the stream everything is launched on
-    cudaEvent_t ev[8] = {};
-    double prof[8] = {};
+    cudaEvent_t ev[10] = {};
+    double prof[10] = {};
     long launches = 0;  // kernels launched since the counter was last reset
 };
-Ctx& ctx();
+Ctx& ctx();          // the context of the device the calling thread works on (thread-local selection, default: the primary device)
 int ensure_init();
+
+// Grow-only scratch buffers every device owns one set of (released by ca_shutdown): what used to be function-local statics.
+struct DevBuf;
+enum ScratchId { SCR_ZEROS, SCR_ECC, SCR_SIM, SCR_OUT, SCR_SIG, SCR_FLAG, SCR_FIRST, SCR_SEGCUR, SCR_PAIR_A, SCR_PAIR_B, SCR_PAIR_TABLE,
+                 SCR_PAIR_SA, SCR_PAIR_SB, SCR_PAIR_ERR, SCR_PAIR_ECS, SCR_PAIR_PARTIAL, SCR_PAIR_OUT, SCR_HASH, SCR_COUNT };
+DevBuf& scratch(int which);
 
 // device memory comes from a small caching allocator (ca_api.cu): freed blocks are parked and reused
 cudaError_t dev_alloc(void** out, size_t bytes);
@@ -80,23 +86,35 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
 // ---- prepared label set -----------------------------------------------------------------------------
 struct Labels {
     int64_t n = 0;
-    int32_t m = 0;
-    int32_t* d_raw = nullptr;  // M x N int32 (partition-major)
+    int32_t m = 0;             // partitions held HERE: the whole set, or one device's share of a sharded set
+    int32_t* d_raw = nullptr;  // m x N int32 (partition-major)
     bool owns_raw = true;      // false: the caller's device memory (ca_labels_wrap)
     bool ranked = false;    // min/max, ranks, compact sizes are valid
-    bool prepared = false;  // ... and the uint16 label matrix (super-tile-major, see lab16_index)
+    bool prepared = false;  // ... and the uint16 label matrix (super-tile-major, see lab16_index), templates, flags
     // filled by prepare():
-    std::vector<int32_t> h_min, h_max, h_k;
+    std::vector<int32_t> h_min, h_max, h_k;   // per local partition
     std::vector<int64_t> h_roff;  // offset of partition p's range in d_cnt / d_rank
     bool identity = true;         // every partition's labels are already dense (rank == label - min)
-    int32_t kmax = 0, kp = 0, mpad = 0;
-    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes, d_lab16, d_spack, d_kinfo, d_tmpl;
+    int32_t kmax = 0, kp = 0, mpad = 0;   // over the WHOLE set (all shards)
+    DevBuf d_min, d_max, d_cnt, d_rank, d_kcount, d_roff, d_sizes;   // per local partition
+    DevBuf d_lab16, d_spack, d_kinfo, d_tmpl;                        // over the whole set (global partition ids)
     int64_t tmpl_bytes = 0;  // bytes of one partition's table template in d_tmpl (= one table buffer of the wave kernel)
-    std::vector<int32_t> h_sizes;  // [m][kp]
+    std::vector<int32_t> h_sizes;  // [m][kp], local partitions
+    // ---- one device's share of a sharded set (one process, several GPUs) ----
+    int32_t m_glob = 0;            // partitions of the whole set; 0 = this IS the whole set
+    std::vector<int32_t> gid;      // global id of local partition k (ascending)
+    std::vector<int32_t> spans;    // the 32-partition spans owned (ascending): local block y of the transposition is span spans[y]
+    DevBuf d_span, d_sizes_g, d_kcount_g;  // span ids on the device; cluster sizes [m_glob][kp] and counts [m_glob] of ALL partitions
+    int dev_index = 0;             // which of the selected devices owns these buffers
+    int32_t mg() const { return m_glob ? m_glob : m; }
+    int32_t gid_of(int32_t k) const { return m_glob ? gid[k] : k; }
+    const int32_t* sizes_all() const { return static_cast<const int32_t*>(m_glob ? d_sizes_g.p : d_sizes.p); }
+    const int32_t* kcount_all() const { return static_cast<const int32_t*>(m_glob ? d_kcount_g.p : d_kcount.p); }
 };
 
-int prepare_ranks(Labels& L);
-int prepare_labels(Labels& L);
+int prepare_ranks(Labels& L);   // min/max, dense ranks, cluster sizes: all the dedup pre-pass needs (any cluster count)
+int prepare_labels(Labels& L);  // ... + uint16 label matrix, table templates: the wave engine's inputs (CA_E_UNSUPPORTED beyond its limits)
+bool engine_supports(int32_t kmax);  // cluster counts the wave engine can take (uint16 labels, one table row per buffer)
 
 // Compact labels live in a uint16 array laid out super-tile-major: the 16 partitions [16 t, 16 t + 16) of cell c
 // are the 32 contiguous bytes at element index (t * (n + 1) + c) * 16.  All cells' labels for one super-tile are
@@ -121,31 +139,48 @@ int launch_sizes(const uint32_t* d_cnt, const uint32_t* d_rank, const int64_t* d
 int launch_spack(const int32_t* d_sizes, const int32_t* d_kcount, int32_t m, int32_t kp, uint32_t* d_spack, int32_t* d_kinfo, cudaStream_t s);
 int launch_table_template(const uint32_t* d_spack, const int32_t* d_kcount, int32_t m, int32_t kp, int64_t tmpl_bytes, int32_t max_rows,
                           uint32_t* d_tmpl, cudaStream_t s);
-int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t mpad, const int32_t* d_min,
-                             const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_kcount, uint16_t* d_lab16, cudaStream_t s);
+constexpr int CA_MAX_DEVICES = 16;
+struct LabDst {  // the lab16 arrays a transposition stores into: the device's own first, then its peers' (sharded label sets)
+    uint16_t* p[CA_MAX_DEVICES];
+    int n;
+};
+int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t nblocks, const int32_t* d_span_of_block, const int32_t* d_min,
+                             const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_kcount, const LabDst& dst, cudaStream_t s);
 int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,
                 const int32_t* d_kcount, const int32_t* d_cstart, int32_t kp, const int32_t* d_parts, int32_t nparts, int32_t* d_perm,
                 int64_t perm_stride, const uint16_t* d_crow, const int32_t* d_sizes, uint32_t* d_qinfo, bool* qinfo_done, cudaStream_t s);
 
-// ca_tile.cu -- the all-pairs engine: persistent blocks of TL_THREADS consumer threads x 4 cells (+ 1 producer warp),
-// work units of 16 partners
+// ca_tile.cu -- the all-pairs engine: persistent blocks (one per SM) of consumer warps + 1 producer warp.
+// Resident items (complete clusters, <= TL_CAP positions): TL_THREADS consumer threads x a quad of cells.
+// Streaming items (one cluster with more than TL_CAP cells): TL_STR_THREADS consumer threads, chunks of a quad per thread.
+// Each kind has its own launch, block size and register allocation.
 constexpr int TL_CPT = 4;
 #ifndef CA_TL_THREADS
 #define CA_TL_THREADS 864
 #endif
-#ifndef CA_TL_BLOCKS
-#define CA_TL_BLOCKS 1
+#ifndef CA_TL_PREFETCH
+#define CA_TL_PREFETCH 0   // resident kernel: the next super-tile's labels (and the next work unit's cell ids) are loaded one tile ahead
 #endif
-constexpr int TL_THREADS = CA_TL_THREADS;   // tuning builds (tools/build_variant.sh) override these two
-constexpr int TL_BLOCKS = CA_TL_BLOCKS;     // persistent blocks per SM (they share the SM's shared memory)
-constexpr int TL_CAP = TL_CPT * TL_THREADS;  // positions per resident item
+#ifndef CA_TL_STR_THREADS
+#define CA_TL_STR_THREADS 864
+#endif
+constexpr int TL_THREADS = CA_TL_THREADS;          // tuning builds (tools/build_variant.sh) override these
+constexpr int TL_STR_THREADS = CA_TL_STR_THREADS;
+constexpr int TL_BLOCKS = 1;                       // persistent blocks per SM
+constexpr int TL_CAP = TL_CPT * TL_THREADS;        // positions per resident item
 constexpr int TL_MAX_ROWS = 1024;
-constexpr int TL_SUPER = 16;                 // partners per super-tile: one 32-byte label sector per cell
+constexpr int TL_SUPER = 16;                       // partners per super-tile: one 32-byte label sector per cell
 #ifndef CA_TL_WU_SPAN
 #define CA_TL_WU_SPAN 32
 #endif
 constexpr int TL_WU_SPAN = CA_TL_WU_SPAN;    // partners per work unit: 1 or 2 super-tiles (cell ids, quad info and the ecc flush are per work unit)
 static_assert(TL_WU_SPAN == 16 || TL_WU_SPAN == 32, "a work unit spans one or two super-tiles");
+// Per-cell sums and per-pair sums are accumulated as 64-bit FIXED-POINT integers: integer addition is associative, so
+// the results are bit-identical from run to run (and across any sharding over GPUs) although the adds are atomics issued
+// in arbitrary order.  ecc: units of 2^-61 of the normalised sum (<= 1); a work unit's sum is rounded once, error
+// <= 2^-62 per add, far below the 1e-9 bound.  sim: units of 2^-F, F = 61 - ceil(log2(n + 1)), of sum_n ECS <= n; every
+// TERM is rounded to that grid before it is added (error <= 2^-(F+1) per cell, so <= 2^-(F+1) in the mean: 2.3e-13 at n = 1M).
+constexpr double ECC_FIX_SCALE = 2305843009213693952.0;  // 2^61
 struct TileParams {
     const uint16_t* lab16;    // [mpad/16][n + 1][16] compact labels (cell n = the pad cell), see lab16_index()
     int64_t n;
@@ -161,8 +196,9 @@ struct TileParams {
     const Item* items;        // sorted by jbeg; nrows carries bit 30 = 32-bit counters, pad_ = perm slot
     const int32_t* wu_prefix; // [nsuper + 1] work units before span s (work unit = item x TL_WU_SPAN partners)
     uint32_t* qinfo;          // [m_slots][perm_stride / 4] x {row in block, cluster size} of every quad of positions
-    double* ecc;              // [n] accumulated with atomics (may be null)
-    double* sim;              // [m*m] accumulated with atomics (may be null)
+    unsigned long long* ecc;  // [n] fixed-point partial sums (units of 2^-61), accumulated with integer atomics (may be null)
+    unsigned long long* sim;  // [m*m] fixed-point sums of ECS over the cells (units of 1 / sim_fix_scale(n)) (may be null)
+    double sim_magic;         // 1.5 * 2^(52 - F): v + sim_magic leaves round(v * 2^F) in the low mantissa bits (sim_fix_magic(n))
     int64_t perm_stride;
     int32_t m, mpad, kp;
     int32_t nsuper, nwu;      // super-tiles, work units
@@ -186,7 +222,18 @@ int pair_ecs_gather(const int32_t* d_a, const int32_t* d_b, int64_t n, int32_t m
 int pair_mean_from_table(const uint32_t* d_table, const uint32_t* d_sa, const uint32_t* d_sb, int32_t ka, int32_t kb,
                          int64_t n, double* d_partial, int32_t* nblocks_out, cudaStream_t s);
 int reduce_partials(const double* d_partial, int32_t nblocks, double scale, double* d_out, cudaStream_t s);
-int launch_finish(double* ecc, int64_t n, double c0, double* sim, int32_t m, cudaStream_t s);
+int launch_finish(double* ecc, int64_t n, double c0, double* sim, int32_t m, cudaStream_t s);  // fixed-point -> double, in place
+// one pair with any cluster counts: hashed contingency table in global memory (the pair-loop fallback beyond the engine's limits)
+int pair_hashed_accumulate(const int32_t* d_a, const int32_t* d_b, int64_t n, const int32_t* d_min_a, const int32_t* d_min_b,
+                           const uint32_t* rk_a, const uint32_t* rk_b, const int32_t* sizes_a, const int32_t* sizes_b, double scale,
+                           unsigned long long* ecc, unsigned long long* sim_slot, double sim_magic, cudaStream_t s);
+struct PeerSrc {  // the peers' partial-sum buffers, read through peer memory
+    const unsigned long long* p[CA_MAX_DEVICES];
+    int n;
+};
+int launch_peer_sum(unsigned long long* dst, const PeerSrc& src, int64_t n, cudaStream_t s);
+double sim_fix_scale(int64_t n);  // 2^F, F = 61 - ceil(log2(n + 1))
+double sim_fix_magic(int64_t n);  // 1.5 * 2^(52 - F)
 
 // ca_dedup.cu
 int dedup_signatures(Labels& L, std::vector<uint64_t>& sig_lo, std::vector<uint64_t>& sig_hi, DevBuf& d_first, cudaStream_t s);

@@ -268,16 +268,21 @@ int launch_table_template(const uint32_t* d_spack, const int32_t* d_kcount, int3
 // A block moves a 32-partition x 128-cell tile through shared memory: coalesced 4-byte reads along n,
 // 32-byte writes along the partition axis.
 // ------------------------------------------------------------------------------------------------
+// Sharded label sets (one process, several GPUs): a device relabels the 32-partition spans it owns -- local block y is
+// the global span span_of_block[y] -- and stores every 32-byte sector into the lab16 array of EVERY device (dst.p[0..n),
+// peer memory over NVLink): the transposition kernel is also the all-gather, no separate copy or collective follows it.
 constexpr int TP = 32, TC = 128;
-__global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* __restrict__ raw, int64_t n, int32_t m, int32_t mpad,
+__global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* __restrict__ raw, int64_t n, int32_t m,
+                                                                const int32_t* __restrict__ span_of_block,
                                                                 const int32_t* __restrict__ d_min,
                                                                 const uint32_t* __restrict__ d_rank,
                                                                 const int64_t* __restrict__ d_roff,
                                                                 const int32_t* __restrict__ d_kcount,
-                                                                uint16_t* __restrict__ lab16) {
+                                                                const LabDst dst) {
     __shared__ __align__(16) uint16_t tile[TP][TC + 2];
     const int64_t c0 = (int64_t)blockIdx.x * TC;
-    const int p0 = blockIdx.y * TP;
+    const int p0 = blockIdx.y * TP;                                                    // local partitions of this block
+    const int g0 = (span_of_block ? span_of_block[blockIdx.y] : (int)blockIdx.y) * TP;  // their global ids
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // every partition's row is 16-byte aligned and the tile is full
     const bool vec = (n & 3) == 0 && c0 + TC <= n && (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
@@ -328,17 +333,21 @@ __global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* _
             uint32_t lo = tile[half * 16 + 2 * q][cell], hi = tile[half * 16 + 2 * q + 1][cell];
             wds[q] = lo | (hi << 16);
         }
-        uint4* dst = reinterpret_cast<uint4*>(lab16 + lab16_index(n, c, p0 + half * 16));
-        dst[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-        dst[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+        const int64_t at = lab16_index(n, c, g0 + half * 16);
+        const uint4 w0 = make_uint4(wds[0], wds[1], wds[2], wds[3]), w1 = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+        for (int d = 0; d < dst.n; d++) {  // own memory first, then the peers'
+            uint4* o = reinterpret_cast<uint4*>(dst.p[d] + at);
+            o[0] = w0;
+            o[1] = w1;
+        }
     }
 }
 
-int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t mpad, const int32_t* d_min,
-                             const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_kcount, uint16_t* d_lab16, cudaStream_t s) {
-    if (n == 0) return CA_OK;
-    dim3 grid((unsigned)((n + 1 + TC - 1) / TC), (unsigned)(mpad / TP));  // n cells + the pad cell
-    relabel_transpose_kernel<<<grid, 256, 0, s>>>(raw, n, m, mpad, d_min, d_rank, d_roff, d_kcount, d_lab16);
+int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t nblocks, const int32_t* d_span_of_block, const int32_t* d_min,
+                             const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_kcount, const LabDst& dst, cudaStream_t s) {
+    if (n == 0 || nblocks <= 0) return CA_OK;
+    dim3 grid((unsigned)((n + 1 + TC - 1) / TC), (unsigned)nblocks);  // n cells + the pad cell
+    relabel_transpose_kernel<<<grid, 256, 0, s>>>(raw, n, m, d_span_of_block, d_min, d_rank, d_roff, d_kcount, dst);
     CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
     return CA_OK;
 }
@@ -513,7 +522,7 @@ int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint3
     *qinfo_done = false;
     if (nparts == 0) return CA_OK;
     CA_CUDA(cudaMemsetAsync(d_perm, 0xff, (size_t)nparts * (size_t)perm_stride * sizeof(int32_t), s));
-    static DevBuf segcur;
+    DevBuf& segcur = scratch(SCR_SEGCUR);  // per device; batches of one call reuse it in stream order
     {   // chunk sort: counts + run bases ([kp] each) and three uint16 arrays of SC_CELLS entries in shared memory
         const size_t smem = (size_t)kp * 8 + (size_t)SC_CELLS * 6;
         if (smem <= 200 * 1024 && getenv("CA_SORT_LEGACY") == nullptr) {  // two blocks per SM up to ~2100 clusters, one beyond

@@ -231,18 +231,19 @@ int reduce_partials(const double* d_partial, int32_t nblocks, double scale, doub
 // finish of the batched path: ecc += c0; sim: upper-triangle sums -> means, mirrored, unit diagonal
 // (R/ECS.R:1475,1491 scalar terms; R/ECS.R:1479-1482,1488,1497 matrix fill)
 // ------------------------------------------------------------------------------------------------
+// The wave kernel leaves 64-bit fixed-point sums (ca_internal.h): both kernels convert in place.
 __global__ void finish_ecc_kernel(double* ecc, int64_t n, double c0) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ecc[i] += c0;
+    if (i < n) ecc[i] = __ll2double_rn(reinterpret_cast<const long long*>(ecc)[i]) * (1.0 / ECC_FIX_SCALE) + c0;
 }
-__global__ void finish_sim_kernel(double* sim, int32_t m, double inv_n) {
+__global__ void finish_sim_kernel(double* sim, int32_t m, double inv_scale_n) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)m * m) return;
     int i = (int)(idx / m), j = (int)(idx % m);
     if (i == j) {
         sim[idx] = 1.0;
     } else if (i < j) {
-        double v = sim[idx] * inv_n;
+        double v = __ll2double_rn(reinterpret_cast<const long long*>(sim)[idx]) * inv_scale_n;
         sim[idx] = v;
         sim[(int64_t)j * m + i] = v;
     }
@@ -256,9 +257,111 @@ int launch_finish(double* ecc, int64_t n, double c0, double* sim, int32_t m, cud
     if (sim) {
         ca::ctx().launches++;
         int64_t t = (int64_t)m * m;
-        finish_sim_kernel<<<(unsigned)((t + 255) / 256), 256, 0, s>>>(sim, m, n > 0 ? 1.0 / (double)n : 0.0);
+        finish_sim_kernel<<<(unsigned)((t + 255) / 256), 256, 0, s>>>(sim, m, n > 0 ? 1.0 / (sim_fix_scale(n) * (double)n) : 0.0);
     }
     CA_CUDA(cudaGetLastError());
+    return CA_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Any cluster count: one pair through a HASHED contingency table in global memory.
+// The batched engine (ca_tile.cu) needs a table row per shared-memory buffer (K <= 24 799) and uint16 labels; the dense
+// per-pair table above needs K1 x K2 cells.  Beyond both -- the reference's myContTable (src/calculate_ecs.cpp:7-19) only
+// needs the memory -- a pair's table is kept as an open-addressing hash of its non-empty cells (at most N of them):
+//   key = (dense rank in a) << 32 | (dense rank in b), 2 N slots rounded up to a power of two, linear probing.
+// Two passes like disjointECS (calculate_ecs.cpp:26,39-43): count, then ECS[n] = T[a][b] / max(S_a, S_b) (one IEEE division),
+// added to the per-cell fixed-point sums (scaled by w_i w_j / norm) and, summed over the cells, to the pair's matrix entry.
+// ------------------------------------------------------------------------------------------------
+static constexpr unsigned long long HASH_EMPTY = ~0ull;
+__device__ __forceinline__ uint64_t hash_slot(uint64_t key, uint64_t mask) {
+    key ^= key >> 33;
+    key *= 0xff51afd7ed558ccdull;
+    key ^= key >> 33;
+    key *= 0xc4ceb9fe1a85ec53ull;
+    key ^= key >> 33;
+    return key & mask;
+}
+__device__ __forceinline__ uint32_t rank_of(const int32_t* x, int64_t i, int mn, const uint32_t* rk) {
+    const uint32_t v = (uint32_t)(__ldg(x + i) - mn);
+    return rk ? __ldg(rk + v) : v;
+}
+__global__ void __launch_bounds__(256) hash_count_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t n,
+                                                         const int32_t* __restrict__ min_a, const int32_t* __restrict__ min_b,
+                                                         const uint32_t* __restrict__ rk_a, const uint32_t* __restrict__ rk_b,
+                                                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ counts, uint64_t mask) {
+    const int mna = *min_a, mnb = *min_b;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = ((unsigned long long)rank_of(a, i, mna, rk_a) << 32) | rank_of(b, i, mnb, rk_b);
+        uint64_t h = hash_slot(key, mask);
+        for (;;) {
+            const unsigned long long seen = atomicCAS(keys + h, HASH_EMPTY, key);
+            if (seen == HASH_EMPTY || seen == key) break;
+            h = (h + 1) & mask;
+        }
+        atomicAdd(counts + h, 1u);
+    }
+}
+__global__ void __launch_bounds__(256) hash_gather_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t n,
+                                                          const int32_t* __restrict__ min_a, const int32_t* __restrict__ min_b,
+                                                          const uint32_t* __restrict__ rk_a, const uint32_t* __restrict__ rk_b,
+                                                          const int32_t* __restrict__ sizes_a, const int32_t* __restrict__ sizes_b,
+                                                          const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                                          uint64_t mask, double scale, unsigned long long* __restrict__ ecc,
+                                                          unsigned long long* __restrict__ sim_slot, double sim_magic) {
+    const int mna = *min_a, mnb = *min_b;
+    unsigned long long local = 0ull;  // every term rounded to the fixed-point grid before it is added (see ca_tile.cu, sim_fix)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t ca = rank_of(a, i, mna, rk_a), cb = rank_of(b, i, mnb, rk_b);
+        const unsigned long long key = ((unsigned long long)ca << 32) | cb;
+        uint64_t h = hash_slot(key, mask);
+        while (keys[h] != key) h = (h + 1) & mask;
+        const double ecs = (double)counts[h] / (double)max(__ldg(sizes_a + ca), __ldg(sizes_b + cb));  // calculate_ecs.cpp:35
+        if (ecc) atomicAdd(ecc + i, (unsigned long long)__double2ll_rn(ecs * scale * ECC_FIX_SCALE));
+        local += (unsigned long long)(__double_as_longlong(ecs + sim_magic) - __double_as_longlong(sim_magic));
+    }
+    if (sim_slot) {  // integer sums: the same bits in every run
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
+        if ((threadIdx.x & 31) == 0 && local != 0ull) atomicAdd(sim_slot, local);
+    }
+}
+
+int pair_hashed_accumulate(const int32_t* d_a, const int32_t* d_b, int64_t n, const int32_t* d_min_a, const int32_t* d_min_b,
+                           const uint32_t* rk_a, const uint32_t* rk_b, const int32_t* sizes_a, const int32_t* sizes_b, double scale,
+                           unsigned long long* ecc, unsigned long long* sim_slot, double sim_magic, cudaStream_t s) {
+    uint64_t cap = 1024;
+    while (cap < 2 * (uint64_t)n) cap <<= 1;
+    DevBuf& hb = scratch(SCR_HASH);
+    CA_TRY(hb.ensure((size_t)cap * 12));
+    unsigned long long* keys = hb.as<unsigned long long>();
+    uint32_t* counts = reinterpret_cast<uint32_t*>(keys + cap);
+    CA_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)cap * 8, s));
+    CA_CUDA(cudaMemsetAsync(counts, 0, (size_t)cap * 4, s));
+    const unsigned nb = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8));
+    hash_count_kernel<<<nb, 256, 0, s>>>(d_a, d_b, n, d_min_a, d_min_b, rk_a, rk_b, keys, counts, cap - 1);
+    hash_gather_kernel<<<nb, 256, 0, s>>>(d_a, d_b, n, d_min_a, d_min_b, rk_a, rk_b, sizes_a, sizes_b, keys, counts, cap - 1, scale, ecc, sim_slot,
+                                          sim_magic);
+    CA_CUDA(cudaGetLastError());
+    ca::ctx().launches += 2;
+    return CA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU jobs without NCCL: the primary device adds its peers' fixed-point partial sums, read through peer memory
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) peer_sum_kernel(unsigned long long* __restrict__ dst, const PeerSrc src, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long v = dst[i];
+        for (int q = 0; q < src.n; q++) v += src.p[q][i];
+        dst[i] = v;
+    }
+}
+int launch_peer_sum(unsigned long long* dst, const PeerSrc& src, int64_t n, cudaStream_t s) {
+    if (n <= 0 || src.n <= 0) return CA_OK;
+    peer_sum_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 4)), 256, 0, s>>>(dst, src, n);
+    CA_CUDA(cudaGetLastError());
+    ca::ctx().launches++;
     return CA_OK;
 }
 

@@ -7,14 +7,12 @@
 //
 // ITEM = a set of COMPLETE clusters of an owner partition i (host planner, ca_plan.cpp).  The cells of i are
 // sorted by cluster (perm_i, ca_pack.cu), so a block that works on an item owns whole ROWS of every contingency
-// table T_ij.  A consumer thread owns a quad of consecutive positions of one cluster.
+// table T_ij.
 //
 // WORK UNIT = (item, span of 32 partner partitions = two 16-partner super-tiles).  Work units are numbered span-major
 // and the persistent blocks (one per SM) take them round-robin, so all SMs sweep the partner axis together and the
 // labels of the current super-tiles -- dense 32 (N+1)-byte slabs of the super-tile-major uint16 label array,
-// lab16_index() -- are fetched from HBM once and then served by L2 to every owner partition.  A thread fetches the 16
-// labels of a cell with ONE 32-byte load (LDG.E.256) per super-tile; cell ids, quad info and the flush of the
-// per-cell sums to ecc happen once per work unit.
+// lab16_index() -- are fetched from HBM once and then served by L2 to every owner partition.
 //
 // PHASE = as many partners of the current 8-partner tile as fit into one of the two shared-memory buffers:
 //   fill    the producer warp initialises the phase's tables with TMA bulk copies completing on the buffer's
@@ -24,26 +22,32 @@
 //   hist    for each partner and cell: red.shared.add.u32 [entry], 1 -- with a CONSTANT 1 this is the SASS
 //           instruction ATOMS.POPC.INC, which merges lanes that hit the same address in hardware (measured,
 //           tools/microbench2.cu: 1.1 SM-cycles per warp instruction whether 32 lanes hit 32 banks or one
-//           word; an add of a register value serialises instead).  Peaked label distributions -- the normal
-//           case for similar partitions -- are therefore the FAST case and need no aggregation code;
+//           word; an add of a register value serialises instead);
 //   sync    ONE named barrier among the consumer warps;
 //   gather  one shared load per (cell, partner) returns count and partner cluster size together;
 //           ECS = T[a][b] / max(S_i[a], S_j[b])  (calculate_ecs.cpp:35) is accumulated in registers; the
 //           consumer warps then release the buffer through its `empty` mbarrier.
-// Tables are row-major per partner with row stride K_j + 1 (rounded to 4), so a table takes R * (K_j + 1) entries
-// whatever the largest cluster count is.  Column K_j is the PAD COLUMN: padding positions of the cluster-sorted order
-// read the pad cell N, whose label in partition j is K_j, so the inner loops carry no validity tests.  The bodies of
-// histogram and gather are instantiated per tile slot (label word and half are compile-time, the slot's meta entries
-// sit at immediate offsets) and entered Duff-style at the phase's first slot.
+// Tables are row-major per partner with row stride K_j + 1 (rounded to 4).  Column K_j is the PAD COLUMN: padding
+// positions of the cluster-sorted order read the pad cell N, whose label in partition j is K_j, so the inner loops
+// carry no validity tests.  The bodies of histogram and gather are instantiated per tile slot (label word and half are
+// compile-time, the slot's meta entries sit at immediate offsets) and entered Duff-style at the phase's first slot.
 //
-// A work unit of a RESIDENT item (<= TL_CAP positions) adds its per-cell sums to ecc once, when the block moves on
-// to its next work unit; clusters larger than TL_CAP are "streaming" items (their own launch, own register
-// allocation): one row; items of at most two chunks keep both chunks' labels in registers between histogram and
-// gather, longer ones stream the cells from global memory in both passes; sums are added per phase; with more than
-// 65535 cells the entries are plain 32-bit counts and the partner sizes come from global memory.
+// Two kinds of items, two launches (own block size and register allocation each):
+//   RESIDENT (<= TL_CAP positions, R >= 1 complete clusters): a consumer thread owns a quad of consecutive positions
+//     of one cluster.  It fetches the 16 labels of a cell for a whole super-tile with ONE 32-byte load (LDG.E.256) and
+//     -- CA_TL_PREFETCH -- does so one tile AHEAD into a second register set: while the upper tile of a super-tile is
+//     being processed the next super-tile's sectors are already in flight, and during a work unit's last tile so are
+//     the next work unit's cell ids, quad info and first sectors (the producer publishes the next unit's coordinates
+//     in the work-unit record).  The per-cell sums go to ecc once per work unit.
+//   STREAMING (one cluster with more than TL_CAP cells, one table row): TL_STR_THREADS threads, cells in chunks of a quad per
+//     thread; items of at most two chunks keep both chunks' labels in registers between histogram and gather, longer ones
+//     stream the cells from global memory in both passes; labels are loaded per 8-partner tile (16 bytes per cell), sums
+//     are added per phase.  More than 65535 cells: plain 32-bit counters, partner sizes from global memory.
 //
 // The division is T * r with r = 1/max from rcp.approx.ftz.f64 + one Newton step (relative error < 1e-13);
 // the batched path has to meet 1e-9 absolute, the per-pair entry points (ca_pair.cu) keep the IEEE division.
+// Sums leave the kernel as 64-bit fixed-point integers (ca_internal.h): integer atomics make the result independent
+// of the order in which blocks, warps and GPUs add -- two runs give identical bits.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -57,10 +61,11 @@ namespace ca {
 #define CA_BACKOFF_NS 200  // the producer's sleep between probes of a buffer that is still in use (tuning builds)
 #endif
 static constexpr unsigned FULL = 0xffffffffu;
-static constexpr int NC = TL_THREADS;       // consumer threads (a quad of cells each)
-static constexpr int NT = NC + 32;          // + the producer warp
+static constexpr int NC_RES = TL_THREADS;      // consumer threads of the resident kernel (a quad of cells each)
+static constexpr int NC_STR = TL_STR_THREADS;  // consumer threads of the streaming kernel
 static constexpr int CAP = TL_CAP;
-static_assert(TL_CPT == 4, "a thread owns one quad of cells");
+static_assert(TL_CPT == 4, "a resident thread owns one quad of cells");
+static_assert(NC_RES % 32 == 0 && NC_STR % 32 == 0 && NC_RES + 32 <= 1024 && NC_STR + 32 <= 1024, "whole warps, one block");
 
 // shared-memory map (byte offsets from the dynamic shared base)
 static constexpr int SM_MBAR = 0;       // four mbarriers: full[2] (tables initialised + meta published), empty[2] (buffer released)
@@ -72,12 +77,15 @@ static constexpr int META_BYTES = 224;
 static constexpr int META_HDR = 0, META_J0 = 4,
                      META_TR = 64,   // [8] {table base, row bytes}
                      META_W = 160;   // [8] double: weights (not written when every weight is 1)
-static constexpr int SM_SIMACC = 480;   // [2][8] double: sum of ECS over the block's cells, per buffer and tile slot
+static constexpr int SM_SIMACC = 480;   // [2][8] u64: fixed-point sum of ECS over the block's cells, per buffer and tile slot
 static constexpr int SM_WUREC = 608;    // two work-unit records (alternating), written once per work unit
-static constexpr int WU_M = 0, WU_POS0 = 4, WU_NPOS = 8, WU_NROWS = 12, WU_SA = 16, WU_SLOT = 20, WUREC_BYTES = 32;
-static constexpr int SM_PLAN = 672;     // producer's scratch for the current span: [32] {row bytes, inclusive prefix of the row
-static constexpr int SM_PLANW = 928;    //   bytes inside the 8-partner tile}; [32] weights
+// work-unit record: the item, and where the NEXT work unit of this block starts (0 positions = none), for the prefetch
+static constexpr int WU_M = 0, WU_POS0 = 4, WU_NPOS = 8, WU_NROWS = 12, WU_SA = 16, WU_SLOT = 20, WU_JHI = 24, WU_NXT_ST = 28,
+                     WU_NXT_SLOT = 32, WU_NXT_POS0 = 36, WU_NXT_NPOS = 40, WUREC_BYTES = 48;
+static constexpr int SM_PLAN = 704;     // producer's scratch for the current span: [32] {row bytes, inclusive prefix of the row
+static constexpr int SM_PLANW = 960;    //   bytes inside the 8-partner tile}; [32] weights
 static constexpr int SM_DYN = 1280;     // two table buffers
+static_assert(SM_WUREC + 2 * WUREC_BYTES <= SM_PLAN && SM_PLAN + 256 <= SM_PLANW && SM_PLANW + 256 <= SM_DYN, "shared-memory map");
 static constexpr uint32_t KK_BIG = 1u << 30;  // partner has a cluster with >= 65535 cells
 
 // ---- shared-space accessors ---------------------------------------------------------------------------------
@@ -101,7 +109,20 @@ __device__ __forceinline__ void sts_u64(uint32_t a, uint32_t x, uint32_t y) { as
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 // the immediate 1 matters: ptxas emits ATOMS.POPC.INC (same-address lanes merged in hardware) only for it
 __device__ __forceinline__ void red_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
-__device__ __forceinline__ void red_add_f64(uint32_t a, double v) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void red_add_u64(uint32_t a, unsigned long long v) { asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long lds_b64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_b64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long __reduce_add_sync_u64(unsigned long long v) {  // integer: any order gives the same sum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// double -> fixed point (round to nearest); the product is far below 2^63 by construction
+__device__ __forceinline__ unsigned long long to_fix(double v, double scale) { return (unsigned long long)__double2ll_rn(v * scale); }
 
 // ---- TMA bulk copies completing on an mbarrier (SASS UBLKCP) ---------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -181,11 +202,13 @@ struct Phase {
     int j0, g0, cnt;  // partners [j0+g0, j0+g0+cnt) of the 8-partner tile at j0
 };
 
-// ---- histogram / gather of one phase for a quad of cells -------------------------------------------------------
+// ---- histogram / gather of one phase ---------------------------------------------------------------------------
 // A phase covers the tile slots [g0, g0 + cnt) of the 8-partner tile whose labels sit in L.  The slot bodies are
 // instantiated per slot (the label's word and half are compile-time, the slot's meta entries are at immediate
 // offsets) and entered Duff-style: one jump to slot g0, then one compare-and-branch per slot.  There are no
 // validity tests: padding positions carry the pad label (ca_internal.h, lab16_index) and count into a spare column.
+// A thread's cells come in GROUPS of 4 (a resident thread has one group, a streaming thread up to SCPT / 4; `ng` =
+// groups in use, block-uniform).
 template <int V> struct Slot { static constexpr int value = V; };
 template <typename F>
 __device__ __forceinline__ void for_slots(int g0, int cnt, F&& f) {
@@ -215,15 +238,21 @@ __device__ __forceinline__ uint32_t slot_label_rt(const uint4& l, int jt) {
     return (jt & 1) ? (w >> 16) : (w & 0xffffu);
 }
 
-__device__ __forceinline__ void hist_quad(const TileParams& P, uint32_t meta, const Phase ph, const uint4 (&L)[4], uint32_t rowidx) {
+template <int NCELL>
+__device__ __forceinline__ void hist_cells(const TileParams& P, uint32_t meta, const Phase ph, const uint4 (&L)[NCELL], uint32_t rowidx, int ng) {
     for_slots(ph.g0, ph.cnt, [&](auto slot) {
         constexpr int JT = decltype(slot)::value;
         const uint2 tr = lds_u64(meta + META_TR + JT * 8);
         const uint32_t rb = tr.x + rowidx * tr.y;
-        red_inc(rb + slot_label<JT>(P, L[0]) * 4u);
-        red_inc(rb + slot_label<JT>(P, L[1]) * 4u);
-        red_inc(rb + slot_label<JT>(P, L[2]) * 4u);
-        red_inc(rb + slot_label<JT>(P, L[3]) * 4u);
+#pragma unroll
+        for (int g = 0; g < NCELL / 4; g++) {
+            if (NCELL == 4 || g < ng) {
+                red_inc(rb + slot_label<JT>(P, L[4 * g + 0]) * 4u);
+                red_inc(rb + slot_label<JT>(P, L[4 * g + 1]) * 4u);
+                red_inc(rb + slot_label<JT>(P, L[4 * g + 2]) * 4u);
+                red_inc(rb + slot_label<JT>(P, L[4 * g + 3]) * 4u);
+            }
+        }
     });
 }
 
@@ -239,41 +268,56 @@ __device__ __forceinline__ double ecs_term(uint32_t count, uint32_t sa, uint32_t
     return u32_to_f64(count) * r;
 }
 
+// The matrix entry of a pair is sum_n ECS_ij[n] / N.  To make it independent of which thread holds which cell (the order of
+// the cells inside a cluster varies from run to run, ca_pack.cu) every term is rounded to the fixed-point grid BEFORE it is
+// added: v + magic (magic = 1.5 * 2^(52 - F)) leaves round(v * 2^F) in the low mantissa bits -- one DADD and a 64-bit integer
+// add per term -- and integer sums are associative.  The warp's sum then joins the block's accumulator of its tile slot.
+__device__ __forceinline__ unsigned long long sim_fix(const TileParams& P, double v) {
+    return (unsigned long long)(__double_as_longlong(v + P.sim_magic) - __double_as_longlong(P.sim_magic));
+}
+__device__ __forceinline__ void sim_warp_add(uint32_t simacc_slot, unsigned long long es, int lane) {
+    es = __reduce_add_sync_u64(es);
+    if (lane == 0 && es != 0ull) red_add_u64(simacc_slot, es);
+}
+
 // UNITW: all weights are 1 (element_consistency of distinct partitions): ECS = count * r is accumulated by one FMA.
 // BIG (block-uniform, rare): a partner of the phase has a cluster with >= 65535 cells, whose size half reads 0xffff
 // = "look the size up in global memory"; WIDE: a streaming item with more than 65535 cells, 32-bit counters and all
 // partner sizes from global memory.  Both take the generic loop with run-time slots.
-template <bool WIDE, bool WANT_SIM, bool UNITW>
-__device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, bool big,
-                                            const uint4 (&L)[4], uint32_t rowidx, uint32_t sa, int nvalid, int lane, double (&acc)[4]) {
+// vmask: bit k = cell k is a real cell (padding positions gather the spare column; they must not count in the matrix).
+template <int NCELL, bool WIDE, bool WANT_SIM, bool UNITW>
+__device__ __forceinline__ void gather_cells(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, bool big,
+                                             const uint4 (&L)[NCELL], uint32_t rowidx, uint32_t sa, uint32_t vmask, int ng, int lane,
+                                             double (&acc)[NCELL]) {
     if (!WIDE && !big) {
         for_slots(ph.g0, ph.cnt, [&](auto slot) {
             constexpr int JT = decltype(slot)::value;
             const uint2 tr = lds_u64(meta + META_TR + JT * 8);
             const uint32_t rb = tr.x + rowidx * tr.y;
             const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + JT * 8);
-            double es = 0.0;
+            unsigned long long es = 0ull;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint32_t e = lds_u32(rb + slot_label<JT>(P, L[c]) * 4u);
-                const uint32_t count = e & 0xffffu, sb = e >> 16;
-                if (UNITW && !WANT_SIM) {
-                    const double mx = u32_to_f64(max(sa, sb));
-                    double r;
-                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
-                    r = fma(fma(-mx, r, 1.0), r, r);
-                    acc[c] = fma(u32_to_f64(count), r, acc[c]);
-                } else {
-                    const double v = ecs_term(count, sa, sb);
-                    acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
-                    if (WANT_SIM) es += c < nvalid ? v : 0.0;  // padding positions gather the spare column
+            for (int g = 0; g < NCELL / 4; g++) {
+                if (NCELL == 4 || g < ng) {
+#pragma unroll
+                    for (int c = 4 * g; c < 4 * g + 4; c++) {
+                        const uint32_t e = lds_u32(rb + slot_label<JT>(P, L[c]) * 4u);
+                        const uint32_t count = e & 0xffffu, sb = e >> 16;
+                        if (UNITW && !WANT_SIM) {
+                            const double mx = u32_to_f64(max(sa, sb));
+                            double r;
+                            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
+                            r = fma(fma(-mx, r, 1.0), r, r);
+                            acc[c] = fma(u32_to_f64(count), r, acc[c]);
+                        } else {
+                            const double v = ecs_term(count, sa, sb);
+                            acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
+                            if (WANT_SIM) es += ((vmask >> c) & 1u) ? sim_fix(P, v) : 0ull;
+                        }
+                    }
                 }
             }
-            if (WANT_SIM) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
-                if (lane == 0 && es != 0.0) red_add_f64(simacc + JT * 8u, es);
-            }
+            if (WANT_SIM) sim_warp_add(simacc + JT * 8u, es, lane);
         });
         return;
     }
@@ -283,29 +327,30 @@ __device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, 
         const uint32_t rb = tr.x + rowidx * tr.y;
         const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + jt * 8);
         const int32_t* szg = P.sizes + (int64_t)(ph.j0 + jt) * P.kp;
-        double es = 0.0;
+        unsigned long long es = 0ull;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const uint32_t lab = slot_label_rt(L[c], jt);
-            const uint32_t e = lds_u32(rb + lab * 4u);
-            uint32_t count, sb;
-            if (WIDE) {
-                count = e;
-                sb = (uint32_t)__ldg(szg + lab);
-            } else {
-                count = e & 0xffffu;
-                sb = e >> 16;
-                if (sb == 0xffffu) sb = (uint32_t)__ldg(szg + lab);
+        for (int g = 0; g < NCELL / 4; g++) {
+            if (NCELL == 4 || g < ng) {
+#pragma unroll
+                for (int c = 4 * g; c < 4 * g + 4; c++) {
+                    const uint32_t lab = slot_label_rt(L[c], jt);
+                    const uint32_t e = lds_u32(rb + lab * 4u);
+                    uint32_t count, sb;
+                    if (WIDE) {
+                        count = e;
+                        sb = (uint32_t)__ldg(szg + lab);
+                    } else {
+                        count = e & 0xffffu;
+                        sb = e >> 16;
+                        if (sb == 0xffffu) sb = (uint32_t)__ldg(szg + lab);
+                    }
+                    const double v = ecs_term(count, sa, sb);
+                    acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
+                    if (WANT_SIM) es += ((vmask >> c) & 1u) ? sim_fix(P, v) : 0ull;
+                }
             }
-            const double v = ecs_term(count, sa, sb);
-            acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
-            if (WANT_SIM) es += c < nvalid ? v : 0.0;
         }
-        if (WANT_SIM) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
-            if (lane == 0 && es != 0.0) red_add_f64(simacc + jt * 8u, es);
-        }
+        if (WANT_SIM) sim_warp_add(simacc + jt * 8u, es, lane);
     }
 }
 
@@ -313,16 +358,20 @@ __device__ __forceinline__ void gather_quad(const TileParams& P, uint32_t meta, 
 __device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, const Phase ph, int m, int t) {
     if (m < 0) return;
     if (t >= ph.g0 && t < ph.g0 + ph.cnt) {  // t = tile slot
-        const double v = lds_f64(simacc + t * 8u);
-        if (v != 0.0) atomicAdd(P.sim + (int64_t)m * P.m + (ph.j0 + t), v);
-        sts_f64(simacc + t * 8u, 0.0);
+        const unsigned long long v = lds_b64(simacc + t * 8u);
+        if (v != 0ull) atomicAdd(P.sim + (int64_t)m * P.m + (ph.j0 + t), v);
+        sts_b64(simacc + t * 8u, 0ull);
     }
+}
+// a cell's sum over the partners of a work unit (already scaled by w_i / norm) joins its fixed-point accumulator
+__device__ __forceinline__ void ecc_add(const TileParams& P, int cell, double v) {
+    atomicAdd(P.ecc + cell, to_fix(v, ECC_FIX_SCALE));
 }
 
 // ---- work units and phase planning (warp 0) -------------------------------------------------------------------
-// Work unit (WU) = (item, super-tile of SUPER partners).  WUs are numbered super-tile-major: WU w belongs to the
-// super-tile s with wu_prefix[s] <= w < wu_prefix[s+1] and to item w - wu_prefix[s]; the items are sorted by their
-// first partner, so the items that have partners inside super-tile s are a PREFIX of the item list.  Block b of
+// Work unit (WU) = (item, span of WSPAN partners).  WUs are numbered span-major: WU w belongs to the
+// span s with wu_prefix[s] <= w < wu_prefix[s+1] and to item w - wu_prefix[s]; the items are sorted by their
+// first partner, so the items that have partners inside span s are a PREFIX of the item list.  Block b of
 // the persistent grid takes WUs b, b + grid, b + 2 grid, ...: all SMs sweep the partner axis together, so the label
 // sectors of the current super-tile (32 bytes per cell) are fetched from HBM once and then served by L2 to every
 // owner partition -- instead of one random HBM sector read per (cell, tile, owner), which is what bounds a
@@ -338,7 +387,7 @@ static constexpr uint32_t NROWS_WIDE = 1u << 30;  // Item::nrows flag: more than
 
 struct Planner {          // the producer warp's registers (all values warp-uniform)
     int w;                // current WU
-    int s;                // its super-tile
+    int s;                // its span
     int wend;             // wu_prefix[s + 1]
     Item it;              // its item
     int jhi;              // partners of this WU: [.., jhi)
@@ -350,7 +399,7 @@ struct Planner {          // the producer warp's registers (all values warp-unif
     int nw, ns, nwend;
 };
 
-// ids of WU w (w ascending over calls): advance the super-tile while w is beyond it
+// ids of WU w (w ascending over calls): advance the span while w is beyond it
 __device__ __forceinline__ void locate_wu(const TileParams& P, int w, int& s, int& wend) {
     while (w >= wend && s + 1 < P.nsuper) {
         s++;
@@ -399,7 +448,7 @@ __device__ __forceinline__ void advance_wu(const TileParams& P, Planner& pl, int
             __syncwarp();
         }
         // the consumers read this WU's cell ids and quad info (streamed from HBM, 6 bytes per position) when they
-        // reach its first phase, one or two phases from now: ask L2 for the lines already
+        // reach it, one or two phases from now (or a tile earlier, with the prefetch): ask L2 for the lines already
         if (pl.it.npos <= CAP) {
             const int64_t off = (int64_t)pl.it.pad_ * P.perm_stride + pl.it.pos0;
             const char* pc = reinterpret_cast<const char*>(P.perm + off);
@@ -478,6 +527,17 @@ __device__ __forceinline__ void plan_publish(const TileParams& P, uint32_t sbase
             sts_u64(wr + WU_M, (uint32_t)pl.it.m, (uint32_t)pl.it.pos0);
             sts_u64(wr + WU_NPOS, (uint32_t)pl.it.npos, (uint32_t)pl.it.nrows);
             sts_u64(wr + WU_SA, (uint32_t)pl.it.sa, (uint32_t)pl.it.pad_);
+            // where this block's next work unit starts: its first super-tile, and its cells in perm
+            uint32_t nst = 0u, nslot = 0u, npos0 = 0u, nnpos = 0u;
+            if (pl.nw < P.nwu) {
+                nst = (uint32_t)(max(pl.nit.jbeg, pl.ns * WSPAN) >> 4);
+                nslot = (uint32_t)pl.nit.pad_;
+                npos0 = (uint32_t)pl.nit.pos0;
+                nnpos = (uint32_t)pl.nit.npos;
+            }
+            sts_u64(wr + WU_JHI, (uint32_t)pl.jhi, nst);
+            sts_u64(wr + WU_NXT_SLOT, nslot, npos0);
+            sts_u32(wr + WU_NXT_NPOS, nnpos);
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the consumers' generic accesses before the async writes
@@ -512,89 +572,60 @@ __device__ __forceinline__ void plan_advance(const TileParams& P, Planner& pl, c
     }
 }
 
+template <bool UNITW>
+__device__ __forceinline__ void producer_loop(const TileParams& P, uint32_t sbase, int half, int lane) {
+    Planner pl;
+    planner_init(P, pl, lane, sbase);
+    for (uint32_t p = 0;; p++) {
+        const uint32_t b = p & 1u;
+        const bool last = pl.w >= P.nwu;
+        PhasePlan pp;
+        if (!last) pp = plan_compute(P, sbase, half, lane, pl);
+        if (p >= 2) mbar_wait<true>(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u);  // consumers are done with buffer b
+        if (last) {
+            plan_terminal(sbase, b, lane);
+            break;
+        }
+        plan_publish<UNITW>(P, sbase, b, sbase + SM_DYN + b * (uint32_t)half, lane, pl, pp);
+        plan_advance(P, pl, pp, lane, sbase);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // The persistent kernel: one block per SM walks its work units; the phases of consecutive WUs form one stream.
 // Warp 0 is the PRODUCER: it plans phases and issues their table fills, running up to two phases ahead of the
-// CONSUMER warps (every other warp; a thread owns a quad of cells).  Hand-offs are mbarriers: full[b] (fill landed
-// + meta published) and empty[b] (every consumer warp has finished gathering from buffer b); the consumers meet
-// at one named barrier per phase, between histogram and gather.
-// A WU of a RESIDENT item (<= CAP positions, R >= 1 complete clusters) keeps the labels of its cells in registers
-// between the histogram and the gather and adds its per-cell sums to ecc once; a WU of a larger cluster streams
-// the cells in chunks of CAP positions in both passes and adds to ecc per phase.
+// CONSUMER warps (every other warp).  Hand-offs are mbarriers: full[b] (fill landed + meta published) and empty[b]
+// (every consumer warp has finished gathering from buffer b); the consumers meet at one named barrier per phase,
+// between histogram and gather.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
+template <int NCT>
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 
-template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool STREAMING>
-__global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
-    const int half = ((P.smem_bytes - SM_DYN) / 2) & ~127;
-    if (threadIdx.x == 0) {
-        mbar_init(sbase + SM_MBAR, 1);                 // full[0], full[1]: the producer's arrive + the fill's bytes
-        mbar_init(sbase + SM_MBAR + 8, 1);
-        mbar_init(sbase + SM_MBAR + 16, NC / 32);      // empty[0], empty[1]: one arrive per consumer warp
-        mbar_init(sbase + SM_MBAR + 24, NC / 32);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (threadIdx.x < 16) sts_f64(sbase + SM_SIMACC + threadIdx.x * 8u, 0.0);
-    __syncthreads();
+struct PhaseHdr {
+    Phase ph;
+    bool first, big;
+    uint32_t wurec;
+};
+__device__ __forceinline__ PhaseHdr read_hdr(uint32_t sbase, uint32_t meta) {
+    const uint2 hdr = lds_u64(meta + META_HDR);  // {cnt | g0 << 8 | first << 16 | big << 17 | WU-record parity << 18, j0}
+    PhaseHdr h;
+    h.ph.cnt = (int)(hdr.x & 0xffu);
+    h.ph.g0 = (int)((hdr.x >> 8) & 0xffu);
+    h.ph.j0 = (int)hdr.y;
+    h.first = (hdr.x >> 16) & 1u;
+    h.big = (hdr.x >> 17) & 1u;
+    h.wurec = sbase + SM_WUREC + ((hdr.x >> 18) & 1u) * WUREC_BYTES;
+    return h;
+}
 
-    if (warp == 0) {  // ---- producer ----
-        Planner pl;
-        planner_init(P, pl, lane, sbase);
-#ifdef CA_ABLATE
-        unsigned n_ahead = 0;  // phases for which the producer had to wait for its buffer (it was ahead of the consumers)
-        long long t_prod = clock64();
-#endif
-#ifdef CA_MEASURE_FILL
-        long long t_fill = 0, b_fill = 0;
-#endif
-        for (uint32_t p = 0;; p++) {
-            const uint32_t b = p & 1u;
-            const bool last = pl.w >= P.nwu;
-            PhasePlan pp;
-            if (!last) pp = plan_compute(P, sbase, half, lane, pl);
-#ifdef CA_ABLATE
-            if (p >= 2) n_ahead += mbar_test(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u) ? 0u : 1u;
-#endif
-            if (p >= 2) mbar_wait<true>(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u);  // consumers are done with buffer b
-            if (last) {
-                plan_terminal(sbase, b, lane);
-#ifdef CA_ABLATE
-                if ((blockIdx.x == 3 || blockIdx.x == 77) && lane == 0)
-                    printf("[kind %s] block %d producer: %u phases, had to wait for a free buffer in %u (%.1f %%), %lld cycles\n", STREAMING ? "streaming" : "resident",
-                           blockIdx.x, p, n_ahead, 100.0 * n_ahead / (p + 1.0), clock64() - t_prod);
-#endif
-#ifdef CA_MEASURE_FILL
-                if ((blockIdx.x == 3 || blockIdx.x == 77) && lane == 0)
-                    printf("[kind %s] block %d fill: %.0f cycles and %.0f bytes per phase from issue to landing\n", STREAMING ? "streaming" : "resident", blockIdx.x,
-                           (double)t_fill / (p + 1.0), (double)b_fill / (p + 1.0));
-#endif
-                break;
-            }
-            plan_publish<UNITW>(P, sbase, b, sbase + SM_DYN + b * (uint32_t)half, lane, pl, pp);
-#ifdef CA_MEASURE_FILL  // tuning builds: the producer waits for its own fill to land (this serialises it: only the latency is meaningful)
-            {
-                const long long t0 = clock64();
-                mbar_wait(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);
-                t_fill += clock64() - t0;
-                b_fill += pp.ttot;
-            }
-#endif
-            plan_advance(P, pl, pp, lane, sbase);
-        }
-        return;
-    }
-
-    // ---- consumers ----
-    const int tid = (int)threadIdx.x - 32;  // consumer thread id: owns positions [4 tid, 4 tid + 4) of a resident item
-    // the current WU, as seen by every thread (everything else is re-read from the phase's meta record)
+// ---- resident items: a quad of consecutive positions per thread -------------------------------------------------
+// The plain consumer: the 16 labels of a cell for a whole super-tile come with ONE 32-byte load when the work unit reaches
+// the super-tile (L = its lower tile, Lh = its upper tile).
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW>
+__device__ __forceinline__ void consume_resident(const TileParams& P, const uint32_t sbase, const int tid, const int lane, const int warp) {
     int m = -1;
-    constexpr bool resident = !STREAMING;  // a launch holds work units of one kind only: two register allocations
     int4 cell = make_int4(-1, -1, -1, -1);
-    int4 cell2 = cell;  // streaming kernel: the second chunk of an item of at most two chunks
-    int nvalid = 0;
+    uint32_t vmask = 0;
     bool wactive = false;
     uint32_t rowidx = 0, sa = 0;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -605,192 +636,359 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
     int prev_m = -1;
 
     auto flush_acc = [&]() {
-        if (WANT_ECC && resident && m >= 0 && !CA_DBG(P, 0)) {
+        if (WANT_ECC && m >= 0 && !CA_DBG(P, 0)) {
             const double wscale = __ldg(P.w + m) * P.inv_norm;
-            if (cell.x >= 0) atomicAdd(P.ecc + cell.x, acc[0] * wscale);
-            if (cell.y >= 0) atomicAdd(P.ecc + cell.y, acc[1] * wscale);
-            if (cell.z >= 0) atomicAdd(P.ecc + cell.z, acc[2] * wscale);
-            if (cell.w >= 0) atomicAdd(P.ecc + cell.w, acc[3] * wscale);
+            if (cell.x >= 0) ecc_add(P, cell.x, acc[0] * wscale);
+            if (cell.y >= 0) ecc_add(P, cell.y, acc[1] * wscale);
+            if (cell.z >= 0) ecc_add(P, cell.z, acc[2] * wscale);
+            if (cell.w >= 0) ecc_add(P, cell.w, acc[3] * wscale);
         }
     };
 
-#ifdef CA_ABLATE
-    long long t_all = clock64(), u_all = 0;  // tuning builds: cycles and (padded) units of this block
-    unsigned n_late = 0;                      // phases whose buffer was not ready when this warp asked for it
-#endif
-#ifdef CA_TIMELINE                            // per-section cycle accounting (perturbs the kernel: spills)
-    long long t_sec[6] = {0, 0, 0, 0, 0, 0}, t_mark = clock64();  // wait full, WU start, histogram, barrier, gather, (unused)
-#define CA_SECTION(i)                 \
-    do {                              \
-        const long long t_ = clock64(); \
-        t_sec[i] += t_ - t_mark;      \
-        t_mark = t_;                  \
-    } while (0)
-#else
-#define CA_SECTION(i) do {} while (0)
-#endif
     uint32_t p = 0;
     for (;; p++) {
         const uint32_t b = p & 1u;
         const uint32_t meta = sbase + SM_META + b * META_BYTES, simacc = sbase + SM_SIMACC + b * 64u;
-#ifdef CA_ABLATE
-        n_late += !mbar_test(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);
-#endif
         mbar_wait(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);  // buffer b initialised, meta of phase p published
-        CA_SECTION(0);
-        const uint2 hdr = lds_u64(meta + META_HDR);  // {cnt | g0 << 8 | first << 16 | big << 17, j0}
+        const uint2 hdr = lds_u64(meta + META_HDR);  // {cnt | g0 << 8 | first << 16 | big << 17 | WU-record parity << 18, j0}
         Phase ph;
         ph.cnt = (int)(hdr.x & 0xffu);
         if (ph.cnt == 0) break;
         ph.g0 = (int)((hdr.x >> 8) & 0xffu);
         ph.j0 = (int)hdr.y;
         const bool big = (hdr.x >> 17) & 1u;
-        const uint32_t wurec = sbase + SM_WUREC + ((hdr.x >> 18) & 1u) * WUREC_BYTES;
         if ((hdr.x >> 16) & 1u) {  // a new work unit: retire the old one, pick up the new item
             flush_acc();
+            const uint32_t wurec = sbase + SM_WUREC + ((hdr.x >> 18) & 1u) * WUREC_BYTES;
             const uint2 w0 = lds_u64(wurec + WU_M), w1 = lds_u64(wurec + WU_NPOS), w2 = lds_u64(wurec + WU_SA);
             m = (int)w0.x;
             const int npos = (int)w1.x;
             const int64_t off = (int64_t)w2.y * P.perm_stride + (int)w0.y;
-            const int32_t* perm = P.perm + off;
-            sa = w2.x;
-            rowidx = 0;
             cur_j0 = -1;
-            if (resident) {
-                cell = make_int4(-1, -1, -1, -1);
-                uint2 qi = make_uint2(0u, 0u);
-                wactive = (tid & ~31) * 4 < npos;  // warp-uniform: the warp owns at least one position of the item
-                if (tid * 4 < npos) {
-                    cell = __ldg(reinterpret_cast<const int4*>(perm + tid * 4));
-                    qi = __ldg(reinterpret_cast<const uint2*>(P.qinfo) + (off >> 2) + tid);
-                }
-                nvalid = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);
-                rowidx = qi.x;
-                sa = qi.y;
-                acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+            cell = make_int4(-1, -1, -1, -1);
+            uint2 qi = make_uint2(0u, 0u);
+            wactive = (tid & ~31) * 4 < npos;  // warp-uniform: the warp owns at least one position of the item
+            if (tid * 4 < npos) {
+                cell = __ldg(reinterpret_cast<const int4*>(P.perm + off + tid * 4));
+                qi = __ldg(reinterpret_cast<const uint2*>(P.qinfo) + (off >> 2) + tid);
             }
+            vmask = (1u << ((cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0))) - 1u;  // padding sits at the end of a cluster
+            rowidx = qi.x;
+            sa = qi.y;
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
         }
-        CA_SECTION(1);
         // ---- histogram ----
-        if (resident) {
-            if (wactive) {
-                if (ph.j0 != cur_j0) {
-                    if (cur_j0 < 0 || ((ph.j0 ^ cur_j0) & ~(SUPER - 1)) != 0) {  // the WU's first phase or its second super-tile: L2 hits, the sectors were fetched by the first block that needed them
-                        if (!CA_DBG(P, 2)) {
-                            load_quad_super(P.lab16 + lab16_index(P.n, 0, ph.j0 & ~(SUPER - 1)), (uint32_t)P.n, cell, L, Lh);
-                        } else {  // tuning builds: no label loads, every cell carries label 0
+        if (wactive) {
+            if (ph.j0 != cur_j0) {
+                if (cur_j0 < 0 || ((ph.j0 ^ cur_j0) & ~(SUPER - 1)) != 0) {  // the WU's first phase or its second super-tile: L2 hits, the sectors were fetched by the first block that needed them
+                    if (!CA_DBG(P, 2)) {
+                        load_quad_super(P.lab16 + lab16_index(P.n, 0, ph.j0 & ~(SUPER - 1)), (uint32_t)P.n, cell, L, Lh);
+                    } else {  // tuning builds: no label loads, every cell carries label 0
 #pragma unroll
-                            for (int c = 0; c < 4; c++) L[c] = Lh[c] = make_uint4(0u, 0u, 0u, 0u);
-                        }
+                        for (int c = 0; c < 4; c++) L[c] = Lh[c] = make_uint4(0u, 0u, 0u, 0u);
                     }
-                    if ((ph.j0 & 8) != 0) {
+                }
+                if ((ph.j0 & 8) != 0) {
 #pragma unroll
-                        for (int c = 0; c < 4; c++) L[c] = Lh[c];
-                    }
-                    cur_j0 = ph.j0;
+                    for (int c = 0; c < 4; c++) L[c] = Lh[c];
                 }
-                if (!CA_DBG(P, 3)) hist_quad(P, meta, ph, L, rowidx);
+                cur_j0 = ph.j0;
             }
-        } else {
-            const int npos = (int)lds_u32(wurec + WU_NPOS);
-            const int32_t* perm = P.perm + (int64_t)lds_u32(wurec + WU_SLOT) * P.perm_stride + (int)lds_u32(wurec + WU_POS0);
-            const uint16_t* labj = P.lab16 + lab16_index(P.n, 0, ph.j0);
-            if (npos <= 2 * CAP) {  // at most two chunks (most streaming items): their labels stay in registers for the gather
-                if ((hdr.x >> 16) & 1u) {
-                    cell = __ldg(reinterpret_cast<const int4*>(perm + tid * 4));
-                    cell2 = tid * 4 + CAP < npos ? __ldg(reinterpret_cast<const int4*>(perm + tid * 4 + CAP)) : make_int4(-1, -1, -1, -1);
-                }
-                load_quad(labj, (uint32_t)P.n, cell, L);
-                hist_quad(P, meta, ph, L, 0u);
-                if ((tid & ~31) * 4 + CAP < npos) {  // warp-uniform: the warp owns positions of the second chunk
-                    load_quad(labj, (uint32_t)P.n, cell2, Lh);
-                    hist_quad(P, meta, ph, Lh, 0u);
-                }
-            } else
-            for (int cb = tid * 4; cb < npos; cb += 2 * CAP) {  // two chunks per trip: their loads are in flight together
-                const int4 none = make_int4(-1, -1, -1, -1);
-                const int4 ca = __ldg(reinterpret_cast<const int4*>(perm + cb));
-                const int4 cb4 = cb + CAP < npos ? __ldg(reinterpret_cast<const int4*>(perm + cb + CAP)) : none;
-                load_quad(labj, (uint32_t)P.n, ca, L);
-                load_quad(labj, (uint32_t)P.n, cb4, Lh);
-                hist_quad(P, meta, ph, L, 0u);
-                if (cb + CAP < npos) hist_quad(P, meta, ph, Lh, 0u);
-            }
+            if (!CA_DBG(P, 3)) hist_cells<4>(P, meta, ph, L, rowidx, 1);
         }
-        CA_SECTION(2);
-        if (!CA_DBG(P, 5)) consumer_sync();  // the tables of phase p are complete; every consumer has left phase p-1
-        CA_SECTION(3);
+        if (!CA_DBG(P, 5)) consumer_sync<NC_RES>();  // the tables of phase p are complete; every consumer has left phase p-1
         if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
         // ---- gather ----
-        if (resident) {
-            if (wactive && !CA_DBG(P, 4)) gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, rowidx, sa, nvalid, lane, acc);
-        } else {
-            const int npos = (int)lds_u32(wurec + WU_NPOS);
-            const bool wide = (lds_u32(wurec + WU_NROWS) & NROWS_WIDE) != 0;
-            const int32_t* perm = P.perm + (int64_t)lds_u32(wurec + WU_SLOT) * P.perm_stride + (int)lds_u32(wurec + WU_POS0);
+        if (wactive && !CA_DBG(P, 4)) gather_cells<4, false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, rowidx, sa, vmask, 1, lane, acc);
+        prev = ph;
+        prev_m = m;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sbase + SM_MBAR + 16 + b * 8u);  // this warp is done with buffer b (and its meta record)
+    }
+    flush_acc();
+    if (WANT_SIM) {
+        consumer_sync<NC_RES>();
+        if (warp == 1) flush_sim(P, sbase + SM_SIMACC + ((p - 1u) & 1u) * 64u, prev, prev_m, lane);
+    }
+}
+
+// The prefetching consumer (CA_TL_PREFETCH=1, needs the registers of a smaller block): a second register set holds a whole
+// super-tile loaded one tile AHEAD.
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW>
+__device__ __forceinline__ void consume_resident_prefetch(const TileParams& P, const uint32_t sbase, const int tid, const int lane, const int warp) {
+    constexpr bool PF = true;
+    int m = -1;
+    int4 cell = make_int4(-1, -1, -1, -1);
+    uint32_t vmask = 0;
+    bool wactive = false;
+    uint32_t rowidx = 0, sa = 0;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    uint4 L[4];           // labels of the current 8-partner tile for this thread's quad
+    uint4 A[4], B[4];     // PF: a whole super-tile (A = partners [16 s, 16 s + 8), B = [16 s + 8, 16 s + 16)), loaded one tile ahead;
+                          // otherwise only B is used (the low tile is loaded straight into L)
+    int n_st = -1;        // PF: the super-tile whose labels A / B hold for the CURRENT cells (-1 = none)
+    bool n_next = false;  // PF: A / B were loaded with the NEXT work unit's cells (they become current at its first phase)
+    int4 cellN = make_int4(-1, -1, -1, -1);  // PF: the next work unit's cell ids and quad info, fetched during this one's last tiles
+    uint2 qiN = make_uint2(0u, 0u);
+    bool haveN = false;
+    uint32_t wurec = sbase + SM_WUREC;  // PF: the current unit's record (its last partner and the next unit's coordinates are re-read from it)
+    int cur_j0 = -1;
+    Phase prev;
+    prev.j0 = prev.g0 = prev.cnt = 0;
+    int prev_m = -1;
+
+    auto flush_acc = [&]() {
+        if (WANT_ECC && m >= 0 && !CA_DBG(P, 0)) {
             const double wscale = __ldg(P.w + m) * P.inv_norm;
-            if (npos <= 2 * CAP) {
+            if (cell.x >= 0) ecc_add(P, cell.x, acc[0] * wscale);
+            if (cell.y >= 0) ecc_add(P, cell.y, acc[1] * wscale);
+            if (cell.z >= 0) ecc_add(P, cell.z, acc[2] * wscale);
+            if (cell.w >= 0) ecc_add(P, cell.w, acc[3] * wscale);
+        }
+    };
+
+    uint32_t p = 0;
+    for (;; p++) {
+        const uint32_t b = p & 1u;
+        const uint32_t meta = sbase + SM_META + b * META_BYTES, simacc = sbase + SM_SIMACC + b * 64u;
+        mbar_wait(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);  // buffer b initialised, meta of phase p published
+        const PhaseHdr h = read_hdr(sbase, meta);
+        const Phase ph = h.ph;
+        if (ph.cnt == 0) break;
+        if (h.first) {  // a new work unit: retire the old one, pick up the new item
+            flush_acc();
+            const uint2 w0 = lds_u64(h.wurec + WU_M), w1 = lds_u64(h.wurec + WU_NPOS), w2 = lds_u64(h.wurec + WU_SA);
+            m = (int)w0.x;
+            const int npos = (int)w1.x;
+            const int64_t off = (int64_t)w2.y * P.perm_stride + (int)w0.y;
+            uint2 qi = make_uint2(0u, 0u);
+            if (PF && haveN) {
+                cell = cellN;
+                qi = qiN;
+            } else {
+                cell = make_int4(-1, -1, -1, -1);
+                if (tid * 4 < npos) {
+                    cell = __ldg(reinterpret_cast<const int4*>(P.perm + off + tid * 4));
+                    qi = __ldg(reinterpret_cast<const uint2*>(P.qinfo) + (off >> 2) + tid);
+                }
+            }
+            if (PF) {
+                wurec = h.wurec;
+                if (!n_next) n_st = -1;  // what A / B hold belongs to the previous unit's cells
+                n_next = false;
+                haveN = false;
+            }
+            wactive = (tid & ~31) * 4 < npos;  // warp-uniform: the warp owns at least one position of the item
+            vmask = (cell.x >= 0 ? 1u : 0u) | (cell.y >= 0 ? 2u : 0u) | (cell.z >= 0 ? 4u : 0u) | (cell.w >= 0 ? 8u : 0u);
+            rowidx = qi.x;
+            sa = qi.y;
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+            cur_j0 = -1;
+        }
+        // ---- labels of the tile ----
+        if (ph.j0 != cur_j0) {
+            const int st = ph.j0 >> 4;
+            if (PF) {
+                if (n_st != st) {  // not loaded ahead (the block's first unit, or a unit of a single tile before this one)
+                    load_quad_super(P.lab16 + lab16_index(P.n, 0, st << 4), (uint32_t)P.n, cell, A, B);
+                    n_st = st;
+                }
+                const bool hi = (ph.j0 & 8) != 0;
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    if (h && !((tid & ~31) * 4 + CAP < npos)) break;  // warp-uniform
-                    const int4 cl = h ? cell2 : cell;
-                    const int nv = (cl.x >= 0) + (cl.y >= 0) + (cl.z >= 0) + (cl.w >= 0);
-                    double a4[4] = {0.0, 0.0, 0.0, 0.0};
-                    gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, h ? Lh : L, 0u, sa, nv, lane, a4);
-                    if (WANT_ECC) {
-                        if (cl.x >= 0) atomicAdd(P.ecc + cl.x, a4[0] * wscale);
-                        if (cl.y >= 0) atomicAdd(P.ecc + cl.y, a4[1] * wscale);
-                        if (cl.z >= 0) atomicAdd(P.ecc + cl.z, a4[2] * wscale);
-                        if (cl.w >= 0) atomicAdd(P.ecc + cl.w, a4[3] * wscale);
+                for (int c = 0; c < 4; c++) L[c] = hi ? B[c] : A[c];
+                const uint2 w3 = lds_u64(wurec + WU_JHI);  // {the unit's last partner + 1, the next unit's first super-tile}
+                const int ti = ph.j0 >> 3, tl = ((int)w3.x - 1) >> 3;  // this tile, the unit's last tile
+                const int nxt_st = (int)w3.y;
+                const bool hadN = haveN;
+                const int nxt_npos = (int)lds_u32(wurec + WU_NXT_NPOS);
+                if (ti + 1 >= tl && !haveN && nxt_npos > 0) {  // the unit's last two tiles: fetch the next unit's cell ids and quad info
+                    const uint2 w4 = lds_u64(wurec + WU_NXT_SLOT);
+                    const int64_t nxt_off = (int64_t)w4.x * P.perm_stride + (int)w4.y;
+                    cellN = make_int4(-1, -1, -1, -1);
+                    qiN = make_uint2(0u, 0u);
+                    if (tid * 4 < nxt_npos) {
+                        cellN = __ldg(reinterpret_cast<const int4*>(P.perm + nxt_off + tid * 4));
+                        qiN = __ldg(reinterpret_cast<const uint2*>(P.qinfo) + (nxt_off >> 2) + tid);
+                    }
+                    haveN = true;
+                }
+                if (hi || ti >= tl) {  // A / B are free from here on: load one tile ahead
+                    if (ti < tl) {     // the unit's next super-tile, same cells
+                        load_quad_super(P.lab16 + lab16_index(P.n, 0, (st + 1) << 4), (uint32_t)P.n, cell, A, B);
+                        n_st = st + 1;
+                    } else if (hadN) {  // the next unit's first super-tile, with the cell ids fetched a tile ago
+                        load_quad_super(P.lab16 + lab16_index(P.n, 0, nxt_st << 4), (uint32_t)P.n, cellN, A, B);
+                        n_st = nxt_st;
+                        n_next = true;
                     }
                 }
-            } else
-            for (int cb0 = 0; cb0 < npos; cb0 += CAP) {  // warp-uniform trip count: gather_quad shuffles when WANT_SIM
+            } else if (wactive) {
+                if (cur_j0 < 0 || ((ph.j0 ^ cur_j0) & ~(SUPER - 1)) != 0) {  // the WU's first phase or its second super-tile
+                    if (!CA_DBG(P, 2)) {
+                        load_quad_super(P.lab16 + lab16_index(P.n, 0, st << 4), (uint32_t)P.n, cell, L, B);
+                    } else {  // tuning builds: no label loads, every cell carries label 0
+#pragma unroll
+                        for (int c = 0; c < 4; c++) L[c] = B[c] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                if ((ph.j0 & 8) != 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) L[c] = B[c];
+                }
+            }
+            cur_j0 = ph.j0;
+        }
+        // ---- histogram ----
+        if (wactive && !CA_DBG(P, 3)) hist_cells<4>(P, meta, ph, L, rowidx, 1);
+        if (!CA_DBG(P, 5)) consumer_sync<NC_RES>();  // the tables of phase p are complete; every consumer has left phase p-1
+        if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
+        // ---- gather ----
+        if (wactive && !CA_DBG(P, 4)) gather_cells<4, false, WANT_SIM, UNITW>(P, meta, simacc, ph, h.big, L, rowidx, sa, vmask, 1, lane, acc);
+        prev = ph;
+        prev_m = m;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sbase + SM_MBAR + 16 + b * 8u);  // this warp is done with buffer b (and its meta record)
+    }
+    flush_acc();
+    if (WANT_SIM) {
+        consumer_sync<NC_RES>();
+        if (warp == 1) flush_sim(P, sbase + SM_SIMACC + ((p - 1u) & 1u) * 64u, prev, prev_m, lane);
+    }
+}
+
+// ---- streaming items: one cluster of more than TL_CAP cells, one table row ----------------------------------------
+// The cells are taken in chunks of SCHUNK = 4 * NC_STR positions, a quad per thread and chunk.  An item of at most two
+// chunks (most of them) keeps both chunks' cell ids for the whole work unit and their labels between histogram and gather;
+// a longer one streams the cells from global memory in both passes.  A warp whose quad of the second chunk lies beyond the
+// item skips it (warp-uniform), so the work is counted in warps x chunks, not in whole chunks.  Labels are loaded per
+// 8-partner tile (16 bytes per cell); the sums go to ecc per phase.
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW>
+__device__ __forceinline__ void consume_streaming(const TileParams& P, const uint32_t sbase, const int tid, const int lane, const int warp) {
+    constexpr int SCHUNK = 4 * NC_STR;
+    int m = -1, npos = 0;
+    bool wide = false;
+    const int32_t* perm = P.perm;
+    uint32_t sa = 0;
+    int4 cell = make_int4(-1, -1, -1, -1), cell2 = cell;
+    uint4 L[4], Lh[4];
+    double wscale = 0.0;
+    Phase prev;
+    prev.j0 = prev.g0 = prev.cnt = 0;
+    int prev_m = -1;
+    auto vmask_of = [](int4 c) { return (c.x >= 0 ? 1u : 0u) | (c.y >= 0 ? 2u : 0u) | (c.z >= 0 ? 4u : 0u) | (c.w >= 0 ? 8u : 0u); };
+    auto flush4 = [&](int4 cl, const double (&a4)[4]) {
+        if (WANT_ECC) {
+            if (cl.x >= 0) ecc_add(P, cl.x, a4[0] * wscale);
+            if (cl.y >= 0) ecc_add(P, cl.y, a4[1] * wscale);
+            if (cl.z >= 0) ecc_add(P, cl.z, a4[2] * wscale);
+            if (cl.w >= 0) ecc_add(P, cl.w, a4[3] * wscale);
+        }
+    };
+
+    uint32_t p = 0;
+    for (;; p++) {
+        const uint32_t b = p & 1u;
+        const uint32_t meta = sbase + SM_META + b * META_BYTES, simacc = sbase + SM_SIMACC + b * 64u;
+        mbar_wait(sbase + SM_MBAR + b * 8u, (p >> 1) & 1u);
+        const PhaseHdr h = read_hdr(sbase, meta);
+        const Phase ph = h.ph;
+        if (ph.cnt == 0) break;
+        if (h.first) {
+            const uint2 w0 = lds_u64(h.wurec + WU_M), w1 = lds_u64(h.wurec + WU_NPOS), w2 = lds_u64(h.wurec + WU_SA);
+            m = (int)w0.x;
+            npos = (int)w1.x;
+            wide = (w1.y & NROWS_WIDE) != 0;
+            sa = w2.x;
+            perm = P.perm + (int64_t)w2.y * P.perm_stride + (int)w0.y;
+            wscale = __ldg(P.w + m) * P.inv_norm;
+            if (npos <= 2 * SCHUNK) {
+                cell = __ldg(reinterpret_cast<const int4*>(perm + tid * 4));
+                cell2 = tid * 4 + SCHUNK < npos ? __ldg(reinterpret_cast<const int4*>(perm + tid * 4 + SCHUNK)) : make_int4(-1, -1, -1, -1);
+            }
+        }
+        const uint16_t* labj = P.lab16 + lab16_index(P.n, 0, ph.j0);
+        const bool second = (tid & ~31) * 4 + SCHUNK < npos;  // warp-uniform: the warp owns positions of the second chunk
+        // ---- histogram ----
+        if (npos <= 2 * SCHUNK) {
+            load_quad(labj, (uint32_t)P.n, cell, L);
+            if (second) load_quad(labj, (uint32_t)P.n, cell2, Lh);
+            hist_cells<4>(P, meta, ph, L, 0u, 1);
+            if (second) hist_cells<4>(P, meta, ph, Lh, 0u, 1);
+        } else {
+            for (int cb = tid * 4; cb < npos; cb += 2 * SCHUNK) {  // two chunks per trip: their loads are in flight together
+                const int4 none = make_int4(-1, -1, -1, -1);
+                const int4 ca = __ldg(reinterpret_cast<const int4*>(perm + cb));
+                const int4 cb4 = cb + SCHUNK < npos ? __ldg(reinterpret_cast<const int4*>(perm + cb + SCHUNK)) : none;
+                load_quad(labj, (uint32_t)P.n, ca, L);
+                load_quad(labj, (uint32_t)P.n, cb4, Lh);
+                hist_cells<4>(P, meta, ph, L, 0u, 1);
+                if (cb + SCHUNK < npos) hist_cells<4>(P, meta, ph, Lh, 0u, 1);
+            }
+        }
+        consumer_sync<NC_STR>();
+        if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
+        // ---- gather ----
+        if (npos <= 2 * SCHUNK) {
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                if (hh && !second) break;  // warp-uniform
+                const int4 cl = hh ? cell2 : cell;
+                double a4[4] = {0.0, 0.0, 0.0, 0.0};
+                gather_cells<4, false, WANT_SIM, UNITW>(P, meta, simacc, ph, h.big, hh ? Lh : L, 0u, sa, vmask_of(cl), 1, lane, a4);
+                flush4(cl, a4);
+            }
+        } else {
+            for (int cb0 = 0; cb0 < npos; cb0 += SCHUNK) {  // block-uniform trip count: gather_cells shuffles when WANT_SIM
                 const int cb = cb0 + tid * 4;
                 int4 cl = make_int4(-1, -1, -1, -1);
                 if (cb < npos) cl = __ldg(reinterpret_cast<const int4*>(perm + cb));
-                const int nv = (cl.x >= 0) + (cl.y >= 0) + (cl.z >= 0) + (cl.w >= 0);
-                load_quad(P.lab16 + lab16_index(P.n, 0, ph.j0), (uint32_t)P.n, cl, L);
+                load_quad(labj, (uint32_t)P.n, cl, L);
                 double a4[4] = {0.0, 0.0, 0.0, 0.0};
                 if (wide)
-                    gather_quad<true, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, 0u, sa, nv, lane, a4);
+                    gather_cells<4, true, WANT_SIM, UNITW>(P, meta, simacc, ph, h.big, L, 0u, sa, vmask_of(cl), 1, lane, a4);
                 else
-                    gather_quad<false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, 0u, sa, nv, lane, a4);
-                if (WANT_ECC) {
-                    if (cl.x >= 0) atomicAdd(P.ecc + cl.x, a4[0] * wscale);
-                    if (cl.y >= 0) atomicAdd(P.ecc + cl.y, a4[1] * wscale);
-                    if (cl.z >= 0) atomicAdd(P.ecc + cl.z, a4[2] * wscale);
-                    if (cl.w >= 0) atomicAdd(P.ecc + cl.w, a4[3] * wscale);
-                }
+                    gather_cells<4, false, WANT_SIM, UNITW>(P, meta, simacc, ph, h.big, L, 0u, sa, vmask_of(cl), 1, lane, a4);
+                flush4(cl, a4);
             }
         }
         prev = ph;
         prev_m = m;
-        CA_SECTION(4);
-#ifdef CA_ABLATE
-        u_all += (long long)lds_u32(wurec + WU_NPOS) * ph.cnt;
-#endif
         __syncwarp();
-        if (lane == 0) mbar_arrive(sbase + SM_MBAR + 16 + b * 8u);  // this warp is done with buffer b (and its meta record)
+        if (lane == 0) mbar_arrive(sbase + SM_MBAR + 16 + b * 8u);
     }
-#ifdef CA_ABLATE
-    if ((blockIdx.x == 3 || blockIdx.x == 77) && (threadIdx.x == 64 || threadIdx.x == 512)) {
-        t_all = clock64() - t_all;
-        printf("[kind %s] block %d warp %d: %lld cycles, %lld padded units (%.3f cycles/unit), %u phases (%.0f units/phase), buffer not ready in %u (%.1f %%)\n",
-               STREAMING ? "streaming" : "resident", blockIdx.x, warp, t_all, u_all, (double)t_all / (double)(u_all + 1), p, (double)u_all / (p + 1.0), n_late,
-               100.0 * n_late / (p + 1.0));
-#ifdef CA_TIMELINE
-        printf("[kind %s] block %d warp %d: %% of cycles: wait-full %.1f, WU start + label loads %.1f, histogram %.1f, barrier %.1f, gather %.1f\n",
-               STREAMING ? "streaming" : "resident", blockIdx.x, warp, 100.0 * t_sec[0] / t_all, 100.0 * t_sec[1] / t_all, 100.0 * t_sec[2] / t_all,
-               100.0 * t_sec[3] / t_all, 100.0 * t_sec[4] / t_all);
-#endif
-    }
-#endif
-    flush_acc();
     if (WANT_SIM) {
-        consumer_sync();
+        consumer_sync<NC_STR>();
         if (warp == 1) flush_sim(P, sbase + SM_SIMACC + ((p - 1u) & 1u) * 64u, prev, prev_m, lane);
     }
+}
+
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool STREAMING>
+__global__ void __launch_bounds__((STREAMING ? NC_STR : NC_RES) + 32, 1) wave_kernel(const TileParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NCT = STREAMING ? NC_STR : NC_RES;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const int half = ((P.smem_bytes - SM_DYN) / 2) & ~127;
+    if (threadIdx.x == 0) {
+        mbar_init(sbase + SM_MBAR, 1);                 // full[0], full[1]: the producer's arrive + the fill's bytes
+        mbar_init(sbase + SM_MBAR + 8, 1);
+        mbar_init(sbase + SM_MBAR + 16, NCT / 32);     // empty[0], empty[1]: one arrive per consumer warp
+        mbar_init(sbase + SM_MBAR + 24, NCT / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 16) sts_b64(sbase + SM_SIMACC + threadIdx.x * 8u, 0ull);
+    __syncthreads();
+    if (warp == 0) {
+        producer_loop<UNITW>(P, sbase, half, lane);
+        return;
+    }
+    const int tid = (int)threadIdx.x - 32;
+    if (STREAMING)
+        consume_streaming<WANT_ECC, WANT_SIM, UNITW>(P, sbase, tid, lane, warp);
+    else if (CA_TL_PREFETCH)
+        consume_resident_prefetch<WANT_ECC, WANT_SIM, UNITW>(P, sbase, tid, lane, warp);
+    else
+        consume_resident<WANT_ECC, WANT_SIM, UNITW>(P, sbase, tid, lane, warp);
 }
 
 // Shared memory one block asks for and the number of table rows a resident block may own so that at least one
@@ -798,10 +996,10 @@ __global__ void __launch_bounds__(NT, TL_BLOCKS) wave_kernel(const TileParams P)
 int tile_smem_budget(int32_t kmax, int32_t* max_rows_out, int32_t* half_out) {
     Ctx& c = ctx();
     const size_t optin = c.smem_optin ? c.smem_optin : 227 * 1024;
-    const int budget = TL_BLOCKS == 1 ? (int)optin : (int)(((optin + 1024) / TL_BLOCKS - 1024) & ~127);  // 1 KB per block is reserved by the system
+    const int budget = (int)optin;
     // Leave 32 KB of the SM's 228 KB to the L1 cache (the carve-out steps are ... 132, 164, 196, 228 KB): register
-    // spills and the producer's small loads otherwise go to L2 at ~300 cycles each.  Measured on C5: 227 KB 356 ms,
-    // 195 KB 340 ms, 163 KB 348 ms, 131 KB 365 ms.  CA_SMEM_KB overrides it (tuning).
+    // spills and the producer's small loads otherwise go to L2 at ~300 cycles each.  Measured on C5 (round 1): 163 KB
+    // 210 ms, 179 KB 210 ms, 195 KB 206 ms, 211 KB 237 ms, 227 KB 234 ms.  CA_SMEM_KB overrides it (tuning).
     int budget_kb = 195;
     if (const char* e = getenv("CA_SMEM_KB")) budget_kb = atoi(e);
     const int budget_eff = budget_kb > 0 ? std::min(budget, budget_kb * 1024) : budget;
@@ -815,7 +1013,7 @@ int tile_smem_budget(int32_t kmax, int32_t* max_rows_out, int32_t* half_out) {
 }
 
 // per-quad row index and cluster size of every owned partition's cluster-sorted order (streamed by the wave kernel
-// instead of three dependent random loads per work unit)
+// instead of three dependent random loads per work unit) -- only behind CA_SORT_LEGACY=1; the chunk sort writes them itself
 __global__ void __launch_bounds__(256) qinfo_kernel(const TileParams P, const int32_t* __restrict__ parts, int32_t nparts, int64_t nquads) {
     const int sl = blockIdx.y;
     if (sl >= nparts) return;
@@ -846,8 +1044,8 @@ static int launch_wave_k(const TileParams& p, cudaStream_t s) {
     if (p.nwu <= 0) return CA_OK;
     auto kern = wave_kernel<E, S, U, STREAMING>;
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-    const int grid = std::min<int>(ca::ctx().sm_count * TL_BLOCKS, p.nwu);
-    kern<<<(unsigned)grid, NT, (size_t)p.smem_bytes, s>>>(p);
+    const int grid = std::min<int>(ca::ctx().sm_count, p.nwu);
+    kern<<<(unsigned)grid, (STREAMING ? NC_STR : NC_RES) + 32, (size_t)p.smem_bytes, s>>>(p);
     CA_CUDA(cudaGetLastError());
     ca::ctx().launches++;
     return CA_OK;
@@ -873,5 +1071,12 @@ int launch_tile(const TileParams& p, cudaStream_t s) {
     }
     return CA_OK;
 }
+
+double sim_fix_scale(int64_t n) {  // 2^F, F = 61 - ceil(log2(n + 1)): n terms of at most 1 stay below 2^62
+    int bits = 0;
+    while (((int64_t)1 << bits) < n + 1) bits++;
+    return ldexp(1.0, 61 - bits);
+}
+double sim_fix_magic(int64_t n) { return 1.5 * 4503599627370496.0 / sim_fix_scale(n); }  // 1.5 * 2^(52 - F)
 
 }  // namespace ca

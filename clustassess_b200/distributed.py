@@ -58,12 +58,15 @@ def upload_sharded(host_labels, device_labels, group=None):
     return device_labels
 
 
-def consistency_sharded(n, m, weights, partial_fn, finish_fn, group=None, want_sim=False, device=None):
+def consistency_sharded(n, m, weights, partial_fn, finish_fn, group=None, want_sim=False, device=None, fixed_point=False):
     """Run one rank's share and combine.
 
     partial_fn(rank, world, ecc_tensor, sim_tensor_or_None): accumulates this rank's partial sums into the
         zeroed float64 tensors (GPU: _capi.DeviceLabels.consistency_partial on their data_ptr()).
     finish_fn(ecc_tensor, sim_tensor_or_None): adds the identical-pair constant, mirrors the matrix.
+    fixed_point: the partial sums are the library's 64-bit fixed-point integers (ca_consistency_partial_dev): they
+        are summed over the ranks AS INTEGERS, which makes the result independent of the reduction order
+        (bit-identical for any world size); finish_fn converts them to doubles.
     Returns (ecc, sim) tensors, identical on every rank.
     """
     import torch
@@ -77,9 +80,9 @@ def consistency_sharded(n, m, weights, partial_fn, finish_fn, group=None, want_s
         torch.cuda.current_stream().synchronize()  # the zero fills must land before the library's stream adds
     partial_fn(rank, world, ecc, sim)
     if world > 1:
-        dist.all_reduce(ecc, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(ecc.view(torch.int64) if fixed_point else ecc, op=dist.ReduceOp.SUM, group=group)
         if sim is not None:
-            dist.all_reduce(sim, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(sim.view(torch.int64) if fixed_point else sim, op=dist.ReduceOp.SUM, group=group)
         if ecc.is_cuda:
             torch.cuda.current_stream().synchronize()
     finish_fn(ecc, sim)

@@ -263,18 +263,39 @@ def merge_partitions(partition_list, ecs_thresh=1, order_logic=("freq", "avg_agr
     elif not all(k in partition_list[0] for k in ("mb", "freq")):
         return [merge_partitions(sub, ecs_thresh, order_logic) for sub in partition_list]
 
-    if ecs_thresh == 1:
-        part_list = merge_identical_partitions(partition_list)
+    need_matrix = return_ecs_matrix or order_logic in ("freq", "avg_agreement")
+    if ecs_thresh == 1 and len(partition_list) > 1:
+        # the partitions cross PCIe ONCE: the dedup pre-pass (R/ECS.R:1204) and the consistency of the kept partitions
+        # (R/ECS.R:1214-1222) work on the same device-resident label set
+        cols, _, m, n = _label_columns([p["mb"] for p in partition_list])
+        dev = _capi.DeviceLabels(n, m, primary=True).upload_columns(cols)
+        try:
+            keep, freq = dev.merge_identical([float(p["freq"]) for p in partition_list])
+            part_list = []
+            for t, f in zip(keep, freq):
+                r = dict(partition_list[int(t)])
+                r["freq"] = int(f) if f == int(f) else float(f)
+                part_list.append(r)
+            if len(part_list) == 1:
+                return {"partitions": part_list, "ecc": np.ones(n)}
+            # nothing merged and one device: the resident set is used as it is; otherwise the kept partitions are copied
+            # device to device (onto every selected GPU when there are several)
+            idx = None if (len(keep) == m and _capi.lib().ca_device_count() <= 1) else keep
+            ecc, mat = dev.consistency(idx, freq, need_matrix)
+        finally:
+            dev.close()
+        ecc = _wrap(ecc, part_list[0]["mb"])
     else:
-        part_list = _merge_partitions_ecs(partition_list, ecs_thresh)
-
-    n = len(part_list[0]["mb"])
-    if len(part_list) == 1:
-        return {"partitions": part_list, "ecc": np.ones(n)}
-
-    cons = weighted_element_consistency([p["mb"] for p in part_list], weights=[p["freq"] for p in part_list],
-                                        calculate_sim_matrix=True)
-    ecc, mat = cons["ecc"], cons["ecs_matrix"]
+        if ecs_thresh == 1:
+            part_list = merge_identical_partitions(partition_list)
+        else:
+            part_list = _merge_partitions_ecs(partition_list, ecs_thresh)
+        n = len(part_list[0]["mb"])
+        if len(part_list) == 1:
+            return {"partitions": part_list, "ecc": np.ones(n)}
+        cons = weighted_element_consistency([p["mb"] for p in part_list], weights=[p["freq"] for p in part_list],
+                                            calculate_sim_matrix=True)
+        ecc, mat = cons["ecc"], cons["ecs_matrix"]
     if order_logic not in ("freq", "avg_agreement"):
         out = {"partitions": part_list, "ecc": ecc}
         if return_ecs_matrix:

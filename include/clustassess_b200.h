@@ -21,8 +21,14 @@
  *     directly.
  *   - Inputs are never written.  Outputs are caller-allocated; "host" pointers unless the name ends in
  *     _dev.  There is NO CPU fallback: without a CUDA device every compute entry returns CA_E_NO_DEVICE.
- *   - fp64 throughout; per-pair ECS is one IEEE division (bit-identical to the reference), set-level
- *     results are within 1e-9 absolute of the reference (summation order differs).
+ *   - fp64 throughout.  Per-pair ECS (ca_ecs_pair, ca_ecs_pair_mean, ca_contingency) is one IEEE division per cell:
+ *     bit-identical to the reference.  The BATCHED entries evaluate count / max as count * (1 / max) with a
+ *     Newton-refined reciprocal (relative error < 1e-13) and sum in another order than the reference: set-level
+ *     results (ecc, matrix, agreement) are within 1e-9 absolute of it, not bit-identical to it.
+ *   - Set-level results are REPRODUCIBLE: the sums are accumulated as 64-bit fixed-point integers, so two runs -- on
+ *     one GPU or sharded over several -- return identical bits.
+ *   - Cluster counts: the batched engine takes up to 24 799 clusters per partition; beyond that (any count that fits
+ *     memory, like the reference) the single-device entries loop over the pairs with a hashed contingency table.
  */
 #ifndef CLUSTASSESS_B200_H
 #define CLUSTASSESS_B200_H
@@ -44,17 +50,34 @@ extern "C" {
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
 
-/* Select the device(s) this process computes on.  devices==NULL or ndev<=0 -> device 0.  Idempotent.
- * One process drives one GPU; multi-GPU jobs run one process per GPU and shard with rank/world below
- * (reference analogue: the foreach %dopar% workers of R/ECS.R:953). */
+/* Select the device(s) this process computes on.  devices==NULL or ndev<=0 -> device 0.  The same list again is a
+ * no-op; a different list releases everything held on the old devices first (refused with CA_E_ARG while label sets
+ * created on them are alive).
+ * ndev > 1: ONE process drives all the listed GPUs (reference analogue: the foreach %dopar% workers of R/ECS.R:953, but
+ * inside one .Call): the batched entries below -- ca_consistency[_cols], ca_sim_matrix[_cols], ca_*_resident -- shard the
+ * label matrix by 32-partition spans, one host thread per device packs its share and stores the compact labels into every
+ * device's memory over NVLink, every device runs the pairs of its own partitions, and ONE ncclAllReduce (64-bit integer
+ * sums) combines the per-cell sums (M x M sums likewise).  Needs peer access between the devices; libnccl.so.2 is loaded
+ * at this call (without it the sums are added by a kernel that reads peer memory).  ca_device_count(): devices selected. */
 int ca_init(const int *devices, int ndev);
+int ca_device_count(void);
 void ca_shutdown(void);
 const char *ca_last_error(void);
 int ca_version(void);
 
-/* Launch all work on this CUDA stream (a cudaStream_t passed as void*).  NULL restores the library's
- * own stream.  Lets a caller time the kernels with its own events. */
+/* Launch the (primary device's) work on a caller's CUDA stream.
+ * ca_set_stream(handle): handle is a cudaStream_t passed as void*; NULL restores the library's own stream.
+ * ca_use_stream(handle, which) also reaches the streams a NULL handle stands for:
+ *   CA_STREAM_LIBRARY the library's own non-blocking stream (default), CA_STREAM_HANDLE the given handle (NULL = the legacy
+ *   default stream), CA_STREAM_LEGACY / CA_STREAM_PER_THREAD the CUDA sentinels.
+ * Work is ordered on that stream only: whoever produced device memory handed to ca_labels_wrap on ANOTHER stream must
+ * synchronise with it first. */
+#define CA_STREAM_LIBRARY 0
+#define CA_STREAM_HANDLE 1
+#define CA_STREAM_LEGACY 2
+#define CA_STREAM_PER_THREAD 3
 int ca_set_stream(void *cuda_stream);
+int ca_use_stream(void *cuda_stream, int which);
 
 /* ---- legacy per-pair entry points (replace the three Rcpp routines one for one) ------------------- */
 
@@ -116,13 +139,19 @@ int ca_merge_identical_cols(const int32_t *const *cols, int64_t n, int32_t m, co
 
 typedef struct ca_labels ca_labels_t;
 
-int ca_labels_create(int64_t n, int32_t m, ca_labels_t **out); /* device M x N int32, uninitialised    */
+/* ca_labels_create: device M x N int32, uninitialised.  With several devices selected (ca_init) and more than 32 partitions the
+ * set is SHARDED over them by 32-partition spans; ca_labels_create_on_primary always makes a single-device set (what the dedup
+ * pre-pass, ca_consistency_partial_dev and ca_labels_device_ptr need).  ca_labels_shape returns n and m of a set. */
+int ca_labels_create(int64_t n, int32_t m, ca_labels_t **out);
+int ca_labels_create_on_primary(int64_t n, int32_t m, ca_labels_t **out);
+int ca_labels_shape(ca_labels_t *h, int64_t *n_out, int32_t *m_out);
+int ca_labels_is_sharded(ca_labels_t *h);
 int ca_labels_wrap(int64_t n, int32_t m, void *device_matrix, ca_labels_t **out); /* caller-owned device M x N int32
                                                                   (e.g. filled by an NCCL all-gather)  */
 int ca_labels_upload(ca_labels_t *h, const int32_t *labels);   /* host -> device, whole matrix         */
 int ca_labels_upload_col(ca_labels_t *h, int32_t p, const int32_t *col);
 int ca_labels_upload_cols(ca_labels_t *h, const int32_t *const *cols); /* all M columns, one staged upload     */
-void *ca_labels_device_ptr(ca_labels_t *h);                    /* raw device matrix (int32 M x N)      */
+void *ca_labels_device_ptr(ca_labels_t *h);                    /* raw device matrix (int32 M x N); NULL for a sharded set */
 int ca_labels_invalidate(ca_labels_t *h);                      /* call after writing through the ptr   */
 int ca_labels_destroy(ca_labels_t *h);
 
@@ -139,15 +168,19 @@ int ca_labels_select(ca_labels_t *src, const int32_t *idx, int32_t k, ca_labels_
 int ca_consistency_resident(ca_labels_t *h, const int32_t *idx, int32_t k, const double *weights, double *ecc_out,
                             double *sim_out);
 int ca_sim_matrix_resident(ca_labels_t *h, const int32_t *idx, int32_t k, double *sim_out);
+/* merge_identical_partitions (R/ECS.R:1021-1054) of a resident single-device set: element_consistency / merge_partitions upload
+ * their partitions once, dedup them here and hand the kept indices + summed frequencies to ca_consistency_resident. */
+int ca_merge_identical_resident(ca_labels_t *h, const double *freq_in, int32_t *keep_out, double *freq_out, int32_t *u_out);
 
 /* One rank's share of the all-pairs job on a device-resident label set.
  *   rank/world : this process handles the partitions i with zigzag(i) == rank and all their pairs (i,j>i);
  *                world == 1 -> everything.
- *   ecc_dev    : device double[n]   (may be NULL)  += sum over owned i of (w_i/norm) sum_{j>i} w_j ECS_ij
- *   sim_dev    : device double[m*m] (may be NULL)  += sum_n ECS_ij[n] at [i*m+j] for owned i, j>i
- * Both buffers must be zeroed by the caller (or hold the values to accumulate onto).  After summing the
- * buffers over ranks (one NCCL allreduce each), ca_consistency_finish_dev() adds the identical-pair
- * constant, and mirrors / normalises the matrix. */
+ *   ecc_dev    : device buffer of n 8-byte words     (may be NULL)  += sum over owned i of (w_i/norm) sum_{j>i} w_j ECS_ij
+ *   sim_dev    : device buffer of m*m 8-byte words   (may be NULL)  += sum_n ECS_ij[n] at [i*m+j] for owned i, j>i
+ * The words are 64-bit FIXED-POINT integers until ca_consistency_finish_dev() has run: zero the buffers before the first
+ * partial call, sum them over the ranks AS INTEGERS (one NCCL allreduce of int64 each: the result is then independent of the
+ * reduction order), then ca_consistency_finish_dev() converts them to doubles in place, adds the identical-pair constant,
+ * and mirrors / normalises the matrix. */
 int ca_shard_owner(int32_t i, int32_t world); /* rank that owns partition i and its pairs (i, j > i) */
 int ca_consistency_partial_dev(ca_labels_t *h, const double *weights_host, int32_t rank, int32_t world,
                                double *ecc_dev, double *sim_dev);
@@ -157,9 +190,11 @@ int ca_consistency_finish_dev(int64_t n, int32_t m, const double *weights_host, 
 /* Stage timings (milliseconds, CUDA events on the library's stream) of the last batched call on this
  * thread: [0] pack (min/max, cluster sizes, compaction)  [1] relabel + transpose to the uint16 label
  * layout  [2] host planning (items)  [3] per-partition counting sort  [4] the wave kernel (tables + ECS)
- * [5] finish  [6] whole call  [7] number of kernel launches of the call.  Returns how many
- * entries were written (<= cap). */
+ * [5] finish  [6] whole call  [7] number of kernel launches of the call  [8] the wave kernel's streaming launch
+ * [9] its resident launch.  Returns how many entries were written (<= cap). */
 int ca_get_profile(double *ms_out, int cap);
+int ca_get_profile_dev(int device_index, double *ms_out, int cap); /* the same for the index-th selected device of a multi-GPU job;
+                                                                   there [0] = packing incl. the label exchange (host clock) */
 
 /* ---- host-only test hook --------------------------------------------------------------------------- */
 

@@ -60,6 +60,9 @@ def _ensure():
         _lib.orc_element_consistency.argtypes = [_I32P, C.c_int64, C.c_int32, _F64P]
         _lib.orc_time_pairs.argtypes = [_I32P, C.c_int64, _I32P, _I32P, C.c_int64, C.c_int32, C.c_void_p]
         _lib.orc_time_pairs.restype = C.c_double
+        _lib.orc_time_pairs_ex.argtypes = [_I32P, C.c_int64, _I32P, _I32P, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int64, C.c_void_p]
+        _lib.orc_time_pairs_ex.restype = C.c_double
         _ref = _load(os.path.join(_HERE, "_ref", "libref_ecs.so"))
         if _ref is not None:
             _ref.ref_myContTable.argtypes = [_I32P, _I32P, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
@@ -69,6 +72,9 @@ def _ensure():
             _ref.ref_disjointECSaverage.restype = C.c_double
             _ref.ref_time_pairs.argtypes = [_I32P, C.c_int64, _I32P, _I32P, C.c_int64, C.c_int32, C.c_void_p]
             _ref.ref_time_pairs.restype = C.c_double
+            _ref.ref_time_pairs_ex.argtypes = [_I32P, C.c_int64, _I32P, _I32P, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_int64, C.c_void_p]
+            _ref.ref_time_pairs_ex.restype = C.c_double
     return _lib
 
 
@@ -192,6 +198,27 @@ def time_pairs(labels, pi, pj, nthreads=1, impl="port"):
             raise RuntimeError("oracle/_ref/libref_ecs.so not built")
         return float(_ref.ref_time_pairs(L, n, pi, pj, pi.size, int(nthreads), None))
     return float(_lib.orc_time_pairs(L, n, pi, pj, pi.size, int(nthreads), None))
+
+
+def pairs_detail(labels, pi, pj, cells=None, nthreads=1, impl="port"):
+    """The per-pair body of the ECC loop (R/ECS.R:1478-1484) over the given pairs, keeping what a parity check needs:
+    returns (seconds, sum over the pairs of ECS -- an N-vector, mean(ECS) per pair, ECS per pair at `cells` or None)."""
+    L = _mat(labels)
+    m, n = L.shape
+    pi, pj = _i32(pi), _i32(pj)
+    _ensure()
+    acc = np.zeros(n, dtype=np.float64)
+    means = np.zeros(pi.size, dtype=np.float64)
+    ci = None if cells is None else np.ascontiguousarray(cells, dtype=np.int64)
+    cv = None if ci is None else np.zeros((pi.size, ci.size), dtype=np.float64)
+    fn = _lib.orc_time_pairs_ex
+    if impl == "reference":
+        if _ref is None:
+            raise RuntimeError("oracle/_ref/libref_ecs.so not built")
+        fn = _ref.ref_time_pairs_ex
+    secs = float(fn(L, n, pi, pj, pi.size, int(nthreads), acc.ctypes.data, means.ctypes.data, None if ci is None else ci.ctypes.data,
+                    0 if ci is None else ci.size, None if cv is None else cv.ctypes.data))
+    return secs, acc, means, cv
 
 
 # ---- the unmodified reference (oracle/_ref/libref_ecs.so) ----------------------------------------

@@ -321,6 +321,10 @@ typedef struct {
     int64_t first, last;
     double *acc;
     double msum;
+    double *means;           /* [npairs] mean(ECS) of every pair (may be NULL) */
+    const int64_t *cell_idx; /* [ncell] cells whose ECS is kept per pair (may be NULL) */
+    int64_t ncell;
+    double *cells;           /* [npairs][ncell] */
 } pair_job_t;
 
 static void *pair_worker(void *arg) {
@@ -328,15 +332,22 @@ static void *pair_worker(void *arg) {
     double *cur = (double *)malloc(sizeof(double) * (size_t)jb->n);
     for (int64_t p = jb->first; p < jb->last; p++) {
         orc_disjoint_ecs(jb->labels + (size_t)jb->pi[p] * jb->n, jb->labels + (size_t)jb->pj[p] * jb->n, jb->n, cur);
-        jb->msum += r_mean(cur, jb->n);
+        const double mean = r_mean(cur, jb->n);
+        jb->msum += mean;
+        if (jb->means) jb->means[p] = mean;
+        if (jb->cells)
+            for (int64_t c = 0; c < jb->ncell; c++) jb->cells[(size_t)p * (size_t)jb->ncell + (size_t)c] = cur[jb->cell_idx[c]];
         for (int64_t k = 0; k < jb->n; k++) jb->acc[k] += cur[k] * 1.0 / 1.0 * 1.0;
     }
     free(cur);
     return NULL;
 }
 
-double orc_time_pairs(const int32_t *labels, int64_t n, const int32_t *pi, const int32_t *pj, int64_t npairs,
-                      int32_t nthreads, double *ecc_out) {
+/* means_out[npairs], cells_out[npairs][ncell] (ECS of every pair at the cells cell_idx[]) may be NULL: they are what
+ * bench.py's parity block and the full-size tests compare the GPU's ECS matrix and per-pair ECS with. */
+double orc_time_pairs_ex(const int32_t *labels, int64_t n, const int32_t *pi, const int32_t *pj, int64_t npairs,
+                         int32_t nthreads, double *ecc_out, double *means_out, const int64_t *cell_idx, int64_t ncell,
+                         double *cells_out) {
     if (nthreads < 1) nthreads = 1;
     pair_job_t *jobs = (pair_job_t *)calloc((size_t)nthreads, sizeof(pair_job_t));
     pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
@@ -348,6 +359,10 @@ double orc_time_pairs(const int32_t *labels, int64_t n, const int32_t *pi, const
         jobs[t].first = npairs * t / nthreads;
         jobs[t].last = npairs * (t + 1) / nthreads;
         jobs[t].acc = (double *)calloc((size_t)n, sizeof(double));
+        jobs[t].means = means_out;
+        jobs[t].cell_idx = cell_idx;
+        jobs[t].ncell = ncell;
+        jobs[t].cells = cell_idx ? cells_out : NULL;
     }
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
@@ -367,4 +382,9 @@ double orc_time_pairs(const int32_t *labels, int64_t n, const int32_t *pi, const
     free(th);
     free(jobs);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+double orc_time_pairs(const int32_t *labels, int64_t n, const int32_t *pi, const int32_t *pj, int64_t npairs,
+                      int32_t nthreads, double *ecc_out) {
+    return orc_time_pairs_ex(labels, n, pi, pj, npairs, nthreads, ecc_out, NULL, NULL, 0, NULL);
 }

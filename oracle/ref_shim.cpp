@@ -50,8 +50,9 @@ double ref_disjointECSaverage(const int32_t* a, const int32_t* b, int64_t n) {
 #include <thread>
 #include <vector>
 
-extern "C" double ref_time_pairs(const int32_t* labels, int64_t n, const int32_t* pi, const int32_t* pj,
-                                 int64_t npairs, int32_t nthreads, double* ecc_out) {
+extern "C" double ref_time_pairs_ex(const int32_t* labels, int64_t n, const int32_t* pi, const int32_t* pj,
+                                    int64_t npairs, int32_t nthreads, double* ecc_out, double* means_out,
+                                    const int64_t* cell_idx, int64_t ncell, double* cells_out) {
     if (nthreads < 1) nthreads = 1;
     std::vector<std::vector<double> > acc(nthreads, std::vector<double>(static_cast<size_t>(n), 0.0));
     std::vector<double> msum(nthreads, 0.0);
@@ -64,7 +65,12 @@ extern "C" double ref_time_pairs(const int32_t* labels, int64_t n, const int32_t
             Rcpp::NumericVector e = disjointECS(va, vb);
             long double s = 0.0L;
             for (int64_t k = 0; k < n; k++) s += e(static_cast<int>(k));
-            msum[t] += static_cast<double>(s / n);
+            const double mean = static_cast<double>(s / n);
+            msum[t] += mean;
+            if (means_out) means_out[p] = mean;  // per-pair mean(ECS): what the GPU's ECS matrix is compared with
+            if (cell_idx && cells_out)
+                for (int64_t c = 0; c < ncell; c++)
+                    cells_out[static_cast<size_t>(p) * static_cast<size_t>(ncell) + static_cast<size_t>(c)] = e(static_cast<int>(cell_idx[c]));
             double* ac = acc[t].data();
             for (int64_t k = 0; k < n; k++) ac[k] += e(static_cast<int>(k)) * 1.0 / 1.0 * 1.0;
         }
@@ -86,4 +92,9 @@ extern "C" double ref_time_pairs(const int32_t* labels, int64_t n, const int32_t
         }
     }
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+extern "C" double ref_time_pairs(const int32_t* labels, int64_t n, const int32_t* pi, const int32_t* pj,
+                                 int64_t npairs, int32_t nthreads, double* ecc_out) {
+    return ref_time_pairs_ex(labels, n, pi, pj, npairs, nthreads, ecc_out, nullptr, nullptr, 0, nullptr);
 }

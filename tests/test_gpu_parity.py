@@ -273,22 +273,43 @@ def test_many_clusters_one_block_per_sm_configuration():
     assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
 
 
-def test_cluster_counts_up_to_the_table_row_limit():
+def test_cluster_counts_up_to_the_table_row_limit_and_beyond():
     """A partner with 24 000 clusters needs 96 KB per table row: one row per item, one partner per phase.  One with
-    30 000 does not fit a table buffer at all: the batched engine refuses it (CA_E_UNSUPPORTED), it never truncates."""
+    30 000 does not fit a table buffer at all, one with 70 000 not even the uint16 labels: the reference has no such limit
+    (src/calculate_ecs.cpp:7-19), so the library loops over the pairs with a hashed contingency table instead -- same
+    results, same entry points."""
     rng = np.random.default_rng(29)
     n = 120_000
     L = np.stack([rng.integers(0, 24_000, size=n), rng.integers(0, 7, size=n), rng.integers(0, 300, size=n)]).astype(np.int32)
     ecc, sim = oracle.weighted_element_consistency(L, calculate_sim_matrix=True)
     res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
     assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
-    L[0] = rng.integers(0, 30_000, size=n)
-    L[0][:30_000] = np.arange(30_000)
-    with pytest.raises(_capi.ClustAssessError) as e:
-        ecs.weighted_element_consistency(list(L))
-    assert e.value.code == -6  # CA_E_UNSUPPORTED
-    # the per-pair entry points have no such limit
+    for k_big in (30_000, 70_000):
+        L[0] = rng.integers(0, k_big, size=n)
+        L[0][:k_big] = np.arange(k_big)
+        w = np.array([2.0, 1.0, 3.0])
+        ecc, sim = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+        res = ecs.weighted_element_consistency(list(L), weights=w, calculate_sim_matrix=True)
+        assert np.abs(res["ecc"] - ecc).max() < TOL and np.abs(res["ecs_matrix"] - sim).max() < TOL
+        assert np.abs(ecs.element_sim_matrix(list(L)) - oracle.element_sim_matrix(L)).max() < TOL
+        got = ecs.element_agreement(L[0], [L[1], L[2]])
+        want = (oracle.disjoint_ecs(L[0], L[1]) + oracle.disjoint_ecs(L[0], L[2])) / 2
+        assert np.abs(got - want).max() < TOL
+    # the per-pair entry points never had the limit
     assert np.array_equal(ecs.element_sim_elscore(L[0], L[2]), oracle.disjoint_ecs(L[0], L[2]))
+
+
+def test_all_singleton_partitions_pass_the_dedup_pre_pass():
+    """Partitions of n > 65535 singletons: are_identical_memberships returns TRUE through its nrow == length(mb) shortcut
+    (R/ECS.R:999), so element_consistency merges them -- the pre-pass only needs ranks, whatever the cluster count."""
+    n = 70_000
+    rng = np.random.default_rng(31)
+    a, b = np.arange(n, dtype=np.int32), rng.permutation(n).astype(np.int32)
+    L = np.stack([a, b, a])
+    assert np.array_equal(ecs.element_consistency(list(L)), np.ones(n))
+    c = rng.integers(0, 50, size=n).astype(np.int32)
+    L = np.stack([a, c, b])
+    assert np.abs(ecs.element_consistency(list(L)) - oracle.element_consistency(L)).max() < TOL
 
 
 def test_identical_partitions_and_m_not_multiple_of_tile():
@@ -310,8 +331,8 @@ def test_errors_through_the_c_abi():
     b = np.array([1, 2, 3], dtype=np.int32)
     tab = np.zeros(4, dtype=np.int32)
     assert lib.ca_contingency(b, b, 3, 1, 1, 2, 2, tab, None, None) == -5  # CA_E_RANGE: label 3 outside [1, 3)
-    with pytest.raises(_capi.ClustAssessError):
-        ecs.weighted_element_consistency([np.arange(70_000), np.arange(70_000)])  # > 65535 clusters
+    res = ecs.weighted_element_consistency([np.arange(70_000), np.arange(70_000)])  # > 65535 clusters: the pair-loop fallback
+    assert np.array_equal(res, np.ones(70_000))
 
 
 def test_rank_sharding_sums_to_the_whole():
