@@ -187,6 +187,7 @@ struct Dev {
     WorkerPool pool;
     ncclComm_t comm = nullptr;
     DevBuf red_ecc, red_sim;  // multi-GPU jobs: this device's partial sums
+    cudaEvent_t ev_lab = nullptr;  // multi-GPU jobs: this device's transposition (with its stores into the peers' memory) has finished
 };
 std::vector<std::unique_ptr<Dev>>& devs() {
     static std::vector<std::unique_ptr<Dev>> d;
@@ -345,6 +346,7 @@ static int init_device(Dev& D, int device) {
     c.stream = c.own_stream;
     for (int i = 0; i < 10; i++)
         if (!c.ev[i]) CA_CUDA(cudaEventCreate(&c.ev[i]));
+    if (!D.ev_lab) CA_CUDA(cudaEventCreateWithFlags(&D.ev_lab, cudaEventDisableTiming));
     c.inited = true;
     return CA_OK;
 }
@@ -364,6 +366,7 @@ static void release_device(Dev& D) {
     D.comm = nullptr;
     for (int i = 0; i < 10; i++)
         if (D.c.ev[i]) { cudaEventDestroy(D.c.ev[i]); D.c.ev[i] = nullptr; }
+    if (D.ev_lab) { cudaEventDestroy(D.ev_lab); D.ev_lab = nullptr; }
     if (D.c.own_stream) { cudaStreamDestroy(D.c.own_stream); D.c.own_stream = nullptr; }
     D.c.stream = nullptr;
     D.c.inited = false;
@@ -709,7 +712,8 @@ static int read_profile(Ctx& c);
 static int run_pairs_fallback(Labels& L, const double* weights_host, int32_t rank, int32_t world, double* d_ecc, double* d_sim, int32_t ref_only,
                               int32_t m_partners);
 static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int32_t world, double* d_ecc, double* d_sim,
-                        int32_t ref_only, int32_t m_partners, int plan_threads = 0, bool finish_sync = true) {
+                        int32_t ref_only, int32_t m_partners, int plan_threads = 0, bool finish_sync = true,
+                        const std::function<int()>* before_wave = nullptr) {
     Ctx& c = ctx();
     cudaStream_t s = c.stream;
     const int32_t m = L.mg();  // partitions of the whole set: the partner axis
@@ -1016,13 +1020,15 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
 #endif
     for (int32_t p = 0; p < mw; p++)
         if (h_w[p] != 1.0) T.unit_w = 0;
-    if (!qinfo_done) {
+    if (!qinfo_done && nparts > 0) {
         if (L.m_glob) {
             set_error("CA_SORT_LEGACY is not available for sharded label sets");
             return CA_E_UNSUPPORTED;
         }
         CA_TRY(launch_qinfo(T, W.parts.as<int32_t>(), nparts, s));
     }
+    if (before_wave) CA_TRY((*before_wave)());  // multi-GPU jobs: the stream waits here for the peers' label stores (planning and sort ran meanwhile)
+    CA_CUDA(cudaEventRecord(c.ev[4], s));
     for (int kind = 1; kind >= 0; kind--) {  // the long streaming items first
         T.items = W.items.as<Item>() + (kind == 1 ? n_kind[0] : 0);
         T.wu_prefix = W.wu_prefix.as<int32_t>() + (kind == 1 ? npre0 : 0);
@@ -1191,7 +1197,6 @@ static int for_each_device(const std::function<int(int)>& fn) {
     th.reserve(G);
     auto body = [&](int g) {
         DevScope scope(devs()[g].get());
-        g_err[0] = 0;
         rcs[g] = fn(g);
         if (rcs[g] != CA_OK) msgs[g] = g_err;
     };
@@ -1276,14 +1281,18 @@ static int multi_allpairs(ca_labels* H, const double* weights, double* ecc_out, 
                         fail(launch_relabel_transpose(L.d_raw, n, L.m, (int32_t)L.spans.size(), L.d_span.as<int32_t>(), L.d_min.as<int32_t>(),
                                                       L.identity ? nullptr : L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(), L.d_kcount.as<int32_t>(), dst, s));
                     if (e == cudaSuccess) e = cudaEventRecord(c.ev[2], s);
-                    if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the stores into the peers' memory have landed
                     if (e != cudaSuccess) {
                         set_error("relabel/transpose into peer memory failed: %s", cudaGetErrorString(e));
                         fail(CA_E_CUDA);
                     }
                 }
+                // no host synchronisation: the event below is what the peers' streams wait for before their wave kernels
+                if (cudaEventRecord(D.ev_lab, s) != cudaSuccess) {
+                    set_error("cudaEventRecord failed");
+                    fail(CA_E_CUDA);
+                }
             }
-            bar.wait();  // every device's label array is complete, all sizes are on the host
+            bar.wait();  // all sizes are on the host, every device has recorded its label event
             // ---- C ----
             if (failed.load() == CA_OK) {
                 fail(L.d_sizes_g.ensure((size_t)m * L.kp * 4));
@@ -1312,9 +1321,17 @@ static int multi_allpairs(ca_labels* H, const double* weights, double* ecc_out, 
                 set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e));
                 fail(CA_E_CUDA);
             }
+            // the wave kernel reads every device's labels: its stream waits for all the label events (recorded above, or already
+            // complete when the set was prepared by an earlier call); items and sort do not, they run while the stores are in flight
+            const std::function<int()> wait_labels = [&]() -> int {
+                if (!need_prepare) return CA_OK;
+                for (int q = 0; q < G; q++)
+                    if (q != g) CA_CUDA(cudaStreamWaitEvent(s, devs()[q]->ev_lab, 0));
+                return CA_OK;
+            };
             if (my == CA_OK && L.m > 0 && n > 0)
                 fail(run_allpairs(L, weights, 0, 1, ecc_out ? D.red_ecc.as<double>() : nullptr, sim_out ? D.red_sim.as<double>() : nullptr, -1, 0,
-                                  plan_threads, /*finish_sync=*/false));
+                                  plan_threads, /*finish_sync=*/false, &wait_labels));
         }
         bar.wait();  // nobody enters the collective unless everybody will
         if (failed.load() != CA_OK) return my;

@@ -178,8 +178,8 @@ static_assert(TL_WU_SPAN == 16 || TL_WU_SPAN == 32, "a work unit spans one or tw
 // Per-cell sums and per-pair sums are accumulated as 64-bit FIXED-POINT integers: integer addition is associative, so
 // the results are bit-identical from run to run (and across any sharding over GPUs) although the adds are atomics issued
 // in arbitrary order.  ecc: units of 2^-61 of the normalised sum (<= 1); a work unit's sum is rounded once, error
-// <= 2^-62 per add, far below the 1e-9 bound.  sim: units of 2^-F, F = 61 - ceil(log2(n + 1)), of sum_n ECS <= n; every
-// TERM is rounded to that grid before it is added (error <= 2^-(F+1) per cell, so <= 2^-(F+1) in the mean: 2.3e-13 at n = 1M).
+// <= 2^-62 per add, far below the 1e-9 bound.  sim: units of 2^-F, F = min(40, 61 - ceil(log2(n + 1))), of sum_n ECS <= n; every
+// TERM is rounded to that grid before it is added (error <= 2^-(F+1) per cell, so <= 2^-(F+1) in the mean: 4.5e-13 up to 2M cells).
 constexpr double ECC_FIX_SCALE = 2305843009213693952.0;  // 2^61
 struct TileParams {
     const uint16_t* lab16;    // [mpad/16][n + 1][16] compact labels (cell n = the pad cell), see lab16_index()
@@ -232,7 +232,7 @@ struct PeerSrc {  // the peers' partial-sum buffers, read through peer memory
     int n;
 };
 int launch_peer_sum(unsigned long long* dst, const PeerSrc& src, int64_t n, cudaStream_t s);
-double sim_fix_scale(int64_t n);  // 2^F, F = 61 - ceil(log2(n + 1))
+double sim_fix_scale(int64_t n);  // 2^F, F = min(40, 61 - ceil(log2(n + 1)))
 double sim_fix_magic(int64_t n);  // 1.5 * 2^(52 - F)
 
 // ca_dedup.cu

@@ -1072,10 +1072,10 @@ int launch_tile(const TileParams& p, cudaStream_t s) {
     return CA_OK;
 }
 
-double sim_fix_scale(int64_t n) {  // 2^F, F = 61 - ceil(log2(n + 1)): n terms of at most 1 stay below 2^62
-    int bits = 0;
+double sim_fix_scale(int64_t n) {  // 2^F, F = min(40, 61 - ceil(log2(n + 1))): n terms of at most 1 stay below 2^62, and v + 1.5 * 2^(52 - F)
+    int bits = 0;                  // keeps its binade for every v in [0, 1]
     while (((int64_t)1 << bits) < n + 1) bits++;
-    return ldexp(1.0, 61 - bits);
+    return ldexp(1.0, std::min(40, 61 - bits));
 }
 double sim_fix_magic(int64_t n) { return 1.5 * 4503599627370496.0 / sim_fix_scale(n); }  // 1.5 * 2^(52 - F)
 

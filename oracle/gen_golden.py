@@ -10,6 +10,9 @@ myContTable / disjointECS / disjointECSaverage (src/calculate_ecs.cpp:7-70).  Se
 the R loop order of R/ECS.R:1466-1499 and R/ECS.R:942-965 -- an independent statement from the C
 restatement in ecs_oracle.c, so the two pin each other.  The one deterministic known answer the
 reference documents (docs/reference/merge_partitions.html:117-142) is stored verbatim.
+tests/golden/merge_golden.json holds merge_partitions results for ecs_thresh in {0.99, 0.9, 0.5, 1, 0.2} with every
+order_logic, full and partial frequency ties: oracle/merge_oracle.py (R/ECS.R:1057-1135, 1166-1311 restated in R's own
+terms) on top of the reference build's per-pair ECS.
 """
 import os
 import sys
@@ -54,6 +57,54 @@ def wec_from_ref(labels, weights):
     return cons, sim
 
 
+def merge_cases(rng):
+    """Inputs for merge_partitions with ecs_thresh < 1 and for the ordering / tie logic (R/ECS.R:1057-1135, 1224-1311):
+    a base partition and noisy relatives at graded distances, so that the pairwise ECS straddles the thresholds; frequencies
+    with full and partial ties."""
+    n = 240
+    base = rng.integers(1, 7, size=n)
+
+    def noisy(frac, k=6):
+        x = base.copy()
+        hit = rng.random(n) < frac
+        x[hit] = rng.integers(1, k + 1, size=int(hit.sum()))
+        return x
+
+    fam = [base, noisy(0.004), noisy(0.02), noisy(0.05), noisy(0.12), noisy(0.3), noisy(0.6), rng.integers(1, 5, size=n),
+           (base % 6) * 2 + 3, noisy(0.02, 9)]
+    cases = []
+    for thresh in (0.99, 0.9, 0.5):
+        for order_logic in ("freq", "avg_agreement", "none"):
+            cases.append(dict(labels=fam, freq=[1] * len(fam), ecs_thresh=thresh, order_logic=order_logic, check_ties=True))
+    cases.append(dict(labels=fam, freq=[3, 1, 3, 2, 1, 3, 2, 1, 1, 2], ecs_thresh=0.9, order_logic="freq", check_ties=True))
+    cases.append(dict(labels=fam, freq=[3, 1, 3, 2, 1, 3, 2, 1, 1, 2], ecs_thresh=0.9, order_logic="freq", check_ties=False))
+    cases.append(dict(labels=fam[:6], freq=[2, 2, 5, 5, 5, 1], ecs_thresh=1, order_logic="freq", check_ties=True))
+    cases.append(dict(labels=fam[:6], freq=[2, 2, 5, 5, 5, 1], ecs_thresh=1, order_logic="avg_agreement", check_ties=True))
+    cases.append(dict(labels=[fam[0], fam[8], fam[3]], freq=[1, 4, 2], ecs_thresh=1, order_logic="freq", check_ties=True))  # identical pair merges
+    cases.append(dict(labels=fam[:4], freq=[1, 1, 1, 1], ecs_thresh=0.2, order_logic="freq", check_ties=True))  # everything merges
+    return cases
+
+
+def write_merge_golden(rng, dst):
+    import json
+
+    from oracle import merge_oracle
+
+    out = []
+    for c in merge_cases(rng):
+        plist = [{"mb": np.asarray(x, dtype=np.int32), "freq": f} for x, f in zip(c["labels"], c["freq"])]
+        res = merge_oracle.merge_partitions(plist, c["ecs_thresh"], c["order_logic"], return_ecs_matrix=True, check_ties=c["check_ties"],
+                                            use_ref=True)  # per-pair ECS from the unmodified reference build
+        rec = dict(labels=[np.asarray(x).tolist() for x in c["labels"]], freq=list(c["freq"]), ecs_thresh=c["ecs_thresh"],
+                   order_logic=c["order_logic"], check_ties=c["check_ties"],
+                   ids=[int(p["id"]) for p in res["partitions"]], out_freq=[float(p["freq"]) for p in res["partitions"]],
+                   avg_agreement=[float(p["avg_agreement"]) for p in res["partitions"]] if "avg_agreement" in res["partitions"][0] else None,
+                   ecc=np.asarray(res["ecc"]).tolist(), ecs_matrix=np.asarray(res["ecs_matrix"]).tolist() if "ecs_matrix" in res else None)
+        out.append(rec)
+    json.dump(out, open(dst, "w"))
+    print("wrote", dst, os.path.getsize(dst), "bytes,", len(out), "cases; partitions kept per case:", [len(r["ids"]) for r in out])
+
+
 def main():
     if not oracle.have_ref():
         raise SystemExit("oracle/_ref/libref_ecs.so missing: run `make -C oracle` where /root/reference exists")
@@ -82,6 +133,8 @@ def main():
     dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ecs_golden.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, os.path.getsize(dst), "bytes")
+    # merge_partitions below the identity threshold, ordering and ties: its own random stream, so the file above does not change
+    write_merge_golden(np.random.Generator(np.random.PCG64(20261020)), os.path.join(os.path.dirname(dst), "merge_golden.json"))
 
 
 if __name__ == "__main__":

@@ -112,6 +112,7 @@ List ecsMergeIdentical(List mb_list, NumericVector freq) {
     std::vector<IntegerVector> keep;
     R_xlen_t n;
     std::vector<const int32_t *> cols = column_pointers(mb_list, keep, n);
+    if (freq.size() != m) stop("freq must have one entry per clustering");
     IntegerVector kept(m);
     NumericVector fout(m);
     int u = 0;
@@ -128,8 +129,9 @@ List ecsMergeIdentical(List mb_list, NumericVector freq) {
 // ---- pipeline glue: the runs of one configuration stay on the device -------------
 // R/stability-3-graph-clustering.R compares the same membership vectors per k (:271-300), per resolution (:25-69)
 // and per k across resolutions (:303-343).  ecsResident(mb_list) uploads them once and returns an external pointer;
-// ecsResidentConsistency(ptr, idx, weights, calculate_sim_matrix, n_cells) / ecsResidentSimMatrix(ptr, idx) run a
-// comparison of the partitions idx (1-based).  The finalizer releases the device memory with the R object.
+// ecsResidentConsistency(ptr, idx, weights, calculate_sim_matrix) / ecsResidentSimMatrix(ptr, idx) run a comparison of
+// the partitions idx (1-based); the length of the result comes from the label set itself (ca_labels_shape), never from
+// the caller.  The finalizer releases the device memory with the R object.
 static void resident_finalizer(ca_labels_t *h) { ca_labels_destroy(h); }
 typedef XPtr<ca_labels_t, PreserveStorage, resident_finalizer, true> ResidentPtr;
 
@@ -151,12 +153,18 @@ SEXP ecsResident(List mb_list) {
 }
 
 // [[Rcpp::export]]
-List ecsResidentConsistency(SEXP resident, IntegerVector idx, Nullable<NumericVector> weights, bool calculate_sim_matrix, int n_cells) {
+List ecsResidentConsistency(SEXP resident, IntegerVector idx, Nullable<NumericVector> weights, bool calculate_sim_matrix) {
     ResidentPtr h(resident);
     const int k = idx.size();
     if (k <= 1) stop("At least two clusterings are required to calculate the consistency.");
+    int64_t n_cells = 0;
+    int32_t m_set = 0;
+    ca_check(ca_labels_shape(h.get(), &n_cells, &m_set));
     std::vector<int32_t> ix(idx.begin(), idx.end());
-    for (size_t t = 0; t < ix.size(); t++) ix[t] -= 1;  // R indices are 1-based
+    for (size_t t = 0; t < ix.size(); t++) {
+        if (ix[t] < 1 || ix[t] > m_set) stop("index %d outside the resident label set (1..%d)", ix[t], (int)m_set);
+        ix[t] -= 1;  // R indices are 1-based
+    }
     const double *w = NULL;
     NumericVector wv;
     if (weights.isNotNull()) {
@@ -173,8 +181,14 @@ List ecsResidentConsistency(SEXP resident, IntegerVector idx, Nullable<NumericVe
 // [[Rcpp::export]]
 NumericMatrix ecsResidentSimMatrix(SEXP resident, IntegerVector idx) {
     ResidentPtr h(resident);
+    int64_t n_cells = 0;
+    int32_t m_set = 0;
+    ca_check(ca_labels_shape(h.get(), &n_cells, &m_set));
     std::vector<int32_t> ix(idx.begin(), idx.end());
-    for (size_t t = 0; t < ix.size(); t++) ix[t] -= 1;
+    for (size_t t = 0; t < ix.size(); t++) {
+        if (ix[t] < 1 || ix[t] > m_set) stop("index %d outside the resident label set (1..%d)", ix[t], (int)m_set);
+        ix[t] -= 1;
+    }
     NumericMatrix sim(ix.size(), ix.size());
     ca_check(ca_sim_matrix_resident(h.get(), ix.data(), (int)ix.size(), sim.begin()));
     return sim;

@@ -25,6 +25,7 @@ typedef unsigned int SEXPTYPE;
 #define REALSXP 14
 #define STRSXP 16
 #define VECSXP 19
+#define EXTPTRSXP 22
 
 #ifndef TRUE
 #define TRUE 1
@@ -55,6 +56,14 @@ int Rf_asLogical(SEXP x);
 int Rf_isNull(SEXP x);
 SEXP Rf_setAttrib(SEXP x, SEXP name, SEXP value);
 SEXP Rf_getAttrib(SEXP x, SEXP name);
+/* external pointers (the resident label sets): address, tag / protected slots are not modelled; the finalizer runs when the
+ * harness "collects" the object (mr_reset or mr_finalize), once, and not at all after R_ClearExternalPtr */
+typedef void (*R_CFinalizer_t)(SEXP);
+typedef int Rboolean;
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot);
+void *R_ExternalPtrAddr(SEXP s);
+void R_ClearExternalPtr(SEXP s);
+void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit);
 SEXP Rf_protect(SEXP x);
 void Rf_unprotect(int n);
 #define PROTECT(x) Rf_protect(x)

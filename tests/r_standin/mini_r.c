@@ -20,11 +20,12 @@ struct SEXPREC {
     void *data; /* int* (INTSXP, LGLSXP), double* (REALSXP), SEXP* (VECSXP, STRSXP), char* (CHARSXP) */
     SEXP names, dim, klass;
     struct SEXPREC *next;
+    R_CFinalizer_t fin; /* EXTPTRSXP: C finalizer, run once when the object is collected */
 };
 
-static struct SEXPREC nil_obj = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL};
-static struct SEXPREC names_sym = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL};
-static struct SEXPREC dim_sym = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL};
+static struct SEXPREC nil_obj = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL, NULL};
+static struct SEXPREC names_sym = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL, NULL};
+static struct SEXPREC dim_sym = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL, NULL};
 SEXP R_NilValue = &nil_obj, R_NamesSymbol = &names_sym, R_DimSymbol = &dim_sym;
 double R_NaReal;
 
@@ -52,7 +53,7 @@ static void init_once(void) {
 static SEXP new_obj(int type, R_xlen_t n) {
     init_once();
     SEXP x = (SEXP)calloc(1, sizeof(struct SEXPREC));
-    size_t elt = type == REALSXP ? sizeof(double) : (type == VECSXP || type == STRSXP) ? sizeof(SEXP) : type == CHARSXP ? 1 : sizeof(int);
+    size_t elt = type == REALSXP ? sizeof(double) : (type == VECSXP || type == STRSXP || type == EXTPTRSXP) ? sizeof(SEXP) : type == CHARSXP ? 1 : sizeof(int);
     x->type = type;
     x->len = n;
     x->data = calloc((size_t)(n > 0 ? n : 1) + (type == CHARSXP), elt);
@@ -153,6 +154,24 @@ int Rf_asLogical(SEXP x) {
     return NA_LOGICAL;
 }
 int Rf_isNull(SEXP x) { return x->type == NILSXP; }
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot) {
+    (void)tag;
+    (void)prot;
+    SEXP x = new_obj(EXTPTRSXP, 1);
+    ((void **)x->data)[0] = p;
+    return x;
+}
+void *R_ExternalPtrAddr(SEXP s) {
+    if (s->type != EXTPTRSXP) Rf_error("R_ExternalPtrAddr: argument of type %d is not an external pointer", s->type);
+    return ((void **)s->data)[0];
+}
+void R_ClearExternalPtr(SEXP s) {
+    if (s->type == EXTPTRSXP) ((void **)s->data)[0] = NULL;
+}
+void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit) {
+    (void)onexit;
+    s->fin = fun;
+}
 SEXP Rf_setAttrib(SEXP x, SEXP name, SEXP value) {
     if (name == R_NamesSymbol) x->names = value;
     else if (name == R_DimSymbol) x->dim = value;
@@ -187,7 +206,21 @@ void Rf_error(const char *fmt, ...) {
 }
 
 /* ---- harness (bound from Python with ctypes) ------------------------------------------------------------------ */
+/* "garbage collection" of one external pointer: runs its finalizer (once) */
+static int finalizers_run = 0;
+void mr_finalize(SEXP x) {
+    if (x->type == EXTPTRSXP && x->fin) {
+        R_CFinalizer_t f = x->fin;
+        x->fin = NULL;
+        in_call = 1; /* a finalizer may not raise, but keep Rf_error from aborting the test process */
+        if (setjmp(call_jb) == 0) f(x);
+        in_call = 0;
+        finalizers_run++;
+    }
+}
+int mr_finalizers_run(void) { return finalizers_run; }
 void mr_reset(void) {
+    for (SEXP x = arena; x; x = x->next) mr_finalize(x);
     while (arena) {
         SEXP n = arena->next;
         free(arena->data);

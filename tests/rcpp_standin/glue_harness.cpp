@@ -85,9 +85,9 @@ int gh_agreement(const int* ref, R_xlen_t nref, const int* const* cols, const R_
         std::memcpy(out, r.begin(), sizeof(double) * (size_t)r.size());
     });
 }
-int gh_merge_identical(const int* const* cols, const R_xlen_t* lens, int m, const double* freq, int* keep, double* fout, int* u) {
+int gh_merge_identical(const int* const* cols, const R_xlen_t* lens, int m, const double* freq, int nfreq, int* keep, double* fout, int* u) {
     return guarded([&] {
-        List res = ecsMergeIdentical(make_list(cols, lens, m, 0), NumericVector(freq, freq + m));
+        List res = ecsMergeIdentical(make_list(cols, lens, m, 0), NumericVector(freq, freq + nfreq));
         IntegerVector k = as<IntegerVector>(res.get("keep"));
         NumericVector f = as<NumericVector>(res.get("freq"));
         *u = (int)k.size();
@@ -104,7 +104,7 @@ int gh_resident(const int* const* cols, const R_xlen_t* lens, int m, const int* 
         SEXP handle = ecsResident(make_list(cols, lens, m, 0));
         Nullable<NumericVector> weights;
         if (w) weights = Nullable<NumericVector>(wrap(NumericVector(w, w + k)));
-        List res = ecsResidentConsistency(handle, IntegerVector(idx1, idx1 + k), weights, want_matrix != 0, (int)lens[0]);
+        List res = ecsResidentConsistency(handle, IntegerVector(idx1, idx1 + k), weights, want_matrix != 0);
         NumericVector e = as<NumericVector>(res.get("ecc"));
         std::memcpy(ecc, e.begin(), sizeof(double) * (size_t)e.size());
         if (want_matrix) std::memcpy(sim, res.get("ecs_matrix")->dm->begin(), sizeof(double) * (size_t)k * k);

@@ -540,3 +540,27 @@ def test_staged_upload_of_pageable_buffers(n, monkeypatch):
         for j in range(i + 1, 5):
             acc += oracle.disjoint_ecs(L[i], L[j])[idx]
     assert np.abs(np.asarray(staged_cols["ecc"])[idx] - acc / 10.0).max() < TOL
+
+
+# ---- merge_partitions against the oracle's golden fixtures ---------------------------------------
+def test_merge_partitions_thresholds_ordering_and_ties_match_the_golden_fixtures():
+    """ecs_thresh in {0.99, 0.9, 0.5, 1, 0.2}, every order_logic, full and partial frequency ties: partitions kept, their
+    order, summed frequencies, avg_agreement, ecc and the (tie-permuted) ECS matrix against tests/golden/merge_golden.json
+    (oracle/merge_oracle.py on the reference build's per-pair ECS; R/ECS.R:1057-1135, 1224-1311)."""
+    import json
+    import os
+
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "merge_golden.json")))
+    assert len(cases) >= 15
+    for c in cases:
+        inputs = [np.asarray(x, dtype=np.int32) for x in c["labels"]]
+        plist = [{"mb": x, "freq": f} for x, f in zip(inputs, c["freq"])]
+        res = ecs.merge_partitions(plist, c["ecs_thresh"], c["order_logic"], return_ecs_matrix=True, check_ties=c["check_ties"])
+        ids = [next(k for k, x in enumerate(inputs) if x is p["mb"]) for p in res["partitions"]]
+        assert ids == c["ids"], (c["ecs_thresh"], c["order_logic"])
+        assert [float(p["freq"]) for p in res["partitions"]] == c["out_freq"]
+        assert np.abs(np.asarray(res["ecc"]) - np.asarray(c["ecc"])).max() < TOL
+        if c["ecs_matrix"] is not None:
+            assert np.abs(res["ecs_matrix"] - np.asarray(c["ecs_matrix"])).max() < TOL
+        if c["avg_agreement"] is not None:
+            assert np.abs(np.asarray([p["avg_agreement"] for p in res["partitions"]]) - np.asarray(c["avg_agreement"])).max() < TOL

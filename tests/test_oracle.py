@@ -107,3 +107,43 @@ def test_generators_are_seeded_and_distinct():
     assert w3.shape == (6,) and np.all(w3 >= 1) and np.all(w3 == np.round(w3))
     a, b = synth.config("C2")[0]
     assert len(np.unique(a)) == 20 and len(np.unique(b)) == 35
+
+
+# ---- merge_partitions below the identity threshold, ordering and ties ---------------------------
+def _merge_golden():
+    import json
+    import os
+
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "merge_golden.json")))
+
+
+def test_merge_oracle_reproduces_the_golden_fixtures_with_the_c_port():
+    """tests/golden/merge_golden.json was generated with the reference build's per-pair ECS (oracle/gen_golden.py); the same
+    restatement of R/ECS.R:1057-1135, 1166-1311 on top of the plain-C port must give the same partitions, order and numbers."""
+    from oracle import merge_oracle
+
+    for c in _merge_golden():
+        plist = [{"mb": np.asarray(x, dtype=np.int32), "freq": f} for x, f in zip(c["labels"], c["freq"])]
+        res = merge_oracle.merge_partitions(plist, c["ecs_thresh"], c["order_logic"], return_ecs_matrix=True, check_ties=c["check_ties"])
+        assert [p["id"] for p in res["partitions"]] == c["ids"]
+        assert [float(p["freq"]) for p in res["partitions"]] == c["out_freq"]
+        assert np.abs(np.asarray(res["ecc"]) - np.asarray(c["ecc"])).max() < 1e-12
+        if c["ecs_matrix"] is not None:
+            assert np.abs(res["ecs_matrix"] - np.asarray(c["ecs_matrix"])).max() < 1e-12
+        if c["avg_agreement"] is not None:
+            assert np.abs(np.asarray([p["avg_agreement"] for p in res["partitions"]]) - np.asarray(c["avg_agreement"])).max() < 1e-12
+
+
+def test_merge_oracle_documented_known_answer_and_invariants():
+    """docs/reference/merge_partitions.html:117-142: partitions (1,1,2) freq 2 and (2,2,2) freq 1, ecc 7/9 7/9 5/9,
+    avg_agreement 0.2777778 for the second; merging conserves the total frequency at every threshold."""
+    from oracle import merge_oracle
+
+    res = merge_oracle.merge_partitions([np.array([1, 1, 2]), np.array([2, 2, 2]), np.array([2, 2, 1])], 1, "freq")
+    assert [p["freq"] for p in res["partitions"]] == [2.0, 1.0]
+    assert np.allclose(res["ecc"], [7 / 9, 7 / 9, 5 / 9], atol=1e-12)
+    assert abs(res["partitions"][1]["avg_agreement"] - 0.2777778) < 1e-7
+    for c in _merge_golden():
+        assert sum(c["out_freq"]) == sum(c["freq"])
+        kept = [len(x["ids"]) for x in _merge_golden() if x["labels"] == c["labels"] and x["freq"] == c["freq"] and x["order_logic"] == c["order_logic"]]
+        assert kept == sorted(kept, reverse=True) or len(kept) == 1  # a lower threshold never keeps more partitions

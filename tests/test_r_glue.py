@@ -41,7 +41,7 @@ class Glue:
             ("gh_cont_table", I, [P, P, X, I, I, P, I, P, P]),
             ("gh_disjoint_ecs", I, [P, X, P, X, P]), ("gh_disjoint_ecs_average", I, [P, X, P, X, P]),
             ("gh_consistency", I, [P, P, I, I, P, I, I, P, P]), ("gh_sim_matrix", I, [P, P, I, I, P]),
-            ("gh_agreement", I, [P, X, P, P, I, P]), ("gh_merge_identical", I, [P, P, I, P, P, P, P]),
+            ("gh_agreement", I, [P, X, P, P, I, P]), ("gh_merge_identical", I, [P, P, I, P, I, P, P, P]),
             ("gh_resident", I, [P, P, I, P, I, P, I, P, P, P]),
         ]:
             f = getattr(self.L, name)
@@ -104,7 +104,7 @@ class Glue:
         arrs, ptrs, lens = self._cols(cols)
         f = np.ascontiguousarray(freq, dtype=np.float64)
         keep, fout, u = np.zeros(len(arrs), np.int32), np.zeros(len(arrs)), C.c_int()
-        self._check(self.L.gh_merge_identical(ptrs, lens, len(arrs), f.ctypes.data, keep.ctypes.data, fout.ctypes.data, C.byref(u)))
+        self._check(self.L.gh_merge_identical(ptrs, lens, len(arrs), f.ctypes.data, f.size, keep.ctypes.data, fout.ctypes.data, C.byref(u)))
         return keep[: u.value], fout[: u.value]
 
     def resident(self, cols, idx, weights=None):
@@ -166,6 +166,8 @@ def test_glue_argument_errors(glue):
         glue.consistency([[1, 2, 3], [1, 2, 2]], weights=[1.0])
     with pytest.raises(RuntimeError, match="The partitions do not have the same length"):
         glue.agreement([1, 2], [[1, 2, 3], [1, 2, 2]])
+    with pytest.raises(RuntimeError, match="freq must have one entry per clustering"):  # a short freq would be read out of bounds
+        glue.merge_identical([[1, 2, 3], [1, 2, 2]], [1.0])
     glue.release()
 
 
@@ -211,4 +213,9 @@ def test_glue_batched_routines(glue):
     ecc_r, sim_r, sim_only = glue.resident(cols, idx, weights=w[[1, 3, 4, 6]])
     ecc_s, sim_s = oracle.weighted_element_consistency(sub, w[[1, 3, 4, 6]], calculate_sim_matrix=True)
     assert np.abs(ecc_r - ecc_s).max() < TOL and np.abs(sim_r - sim_s).max() < TOL and np.abs(sim_only - sim_s).max() < TOL
+    assert ecc_r.size == L.shape[1]  # sized from the label set (ca_labels_shape), not from a caller-supplied length
+    with pytest.raises(RuntimeError, match="outside the resident label set"):
+        glue.resident(cols, [2, 9])
+    with pytest.raises(RuntimeError, match="weights must have one entry per clustering"):
+        glue.resident(cols, [1, 2, 3], weights=[1.0, 2.0])
     glue.release()

@@ -48,7 +48,7 @@ class MiniR:
             ("mr_list_set", None, [P, C.c_ssize_t, P]), ("mr_call", P, [P, C.c_int, P, P, P, P]), ("mr_error", C.c_char_p, []),
             ("mr_protect_depth", C.c_int, []), ("mr_protect_underflow", C.c_int, []), ("mr_type", C.c_int, [P]),
             ("mr_len", C.c_ssize_t, [P]), ("mr_data", P, [P]), ("mr_elt", P, [P, C.c_ssize_t]), ("mr_name", C.c_char_p, [P, C.c_ssize_t]),
-            ("mr_dim", C.c_int, [P, C.c_int]),
+            ("mr_dim", C.c_int, [P, C.c_int]), ("mr_finalize", None, [P]), ("mr_finalizers_run", C.c_int, []),
         ]:
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
@@ -131,7 +131,7 @@ def test_shim_registers_the_reference_symbols(R):
     class Def(C.Structure):
         _fields_ = [("name", C.c_char_p), ("fun", C.c_void_p), ("numArgs", C.c_int)]
 
-    table = (Def * 6).in_dll(R.L, "ca_shim_entries")
+    table = (Def * 11).in_dll(R.L, "ca_shim_entries")
     got = {}
     for d in table:
         if d.name is None:
@@ -141,6 +141,10 @@ def test_shim_registers_the_reference_symbols(R):
     # src/RcppExports.cpp:130-132: the three names and arities the package registers today
     assert got["_ClustAssess_myContTable"] == 4 and got["_ClustAssess_disjointECS"] == 2 and got["_ClustAssess_disjointECSaverage"] == 2
     assert got["_ClustAssess_ecs_consistency"] == 3 and got["_ClustAssess_ecs_sim_matrix"] == 1
+    # the same set of batched entries route A exports (r/calculate_ecs_b200.cpp): agreement, dedup, resident label sets
+    assert got["_ClustAssess_ecs_agreement"] == 2 and got["_ClustAssess_ecs_merge_identical"] == 2
+    assert got["_ClustAssess_ecs_resident"] == 1 and got["_ClustAssess_ecs_resident_consistency"] == 4
+    assert got["_ClustAssess_ecs_resident_sim_matrix"] == 2 and len(got) == 10
     assert table[len(got)].name is None  # NULL-terminated like R_CallMethodDef tables must be
 
 
@@ -156,6 +160,15 @@ def test_shim_raises_argument_errors_as_r_conditions(R):
         R.call("_ClustAssess_ecs_consistency", R.list([R.int([1, 2, 3]), R.int([1, 2])]), R.null(), R.lgl(False))
     with pytest.raises(RuntimeError, match="The partitions do not have the same length"):
         R.call("_ClustAssess_ecs_sim_matrix", R.list([R.int([1, 2, 3]), R.real([1, 2])]))
+    two = [R.int([1, 2, 3]), R.int([1, 2, 2])]
+    with pytest.raises(RuntimeError, match="weights must have one entry per clustering"):  # a short vector would be read out of bounds
+        R.call("_ClustAssess_ecs_consistency", R.list(two), R.real([1.0]), R.lgl(False))
+    with pytest.raises(RuntimeError, match="freq must have one entry per clustering"):
+        R.call("_ClustAssess_ecs_merge_identical", R.list(two), R.real([1.0, 1.0, 1.0]))
+    with pytest.raises(RuntimeError, match="The partitions do not have the same length"):
+        R.call("_ClustAssess_ecs_agreement", R.int([1, 2]), R.list(two))
+    with pytest.raises(RuntimeError, match="not a resident label set"):
+        R.call("_ClustAssess_ecs_resident_sim_matrix", R.int([1]), R.int([1, 2]))
     R.reset()
 
 
@@ -166,7 +179,10 @@ def test_shim_has_no_cpu_fallback(R):
                       ("_ClustAssess_disjointECSaverage", (R.int([1, 1, 2]), R.int([2, 2, 2]))),
                       ("_ClustAssess_myContTable", (R.int([1, 1, 2]), R.int([2, 2, 2]), R.int([1]), R.int([2]))),
                       ("_ClustAssess_ecs_consistency", (R.list([R.int([1, 1, 2]), R.int([2, 2, 2])]), R.null(), R.lgl(True))),
-                      ("_ClustAssess_ecs_sim_matrix", (R.list([R.int([1, 1, 2]), R.int([2, 2, 2])]),))]:
+                      ("_ClustAssess_ecs_sim_matrix", (R.list([R.int([1, 1, 2]), R.int([2, 2, 2])]),)),
+                      ("_ClustAssess_ecs_agreement", (R.int([1, 1, 2]), R.list([R.int([1, 1, 2]), R.int([2, 2, 2])]))),
+                      ("_ClustAssess_ecs_merge_identical", (R.list([R.int([1, 1, 2]), R.int([2, 2, 2])]), R.real([1.0, 1.0]))),
+                      ("_ClustAssess_ecs_resident", (R.list([R.int([1, 1, 2]), R.int([2, 2, 2])]),))]:
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             R.call(sym, *args)
     R.reset()
@@ -215,4 +231,39 @@ def test_shim_batched_routines_match_the_reference(R):
     bad[5] = np.iinfo(np.int32).min
     with pytest.raises(RuntimeError, match="NA"):
         R.call("_ClustAssess_ecs_sim_matrix", R.list([R.int(bad), R.int(L[1])]))
+    R.reset()
+
+
+@pytest.mark.gpu
+def test_shim_agreement_dedup_and_resident_sets(R):
+    """The entries that bring route B level with route A: element_agreement's flat branch (R/ECS.R:1639-1647),
+    merge_identical_partitions (R/ECS.R:1021-1054) and the resident label sets of the pipeline glue."""
+    R.reset()
+    L, w = synth.config("C3", m=7, n=15_013)
+    cols = [R.int(L[p]) for p in range(7)]
+    want = np.mean([oracle.corrected_l1_mb(L[0], L[p]) for p in range(1, 7)], axis=0)
+    agr = R.values(R.call("_ClustAssess_ecs_agreement", R.real(L[0].astype(np.float64)), R.list(cols[1:])))
+    assert agr.shape == (15_013,) and np.abs(agr - want).max() < TOL
+    dup = [L[0], L[1], L[0].max() + 1 - L[0], L[2], L[1]]  # 0 == 2, 1 == 4
+    res = R.values(R.call("_ClustAssess_ecs_merge_identical", R.list([R.int(x) for x in dup]), R.int([1, 1, 1, 1, 1])))
+    assert list(res) == ["keep", "freq"] and res["keep"].tolist() == [1, 2, 4] and res["freq"].tolist() == [2.0, 2.0, 1.0]
+    # resident: one upload, comparisons by 1-based index, result length taken from the set itself
+    ptr = R.call("_ClustAssess_ecs_resident", R.list(cols))
+    idx, sel = [2, 4, 5, 7], [1, 3, 4, 6]
+    ecc_s, sim_s = oracle.weighted_element_consistency(L[sel], w[sel], calculate_sim_matrix=True)
+    out = R.values(R.call("_ClustAssess_ecs_resident_consistency", ptr, R.int(idx), R.real(w[sel]), R.lgl(True)))
+    assert out["ecc"].shape == (15_013,) and np.abs(out["ecc"] - ecc_s).max() < TOL and np.abs(out["ecs_matrix"] - sim_s).max() < TOL
+    sim = R.values(R.call("_ClustAssess_ecs_resident_sim_matrix", ptr, R.real([2.0, 4.0, 5.0, 7.0])))
+    assert sim.shape == (4, 4) and np.abs(sim - sim_s).max() < TOL
+    with pytest.raises(RuntimeError, match="outside the resident label set"):
+        R.call("_ClustAssess_ecs_resident_sim_matrix", ptr, R.int([1, 8]))
+    with pytest.raises(RuntimeError, match="weights must have one entry per clustering"):
+        R.call("_ClustAssess_ecs_resident_consistency", ptr, R.int([1, 2, 3]), R.real([1.0, 2.0]), R.lgl(False))
+    # the finalizer releases the device memory exactly once; a released set is an R error, not a crash
+    before = R.L.mr_finalizers_run()
+    R.L.mr_finalize(ptr)
+    R.L.mr_finalize(ptr)
+    assert R.L.mr_finalizers_run() == before + 1
+    with pytest.raises(RuntimeError, match="has been released"):
+        R.call("_ClustAssess_ecs_resident_sim_matrix", ptr, R.int([1, 2]))
     R.reset()
