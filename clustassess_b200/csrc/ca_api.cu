@@ -347,6 +347,9 @@ static int init_device(Dev& D, int device) {
     for (int i = 0; i < 10; i++)
         if (!c.ev[i]) CA_CUDA(cudaEventCreate(&c.ev[i]));
     if (!D.ev_lab) CA_CUDA(cudaEventCreateWithFlags(&D.ev_lab, cudaEventDisableTiming));
+    if (!c.up_stream) CA_CUDA(cudaStreamCreateWithFlags(&c.up_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++)
+        if (!c.up_ev[i]) CA_CUDA(cudaEventCreateWithFlags(&c.up_ev[i], cudaEventDisableTiming));
     c.inited = true;
     return CA_OK;
 }
@@ -367,6 +370,9 @@ static void release_device(Dev& D) {
     for (int i = 0; i < 10; i++)
         if (D.c.ev[i]) { cudaEventDestroy(D.c.ev[i]); D.c.ev[i] = nullptr; }
     if (D.ev_lab) { cudaEventDestroy(D.ev_lab); D.ev_lab = nullptr; }
+    for (int i = 0; i < 8; i++)
+        if (D.c.up_ev[i]) { cudaEventDestroy(D.c.up_ev[i]); D.c.up_ev[i] = nullptr; }
+    if (D.c.up_stream) { cudaStreamDestroy(D.c.up_stream); D.c.up_stream = nullptr; }
     if (D.c.own_stream) { cudaStreamDestroy(D.c.own_stream); D.c.own_stream = nullptr; }
     D.c.stream = nullptr;
     D.c.inited = false;
@@ -549,11 +555,11 @@ static int ranks_stage_a(Labels& L) {
 }
 
 // stage B: compact cluster sizes of the partitions held here, at the row stride of the whole set (kmax over all shards)
-static int ranks_stage_b(Labels& L, int32_t kmax_all) {
+static int ranks_stage_b(Labels& L, int32_t kmax_all, int32_t kp_fixed = 0) {
     cudaStream_t s = ctx().stream;
     const int32_t m = L.m;
     L.kmax = kmax_all;
-    L.kp = std::max(8, (L.kmax + 1 + 7) & ~7);  // + the pad column
+    L.kp = kp_fixed ? kp_fixed : std::max(8, (L.kmax + 1 + 7) & ~7);  // + the pad column
     L.mpad = (L.mg() + 31) & ~31;
     if (m == 0) return CA_OK;
     int64_t max_range = 0;
@@ -981,13 +987,13 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
 
     // ---- the wave kernel ----------------------------------------------------------------------------
     TileParams T;
-    T.lab16 = L.d_lab16.as<uint16_t>();
+    T.lab16 = L.lab16_all();
     T.n = n;
     T.perm = W.perm.as<int32_t>();
     T.sizes = L.sizes_all();
-    T.tmpl = L.d_tmpl.as<uint32_t>();
-    T.tmpl_bytes = L.tmpl_bytes;
-    T.kinfo = L.d_kinfo.as<int32_t>();
+    T.tmpl = L.tmpl_all();
+    T.tmpl_bytes = L.tmpl_bytes_all();
+    T.kinfo = L.kinfo_all();
     {
         DevBuf& zeros = scratch(SCR_ZEROS);
         if (!zeros.p) {
@@ -1005,6 +1011,7 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     T.ecc = reinterpret_cast<unsigned long long*>(d_ecc);  // fixed-point partial sums until launch_finish converts them
     T.sim = reinterpret_cast<unsigned long long*>(d_sim);
     T.sim_magic = sim_fix_magic(n);
+    T.sim_scale = sim_fix_scale(n);
     T.perm_stride = perm_stride;
     T.m = m;
     T.mpad = L.mpad;
@@ -1740,6 +1747,223 @@ static int set_allpairs(ca_labels_t* h, const double* weights, double* ecc_out, 
     return CA_OK;
 }
 
+// ---- the pipelined host path (one device): the upload of later partitions overlaps the wave kernel of earlier ones ----------
+// A job from HOST buffers used to be upload (2 GB over PCIe: 36 ms at config 5) THEN compute.  Owner partition i only meets
+// partners j > i, so once the LAST partitions are on the device their pairs can run while the rest is still crossing PCIe.  The
+// partitions are cut into span-aligned groups from the top -- 1, 2, 4 spans, then the rest -- uploaded in that order on a second
+// stream (its own thread: pageable sources are staged through pinned slots); each group is one share of a sharded label set whose
+// shares all live on this device: as soon as its upload event fires it is packed (ranks, sizes, templates, its slabs of the compact
+// label array -- all into the whole-set arrays of the container) and the pairs of ITS owners against every partition above them run
+// as one launch set of the wave kernel.  The work available after a fraction f of the upload is f^2 of the job, so the engine stops
+// waiting after the first few milliseconds.  Partner rows of the sizes / template arrays have one stride for the whole job; it is
+// fixed from the first group with a 2x margin, and a later group that needs more makes the function bail out (handled = false)
+// so that the caller takes the plain path.  Results are bit-identical to the plain path (integer sums).
+static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols, int64_t n, int32_t m, const double* weights, double* ecc_out,
+                              double* sim_out, bool* handled) {
+    *handled = false;
+    const int32_t nspan = (m + 31) / 32;
+    if (ndevices() != 1 || nspan < 8 || (int64_t)n * m * 4 < (128ll << 20) || getenv("CA_NO_PIPELINE")) return CA_OK;
+    Dev& D = cur();
+    Ctx& c = D.c;
+    cudaStream_t s = c.stream;
+    // groups of spans from the top: 1, 2, 4, then the rest
+    std::vector<std::pair<int32_t, int32_t>> groups;  // [first span, last span + 1)
+    {
+        int32_t hi = nspan, sz = 1;
+        while (hi > 0 && (int)groups.size() < 3 && hi - sz >= nspan / 2) {
+            groups.push_back({hi - sz, hi});
+            hi -= sz;
+            sz *= 2;
+        }
+        groups.push_back({0, hi});
+    }
+    const int G = (int)groups.size();
+    ca_labels H;  // the container: whole-set arrays in H.L, one share per group
+    H.sharded = true;
+    H.n = n;
+    H.m = m;
+    Labels& WL = H.L;
+    WL.n = n;
+    WL.m = 0;
+    WL.m_glob = m;
+    WL.mpad = (m + 31) & ~31;
+    for (int g = 0; g < G; g++) {
+        H.sh.emplace_back(new Labels());
+        Labels& L = *H.sh[g];
+        L.n = n;
+        L.m_glob = m;
+        L.whole = &WL;
+        for (int32_t sp = groups[g].first; sp < groups[g].second; sp++) {
+            L.spans.push_back(sp);
+            for (int32_t i = sp * 32; i < std::min(m, sp * 32 + 32); i++) L.gid.push_back(i);
+        }
+        L.m = (int32_t)L.gid.size();
+    }
+    int rc = CA_OK;
+    std::atomic<int> enqueued{0}, up_rc{CA_OK};
+    std::string up_msg;
+    std::thread uploader;
+    auto cleanup = [&]() {
+        if (uploader.joinable()) uploader.join();
+        cudaStreamSynchronize(c.up_stream);
+        cudaStreamSynchronize(s);
+        for (auto& sh : H.sh) release_labels(*sh);
+        release_labels(WL);
+    };
+    // ---- allocations, then the uploads (all of them queued at once, in group order) ----
+    for (int g = 0; g < G && rc == CA_OK; g++) {
+        Labels& L = *H.sh[g];
+        cudaError_t e = dev_alloc((void**)&L.d_raw, (size_t)n * (size_t)L.m * 4);
+        if (e != cudaSuccess) {
+            L.d_raw = nullptr;
+            set_error("cudaMalloc for the label matrix failed: %s", cudaGetErrorString(e));
+            rc = CA_E_NOMEM;
+            break;
+        }
+        rc = L.d_span.ensure(L.spans.size() * 4);
+        if (rc == CA_OK && cudaMemcpyAsync(L.d_span.p, L.spans.data(), L.spans.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) rc = CA_E_CUDA;
+    }
+    if (rc == CA_OK) rc = WL.d_lab16.ensure((size_t)(n + 1) * WL.mpad * 2);
+    if (rc == CA_OK) rc = WL.d_kinfo.ensure((size_t)WL.mpad * 4);
+    if (rc == CA_OK) rc = WL.d_kcount_g.ensure((size_t)m * 4);
+    DevBuf &d_ecc = scratch(SCR_ECC), &d_sim = scratch(SCR_SIM);
+    if (rc == CA_OK && ecc_out) rc = d_ecc.ensure((size_t)n * 8);
+    if (rc == CA_OK && sim_out) rc = d_sim.ensure((size_t)m * m * 8);
+    if (rc == CA_OK) {
+        cudaError_t e = cudaMemsetAsync(WL.d_kinfo.p, 0, (size_t)WL.mpad * 4, s);
+        if (e == cudaSuccess && ecc_out) e = cudaMemsetAsync(d_ecc.p, 0, (size_t)n * 8, s);
+        if (e == cudaSuccess && sim_out) e = cudaMemsetAsync(d_sim.p, 0, (size_t)m * m * 8, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the span ids are on the device before the uploader's stream touches anything
+        if (e != cudaSuccess) {
+            set_error("pipelined path: set-up failed: %s", cudaGetErrorString(e));
+            rc = CA_E_CUDA;
+        }
+    }
+    if (rc != CA_OK) {
+        std::string msg = g_err;
+        cleanup();
+        set_error("%s", msg.c_str());
+        return rc;
+    }
+    Dev* dev_ptr = &D;
+    uploader = std::thread([&, dev_ptr]() {
+        DevScope scope(dev_ptr);
+        for (int g = 0; g < G; g++) {
+            Labels& L = *H.sh[g];
+            int urc = CA_OK;
+            if (labels) {  // a group is a contiguous block of rows
+                const UploadSeg seg = {labels + (size_t)L.gid[0] * n, L.d_raw, (size_t)L.m * n * 4};
+                urc = upload_segments(&seg, 1, c.up_stream);
+            } else {
+                std::vector<UploadSeg> segs((size_t)L.m);
+                for (int32_t k = 0; k < L.m && urc == CA_OK; k++) {
+                    if (!cols[L.gid[k]]) {
+                        set_error("NULL column pointer %d", L.gid[k]);
+                        urc = CA_E_ARG;
+                    }
+                    segs[k] = {cols[L.gid[k]], L.d_raw + (size_t)k * n, (size_t)n * 4};
+                }
+                if (urc == CA_OK) urc = upload_segments(segs.data(), segs.size(), c.up_stream);
+            }
+            if (urc == CA_OK && cudaEventRecord(c.up_ev[g], c.up_stream) != cudaSuccess) {
+                set_error("cudaEventRecord failed");
+                urc = CA_E_CUDA;
+            }
+            if (urc != CA_OK) {
+                up_msg = g_err;
+                up_rc.store(urc);
+            }
+            enqueued.store(g + 1, std::memory_order_release);  // the main thread may now wait for this group's event
+        }
+    });
+    // ---- the groups, in upload order ----
+    int32_t kmax_sofar = 0, kp_fixed = 0;
+    bool bail = false;
+    for (int g = 0; g < G && rc == CA_OK && !bail; g++) {
+        Labels& L = *H.sh[g];
+        while (enqueued.load(std::memory_order_acquire) <= g) std::this_thread::yield();
+        if (up_rc.load() != CA_OK) {
+            set_error("%s", up_msg.c_str());
+            rc = up_rc.load();
+            break;
+        }
+        if (cudaStreamWaitEvent(s, c.up_ev[g], 0) != cudaSuccess) {
+            set_error("cudaStreamWaitEvent failed");
+            rc = CA_E_CUDA;
+            break;
+        }
+        rc = ranks_stage_a(L);  // min / max, histograms, ranks of this group (its host syncs also end the previous group's kernels)
+        if (rc != CA_OK) break;
+        kmax_sofar = std::max(kmax_sofar, L.kmax);
+        if (!engine_supports(kmax_sofar)) {
+            bail = true;  // the plain path decides (pair-loop fallback)
+            break;
+        }
+        if (g == 0) {
+            int32_t lim = kmax_sofar;
+            while (engine_supports(lim + 1024) && lim < 2 * kmax_sofar + 64) lim += 1024;  // up to 2x the first group's cluster counts
+            kp_fixed = std::max(8, (std::max(lim, kmax_sofar) + 1 + 7) & ~7);
+            rc = WL.d_sizes_g.ensure((size_t)m * kp_fixed * 4);
+            if (rc == CA_OK) rc = WL.d_spack.ensure((size_t)m * kp_fixed * 4);
+            int32_t half = 0;
+            tile_smem_budget(kmax_sofar, nullptr, &half);
+            WL.tmpl_bytes = std::max(half, 16);
+            if (rc == CA_OK) rc = WL.d_tmpl.ensure((size_t)m * (size_t)WL.tmpl_bytes);
+            if (rc != CA_OK) break;
+            WL.kp = kp_fixed;
+        } else if (kmax_sofar + 1 > kp_fixed) {
+            bail = true;  // this group has more clusters than the row stride fixed from the first group allows
+            break;
+        }
+        rc = ranks_stage_b(L, kmax_sofar, kp_fixed);
+        if (rc != CA_OK) break;
+        WL.kmax = kmax_sofar;
+        const int32_t p0 = L.gid[0];
+        int32_t max_rows = 0;
+        tile_smem_budget(kmax_sofar, &max_rows);
+        cudaError_t e = cudaMemcpyAsync(static_cast<int32_t*>(WL.d_sizes_g.p) + (size_t)p0 * kp_fixed, L.d_sizes.p, (size_t)L.m * kp_fixed * 4, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(static_cast<int32_t*>(WL.d_kcount_g.p) + p0, L.d_kcount.p, (size_t)L.m * 4, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) {
+            set_error("pipelined path: device copy failed: %s", cudaGetErrorString(e));
+            rc = CA_E_CUDA;
+            break;
+        }
+        // this group's rows of the partner arrays: initial table entries, K | flags, table templates; its slabs of the label array
+        rc = launch_spack(static_cast<int32_t*>(WL.d_sizes_g.p) + (size_t)p0 * kp_fixed, static_cast<int32_t*>(WL.d_kcount_g.p) + p0, L.m, kp_fixed,
+                          static_cast<uint32_t*>(WL.d_spack.p) + (size_t)p0 * kp_fixed, static_cast<int32_t*>(WL.d_kinfo.p) + p0, s);
+        if (rc == CA_OK)
+            rc = launch_table_template(static_cast<uint32_t*>(WL.d_spack.p) + (size_t)p0 * kp_fixed, static_cast<int32_t*>(WL.d_kcount_g.p) + p0, L.m, kp_fixed,
+                                       WL.tmpl_bytes, std::max(max_rows, 1),
+                                       reinterpret_cast<uint32_t*>(static_cast<char*>(WL.d_tmpl.p) + (size_t)p0 * (size_t)WL.tmpl_bytes), s);
+        if (rc != CA_OK) break;
+        LabDst dst;
+        dst.n = 1;
+        dst.p[0] = static_cast<uint16_t*>(WL.d_lab16.p);
+        rc = launch_relabel_transpose(L.d_raw, n, L.m, (int32_t)L.spans.size(), L.d_span.as<int32_t>(), L.d_min.as<int32_t>(),
+                                      L.identity ? nullptr : L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(), L.d_kcount.as<int32_t>(), dst, s);
+        if (rc != CA_OK) break;
+        L.mpad = WL.mpad;
+        L.ranked = L.prepared = true;
+        rc = run_allpairs(L, weights, 0, 1, ecc_out ? d_ecc.as<double>() : nullptr, sim_out ? d_sim.as<double>() : nullptr, -1, 0, 0, /*finish_sync=*/false);
+    }
+    if (rc == CA_OK && !bail) {
+        rc = launch_finish(ecc_out ? d_ecc.as<double>() : nullptr, n, ident_constant(weights, m), sim_out ? d_sim.as<double>() : nullptr, m, s);
+        cudaError_t e = cudaSuccess;
+        if (rc == CA_OK && ecc_out) e = cudaMemcpyAsync(ecc_out, d_ecc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
+        if (rc == CA_OK && e == cudaSuccess && sim_out) e = cudaMemcpyAsync(sim_out, d_sim.p, (size_t)m * m * 8, cudaMemcpyDeviceToHost, s);
+        if (rc == CA_OK && e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (rc == CA_OK && e != cudaSuccess) {
+            set_error("pipelined path: device-to-host copy failed: %s", cudaGetErrorString(e));
+            rc = CA_E_CUDA;
+        }
+    }
+    std::string msg = g_err;
+    cleanup();
+    if (rc != CA_OK) set_error("%s", msg.c_str());
+    *handled = rc == CA_OK && !bail;
+    return rc;
+}
+
 // ---- host-pointer batched entry points -----------------------------------------------------------------
 static int host_allpairs(const int32_t* labels, const int32_t* const* cols, int64_t n, int32_t m, const double* weights,
                          double* ecc_out, double* sim_out) {
@@ -1748,6 +1972,11 @@ static int host_allpairs(const int32_t* labels, const int32_t* const* cols, int6
     if (n == 0) {
         if (sim_out) fill_empty_sim(sim_out, m);
         return CA_OK;
+    }
+    if (m >= 2) {  // large single-device jobs: the upload overlaps the computation
+        bool handled = false;
+        CA_TRY(pipelined_allpairs(labels, cols, n, m, weights, ecc_out, sim_out, &handled));
+        if (handled) return CA_OK;
     }
     ca_labels_t* h = nullptr;
     CA_TRY(ca_labels_create(n, m, &h));

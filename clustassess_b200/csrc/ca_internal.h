@@ -34,6 +34,8 @@ struct Ctx {
     size_t smem_optin = 0;        // max dynamic shared memory per block (opt-in)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // the stream everything is launched on
+    cudaStream_t up_stream = nullptr;  // host -> device copies that run beside the kernels (pipelined host path)
+    cudaEvent_t up_ev[8] = {};         // one per upload group
     cudaEvent_t ev[10] = {};
     double prof[10] = {};
     long launches = 0;  // kernels launched since the counter was last reset
@@ -106,10 +108,18 @@ struct Labels {
     std::vector<int32_t> spans;    // the 32-partition spans owned (ascending): local block y of the transposition is span spans[y]
     DevBuf d_span, d_sizes_g, d_kcount_g;  // span ids on the device; cluster sizes [m_glob][kp] and counts [m_glob] of ALL partitions
     int dev_index = 0;             // which of the selected devices owns these buffers
+    // Several shares on ONE device (the pipelined host path: later shares are still crossing PCIe while earlier ones compute)
+    // use the whole-set arrays of a common owner instead of their own
+    const Labels* whole = nullptr;
     int32_t mg() const { return m_glob ? m_glob : m; }
     int32_t gid_of(int32_t k) const { return m_glob ? gid[k] : k; }
-    const int32_t* sizes_all() const { return static_cast<const int32_t*>(m_glob ? d_sizes_g.p : d_sizes.p); }
-    const int32_t* kcount_all() const { return static_cast<const int32_t*>(m_glob ? d_kcount_g.p : d_kcount.p); }
+    const Labels& W() const { return whole ? *whole : *this; }
+    const int32_t* sizes_all() const { return static_cast<const int32_t*>(m_glob ? W().d_sizes_g.p : d_sizes.p); }
+    const int32_t* kcount_all() const { return static_cast<const int32_t*>(m_glob ? W().d_kcount_g.p : d_kcount.p); }
+    const uint16_t* lab16_all() const { return static_cast<const uint16_t*>(W().d_lab16.p); }
+    const uint32_t* tmpl_all() const { return static_cast<const uint32_t*>(W().d_tmpl.p); }
+    const int32_t* kinfo_all() const { return static_cast<const int32_t*>(W().d_kinfo.p); }
+    int64_t tmpl_bytes_all() const { return W().tmpl_bytes; }
 };
 
 int prepare_ranks(Labels& L);   // min/max, dense ranks, cluster sizes: all the dedup pre-pass needs (any cluster count)
@@ -162,7 +172,7 @@ constexpr int TL_CPT = 4;
 #define CA_TL_PREFETCH 0   // resident kernel: the next super-tile's labels (and the next work unit's cell ids) are loaded one tile ahead
 #endif
 #ifndef CA_TL_STR_THREADS
-#define CA_TL_STR_THREADS 864
+#define CA_TL_STR_THREADS 608
 #endif
 constexpr int TL_THREADS = CA_TL_THREADS;          // tuning builds (tools/build_variant.sh) override these
 constexpr int TL_STR_THREADS = CA_TL_STR_THREADS;
@@ -198,7 +208,8 @@ struct TileParams {
     uint32_t* qinfo;          // [m_slots][perm_stride / 4] x {row in block, cluster size} of every quad of positions
     unsigned long long* ecc;  // [n] fixed-point partial sums (units of 2^-61), accumulated with integer atomics (may be null)
     unsigned long long* sim;  // [m*m] fixed-point sums of ECS over the cells (units of 1 / sim_fix_scale(n)) (may be null)
-    double sim_magic;         // 1.5 * 2^(52 - F): v + sim_magic leaves round(v * 2^F) in the low mantissa bits (sim_fix_magic(n))
+    double sim_magic;         // 1.5 * 2^(52 - F): (v + sim_magic) - sim_magic rounds v to the grid 2^-F (sim_fix_magic(n))
+    double sim_scale;         // 2^F (sim_fix_scale(n))
     int64_t perm_stride;
     int32_t m, mpad, kp;
     int32_t nsuper, nwu;      // super-tiles, work units

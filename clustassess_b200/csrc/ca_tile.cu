@@ -116,11 +116,6 @@ __device__ __forceinline__ unsigned long long lds_b64(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ void sts_b64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
-__device__ __forceinline__ unsigned long long __reduce_add_sync_u64(unsigned long long v) {  // integer: any order gives the same sum
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 // double -> fixed point (round to nearest); the product is far below 2^63 by construction
 __device__ __forceinline__ unsigned long long to_fix(double v, double scale) { return (unsigned long long)__double2ll_rn(v * scale); }
 
@@ -269,15 +264,20 @@ __device__ __forceinline__ double ecs_term(uint32_t count, uint32_t sa, uint32_t
 }
 
 // The matrix entry of a pair is sum_n ECS_ij[n] / N.  To make it independent of which thread holds which cell (the order of
-// the cells inside a cluster varies from run to run, ca_pack.cu) every term is rounded to the fixed-point grid BEFORE it is
-// added: v + magic (magic = 1.5 * 2^(52 - F)) leaves round(v * 2^F) in the low mantissa bits -- one DADD and a 64-bit integer
-// add per term -- and integer sums are associative.  The warp's sum then joins the block's accumulator of its tile slot.
-__device__ __forceinline__ unsigned long long sim_fix(const TileParams& P, double v) {
-    return (unsigned long long)(__double_as_longlong(v + P.sim_magic) - __double_as_longlong(P.sim_magic));
-}
-__device__ __forceinline__ void sim_warp_add(uint32_t simacc_slot, unsigned long long es, int lane) {
-    es = __reduce_add_sync_u64(es);
-    if (lane == 0 && es != 0ull) red_add_u64(simacc_slot, es);
+// the cells inside a cluster varies from run to run, ca_pack.cu) every term is rounded to the fixed-point grid 2^-F BEFORE
+// it is added: (v + magic) - magic with magic = 1.5 * 2^(52 - F).  Sums of grid values below 2^(53 - F) are EXACT in fp64
+// (F <= 40, a warp adds at most 128 terms <= 1), so a thread's and a warp's partial sums do not depend on the order of the
+// additions; the warp's total then joins the block's 64-bit integer accumulator of its tile slot, and integers are associative.
+__device__ __forceinline__ double sim_round(const TileParams& P, double v) { return (v + P.sim_magic) - P.sim_magic; }
+// A thread's sum `es` is an exact multiple of 2^-F below 2^11: es + magic carries es * 2^F as an integer in its low mantissa bits
+// (magic's own low word is zero), so the warp total is two hardware integer reductions (REDUX) of its 24-bit pieces instead of a
+// shuffle tree of doubles.
+__device__ __forceinline__ void sim_warp_add(const TileParams& P, uint32_t simacc_slot, double es, int lane) {
+    const double t = es + P.sim_magic;
+    const uint32_t lo = (uint32_t)__double2loint(t), hi = (uint32_t)(__double2hiint(t) - __double2hiint(P.sim_magic));
+    const uint32_t s0 = __reduce_add_sync(FULL, lo & 0xffffffu);
+    const uint32_t s1 = __reduce_add_sync(FULL, __funnelshift_r(lo, hi, 24));
+    if (lane == 0 && (s0 | s1) != 0u) red_add_u64(simacc_slot, ((unsigned long long)s1 << 24) + s0);
 }
 
 // UNITW: all weights are 1 (element_consistency of distinct partitions): ECS = count * r is accumulated by one FMA.
@@ -295,7 +295,7 @@ __device__ __forceinline__ void gather_cells(const TileParams& P, uint32_t meta,
             const uint2 tr = lds_u64(meta + META_TR + JT * 8);
             const uint32_t rb = tr.x + rowidx * tr.y;
             const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + JT * 8);
-            unsigned long long es = 0ull;
+            double es = 0.0;
 #pragma unroll
             for (int g = 0; g < NCELL / 4; g++) {
                 if (NCELL == 4 || g < ng) {
@@ -312,12 +312,12 @@ __device__ __forceinline__ void gather_cells(const TileParams& P, uint32_t meta,
                         } else {
                             const double v = ecs_term(count, sa, sb);
                             acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
-                            if (WANT_SIM) es += ((vmask >> c) & 1u) ? sim_fix(P, v) : 0ull;
+                            if (WANT_SIM) es += ((vmask >> c) & 1u) ? sim_round(P, v) : 0.0;
                         }
                     }
                 }
             }
-            if (WANT_SIM) sim_warp_add(simacc + JT * 8u, es, lane);
+            if (WANT_SIM) sim_warp_add(P, simacc + JT * 8u, es, lane);
         });
         return;
     }
@@ -327,7 +327,7 @@ __device__ __forceinline__ void gather_cells(const TileParams& P, uint32_t meta,
         const uint32_t rb = tr.x + rowidx * tr.y;
         const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + jt * 8);
         const int32_t* szg = P.sizes + (int64_t)(ph.j0 + jt) * P.kp;
-        unsigned long long es = 0ull;
+        double es = 0.0;
 #pragma unroll
         for (int g = 0; g < NCELL / 4; g++) {
             if (NCELL == 4 || g < ng) {
@@ -346,11 +346,11 @@ __device__ __forceinline__ void gather_cells(const TileParams& P, uint32_t meta,
                     }
                     const double v = ecs_term(count, sa, sb);
                     acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
-                    if (WANT_SIM) es += ((vmask >> c) & 1u) ? sim_fix(P, v) : 0ull;
+                    if (WANT_SIM) es += ((vmask >> c) & 1u) ? sim_round(P, v) : 0.0;
                 }
             }
         }
-        if (WANT_SIM) sim_warp_add(simacc + jt * 8u, es, lane);
+        if (WANT_SIM) sim_warp_add(P, simacc + jt * 8u, es, lane);
     }
 }
 

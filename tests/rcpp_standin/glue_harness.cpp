@@ -98,12 +98,12 @@ int gh_merge_identical(const int* const* cols, const R_xlen_t* lens, int m, cons
     });
 }
 // ecsResident once, then two comparisons on index subsets without another upload
-int gh_resident(const int* const* cols, const R_xlen_t* lens, int m, const int* idx1, int k, const double* w, int want_matrix, double* ecc,
+int gh_resident(const int* const* cols, const R_xlen_t* lens, int m, const int* idx1, int k, const double* w, int nw, int want_matrix, double* ecc,
                 double* sim, double* sim_only) {
     return guarded([&] {
         SEXP handle = ecsResident(make_list(cols, lens, m, 0));
         Nullable<NumericVector> weights;
-        if (w) weights = Nullable<NumericVector>(wrap(NumericVector(w, w + k)));
+        if (w) weights = Nullable<NumericVector>(wrap(NumericVector(w, w + nw)));
         List res = ecsResidentConsistency(handle, IntegerVector(idx1, idx1 + k), weights, want_matrix != 0);
         NumericVector e = as<NumericVector>(res.get("ecc"));
         std::memcpy(ecc, e.begin(), sizeof(double) * (size_t)e.size());

@@ -564,3 +564,120 @@ def test_merge_partitions_thresholds_ordering_and_ties_match_the_golden_fixtures
             assert np.abs(res["ecs_matrix"] - np.asarray(c["ecs_matrix"])).max() < TOL
         if c["avg_agreement"] is not None:
             assert np.abs(np.asarray([p["avg_agreement"] for p in res["partitions"]]) - np.asarray(c["avg_agreement"])).max() < TOL
+
+
+# ---- full sizes inside pytest (the driver's view): C3 and C4 complete, a 4-span job at one million cells ------------------
+def _host_threads():
+    import os
+
+    return max(1, os.cpu_count() or 1)
+
+
+def test_config3_full_size_weighted_consistency_and_matrix():
+    """BASELINE config 3 at its full size (100 partitions x 100k cells, integer frequency weights): every cell and every
+    matrix entry against the oracle (R/ECS.R:1446-1500)."""
+    L, w = synth.config("C3")
+    assert L.shape == (100, 100_000)
+    res = ecs.weighted_element_consistency(list(L), weights=w, calculate_sim_matrix=True)
+    pi, pj = np.triu_indices(L.shape[0], k=1)
+    _, acc_unused, means, _ = oracle.pairs_detail(L, pi, pj, nthreads=_host_threads())
+    ecc_ref, sim_ref = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - ecc_ref).max() < TOL
+    assert np.abs(res["ecs_matrix"] - sim_ref).max() < TOL
+    assert np.abs(res["ecs_matrix"][pi, pj] - means).max() < TOL  # the threaded per-pair body agrees with the sequential loop
+
+
+def test_config4_full_size_matrix():
+    """BASELINE config 4 at its full size (element_sim_matrix of 1000 partitions x 50k cells): 499 500 entries on the GPU,
+    1500 randomly drawn ones against the oracle's mean(disjointECS) (R/ECS.R:942-965), symmetry and unit diagonal for all."""
+    L, _ = synth.config("C4")
+    assert L.shape == (1000, 50_000)
+    sim = ecs.element_sim_matrix(list(L))
+    assert sim.shape == (1000, 1000) and np.array_equal(sim, sim.T) and np.all(np.diag(sim) == 1.0)
+    rng = np.random.default_rng(44)
+    pi = rng.integers(0, 999, size=1500)
+    pj = np.array([rng.integers(i + 1, 1000) for i in pi])
+    _, _, means, _ = oracle.pairs_detail(L, pi, pj, nthreads=_host_threads())
+    assert np.abs(sim[pi, pj] - means).max() < TOL
+    assert np.all((sim >= 0.0) & (sim <= 1.0))
+
+
+def test_one_million_cells_four_spans_every_cell_against_the_oracle():
+    """The headline family at N = 1M with 100 partitions = four 32-partition spans, resident and streaming items, up to 2000
+    clusters: ALL 4950 pairs on the host (threaded per-pair body of R/ECS.R:1478-1484, ~0.1 core-seconds per pair), every
+    cell's consistency and every matrix entry compared."""
+    L, _ = synth.config("C5", m=100)
+    m, n = L.shape
+    assert n == 1_000_000
+    pi, pj = np.triu_indices(m, k=1)
+    _, acc, means, _ = oracle.pairs_detail(L, pi, pj, nthreads=_host_threads())
+    res = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
+    assert np.abs(res["ecc"] - acc / float(pi.size)).max() < TOL
+    assert np.abs(res["ecs_matrix"][pi, pj] - means).max() < TOL
+    again = ecs.weighted_element_consistency(list(L), calculate_sim_matrix=True)
+    assert np.array_equal(again["ecc"], res["ecc"]) and np.array_equal(again["ecs_matrix"], res["ecs_matrix"])  # same bits in every run
+
+
+# ---- the pipelined host path: upload of later partition groups overlaps the computation of earlier ones -----------------------
+def _louvainish(m, n, k_lo, k_hi, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, k_lo, size=n)
+    out = np.empty((m, n), dtype=np.int32)
+    for p in range(m):
+        k = int(rng.integers(k_lo, k_hi + 1))
+        x = base.copy()
+        hit = rng.random(n) < rng.uniform(0.02, 0.2)
+        x[hit] = rng.integers(0, k, size=int(hit.sum()))
+        out[p] = rng.permutation(k_hi + 1)[x] + 1
+    return out
+
+
+def test_pipelined_host_path_equals_plain_path_and_oracle(monkeypatch):
+    """256 partitions x 140k cells from host buffers (143 MB, 8 spans): the host entry cuts the partitions into groups from the
+    top and computes each group's pairs while the next one is still being uploaded.  Same bits as the plain path
+    (CA_NO_PIPELINE=1), every cell and every matrix entry against the oracle."""
+    L = _louvainish(256, 140_000, 20, 60, seed=77)
+    m, n = L.shape
+    w = (1 + np.random.default_rng(78).poisson(1.0, size=m)).astype(np.float64)
+    cols = [np.ascontiguousarray(r) for r in L]
+    res = ecs.weighted_element_consistency(cols, weights=w, calculate_sim_matrix=True)
+    only_ecc = ecs.weighted_element_consistency(cols, weights=w)
+    sim_only = ecs.element_sim_matrix(cols)
+    packed = np.empty(n, dtype=np.float64)
+    _capi.check(_capi.lib().ca_consistency(L.reshape(-1), n, m, w.ctypes.data, packed, None))  # the matrix form of the same entry
+    monkeypatch.setenv("CA_NO_PIPELINE", "1")
+    plain = ecs.weighted_element_consistency(cols, weights=w, calculate_sim_matrix=True)
+    monkeypatch.delenv("CA_NO_PIPELINE")
+    assert np.array_equal(res["ecc"], plain["ecc"]) and np.array_equal(res["ecs_matrix"], plain["ecs_matrix"])
+    assert np.array_equal(only_ecc, plain["ecc"]) and np.array_equal(sim_only, plain["ecs_matrix"]) and np.array_equal(packed, plain["ecc"])
+    ecc_ref, sim_ref = oracle.weighted_element_consistency(L[:64], w[:64], calculate_sim_matrix=True)
+    sub = ecs.weighted_element_consistency(cols[:64], weights=w[:64], calculate_sim_matrix=True)  # 64 partitions: the plain path
+    assert np.abs(sub["ecc"] - ecc_ref).max() < TOL and np.abs(sub["ecs_matrix"] - sim_ref).max() < TOL
+    pi, pj = np.triu_indices(m, k=1)
+    _, _, means, _ = oracle.pairs_detail(L, pi, pj, nthreads=_host_threads())
+    assert np.abs(res["ecs_matrix"][pi, pj] - means).max() < TOL
+    # weighted ecc of the whole set from the per-pair ECS sums needs all pairs' vectors; check it through the identity
+    # ecc = sum_i w_i (w_i - 1) / 2 / norm + sum_{i<j} w_i w_j ECS_ij / norm on a sample of cells instead
+    cells = np.random.default_rng(79).choice(n, size=300, replace=False)
+    tot = w.sum()
+    norm = tot * (tot - 1) / 2
+    want = np.full(cells.size, float((w * (w - 1) / 2).sum() / norm))
+    _, _, _, cv = oracle.pairs_detail(L, pi, pj, cells=cells, nthreads=_host_threads())
+    want += (cv * (w[pi] * w[pj] / norm)[:, None]).sum(axis=0)
+    assert np.abs(res["ecc"][cells] - want).max() < TOL
+
+
+def test_pipelined_host_path_bails_out_when_later_groups_have_many_more_clusters():
+    """The row stride of the partner arrays is fixed from the first uploaded group (the LAST partitions) with a 2x margin; when an
+    earlier partition turns out to have far more clusters the pipelined path gives up and the plain path answers -- same result."""
+    rng = np.random.default_rng(81)
+    m, n = 256, 131_072
+    L = np.stack([rng.integers(0, 40, size=n) for _ in range(m)]).astype(np.int32)
+    L[5] = rng.integers(0, 3000, size=n)
+    L[5][:3000] = np.arange(3000)
+    cols = [np.ascontiguousarray(r) for r in L]
+    got = ecs.element_sim_matrix(cols)
+    pi = np.array([5] * 6 + [0, 100, 254])
+    pj = np.array([6, 40, 100, 200, 254, 255, 5, 255, 255])
+    _, _, means, _ = oracle.pairs_detail(L, pi, pj, nthreads=4)
+    assert np.abs(got[pi, pj] - means).max() < TOL and np.array_equal(got, got.T)

@@ -42,7 +42,7 @@ class Glue:
             ("gh_disjoint_ecs", I, [P, X, P, X, P]), ("gh_disjoint_ecs_average", I, [P, X, P, X, P]),
             ("gh_consistency", I, [P, P, I, I, P, I, I, P, P]), ("gh_sim_matrix", I, [P, P, I, I, P]),
             ("gh_agreement", I, [P, X, P, P, I, P]), ("gh_merge_identical", I, [P, P, I, P, I, P, P, P]),
-            ("gh_resident", I, [P, P, I, P, I, P, I, P, P, P]),
+            ("gh_resident", I, [P, P, I, P, I, P, I, I, P, P, P]),
         ]:
             f = getattr(self.L, name)
             f.restype, f.argtypes = res, args
@@ -113,7 +113,7 @@ class Glue:
         k, n = ix.size, arrs[0].size
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
         ecc, sim, sim_only = np.zeros(n), np.zeros((k, k)), np.zeros((k, k))
-        self._check(self.L.gh_resident(ptrs, lens, len(arrs), ix.ctypes.data, k, None if w is None else w.ctypes.data, 1,
+        self._check(self.L.gh_resident(ptrs, lens, len(arrs), ix.ctypes.data, k, None if w is None else w.ctypes.data, 0 if w is None else w.size, 1,
                                        ecc.ctypes.data, sim.ctypes.data, sim_only.ctypes.data))
         return ecc, sim, sim_only
 
