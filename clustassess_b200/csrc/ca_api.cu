@@ -503,6 +503,11 @@ static int ranks_stage_a(Labels& L) {
     cudaStream_t s = c.stream;
     const int32_t m = L.m;
     const int64_t n = L.n;
+    const bool dbg = getenv("CA_PIPE_DEBUG") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (dbg) fprintf(stderr, "    [stage A] %-18s +%.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
     L.h_min.assign(m, 0);
     L.h_max.assign(m, 0);
     L.h_k.assign(m, 0);
@@ -512,10 +517,13 @@ static int ranks_stage_a(Labels& L) {
     if (m == 0) return CA_OK;
     CA_TRY(L.d_min.ensure((size_t)m * 4));
     CA_TRY(L.d_max.ensure((size_t)m * 4));
+    lap("buffers");
     CA_TRY(launch_minmax(L.d_raw, n, m, L.d_min.as<int32_t>(), L.d_max.as<int32_t>(), s));
+    lap("minmax launched");
     CA_CUDA(cudaMemcpyAsync(L.h_min.data(), L.d_min.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
     CA_CUDA(cudaMemcpyAsync(L.h_max.data(), L.d_max.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
     CA_CUDA(cudaStreamSynchronize(s));
+    lap("minmax synced");
     int64_t max_range = 0;
     for (int32_t p = 0; p < m; p++) {
         if (L.h_min[p] == INT32_MIN) {
@@ -546,7 +554,9 @@ static int ranks_stage_a(Labels& L) {
     CA_TRY(launch_rank(L.d_cnt.as<uint32_t>(), L.d_roff.as<int64_t>(), nullptr, nullptr, m, L.d_rank.as<uint32_t>(),
                        L.d_kcount.as<int32_t>(), s));
     CA_CUDA(cudaMemcpyAsync(L.h_k.data(), L.d_kcount.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    lap("count/rank queued");
     CA_CUDA(cudaStreamSynchronize(s));
+    lap("count/rank synced");
     for (int32_t p = 0; p < m; p++) {
         L.kmax = std::max(L.kmax, L.h_k[p]);
         if ((int64_t)L.h_k[p] != L.h_roff[p + 1] - L.h_roff[p]) L.identity = false;
@@ -1758,6 +1768,52 @@ static int set_allpairs(ca_labels_t* h, const double* weights, double* ecc_out, 
 // waiting after the first few milliseconds.  Partner rows of the sizes / template arrays have one stride for the whole job; it is
 // fixed from the first group with a 2x margin, and a later group that needs more makes the function bail out (handled = false)
 // so that the caller takes the plain path.  Results are bit-identical to the plain path (integer sums).
+// A host -> device copy that leaves room for others: the DMA engine serves copies in the order they were SUBMITTED, whatever
+// their streams, so two gigabytes queued at once would make every small copy the packing and planning stages issue meanwhile
+// (range offsets, cluster starts, items) wait for all of it -- measured: the second group's packing finished 37 ms after the
+// start instead of 7.  And a copy queue that never runs empty starves the OTHER streams' copies on the same engine even when
+// it is short (four 8 MB pieces in flight: still 16.7 ms, the engine only switches channels when the active one idles).
+// Pinned sources therefore go out in 16 MB pieces, ONE in flight: the few microseconds between two pieces are where the small
+// copies get in (measured at config 5: 247 -> 220 ms end to end; CA_PIPE_DEPTH / CA_PIPE_PIECE_MB to experiment).  Pageable
+// sources are staged through the pinned slots of upload_segments.
+static int upload_throttled(const UploadSeg* segs, size_t nseg, cudaStream_t s, int max_threads) {
+    bool pinned = true;
+    for (size_t i = 0; i < nseg; i++)
+        if (segs[i].bytes && is_pageable(segs[i].src)) pinned = false;
+    if (!pinned) return upload_segments(segs, nseg, s, max_threads);
+    static const size_t PIECE = (size_t)(getenv("CA_PIPE_PIECE_MB") ? atoi(getenv("CA_PIPE_PIECE_MB")) : 16) << 20;
+    static const int DEPTH_ENV = getenv("CA_PIPE_DEPTH") ? atoi(getenv("CA_PIPE_DEPTH")) : 1;
+    constexpr int MAXDEPTH = 8;
+    const int DEPTH = std::max(1, std::min(DEPTH_ENV, MAXDEPTH));
+    cudaEvent_t ev[MAXDEPTH] = {};
+    for (int k = 0; k < DEPTH; k++)
+        if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            for (int q = 0; q < k; q++) cudaEventDestroy(ev[q]);
+            return upload_segments(segs, nseg, s, max_threads);
+        }
+    cudaError_t e = cudaSuccess;
+    size_t issued = 0;
+    for (size_t i = 0; i < nseg && e == cudaSuccess; i++)
+        for (size_t off = 0; off < segs[i].bytes && e == cudaSuccess; off += PIECE, issued++) {
+            const int k = (int)(issued % DEPTH);
+            if (issued >= (size_t)DEPTH) {  // wait until the piece submitted DEPTH pieces ago has landed -- polling with short sleeps: a
+                // blocking cudaEventSynchronize in this thread kept the driver busy enough to hold up the main thread's launches
+                while ((e = cudaEventQuery(ev[k])) == cudaErrorNotReady) std::this_thread::sleep_for(std::chrono::microseconds(40));
+            }
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync((char*)segs[i].dst + off, (const char*)segs[i].src + off, std::min(PIECE, segs[i].bytes - off), cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[k], s);
+        }
+    for (int k = 0; k < DEPTH; k++) cudaEventDestroy(ev[k]);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("host-to-device copy failed: %s", cudaGetErrorString(e));
+        return CA_E_CUDA;
+    }
+    return CA_OK;
+}
+
 static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols, int64_t n, int32_t m, const double* weights, double* ecc_out,
                               double* sim_out, bool* handled) {
     *handled = false;
@@ -1853,7 +1909,7 @@ static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols,
             int urc = CA_OK;
             if (labels) {  // a group is a contiguous block of rows
                 const UploadSeg seg = {labels + (size_t)L.gid[0] * n, L.d_raw, (size_t)L.m * n * 4};
-                urc = upload_segments(&seg, 1, c.up_stream);
+                urc = upload_throttled(&seg, 1, c.up_stream, Stager::MAXT);
             } else {
                 std::vector<UploadSeg> segs((size_t)L.m);
                 for (int32_t k = 0; k < L.m && urc == CA_OK; k++) {
@@ -1863,7 +1919,7 @@ static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols,
                     }
                     segs[k] = {cols[L.gid[k]], L.d_raw + (size_t)k * n, (size_t)n * 4};
                 }
-                if (urc == CA_OK) urc = upload_segments(segs.data(), segs.size(), c.up_stream);
+                if (urc == CA_OK) urc = upload_throttled(segs.data(), segs.size(), c.up_stream, Stager::MAXT);
             }
             if (urc == CA_OK && cudaEventRecord(c.up_ev[g], c.up_stream) != cudaSuccess) {
                 set_error("cudaEventRecord failed");
@@ -1879,13 +1935,24 @@ static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols,
     // ---- the groups, in upload order ----
     int32_t kmax_sofar = 0, kp_fixed = 0;
     bool bail = false;
+    const bool dbg = getenv("CA_PIPE_DEBUG") != nullptr;
+    const auto t_pipe0 = std::chrono::steady_clock::now();
+    auto lap = [&](int g, const char* what) {
+        if (dbg) fprintf(stderr, "[pipe] group %d %-22s %.3f ms\n", g, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pipe0).count());
+    };
     for (int g = 0; g < G && rc == CA_OK && !bail; g++) {
         Labels& L = *H.sh[g];
+        lap(g, "start");
         while (enqueued.load(std::memory_order_acquire) <= g) std::this_thread::yield();
+        lap(g, "upload enqueued");
         if (up_rc.load() != CA_OK) {
             set_error("%s", up_msg.c_str());
             rc = up_rc.load();
             break;
+        }
+        if (getenv("CA_PIPE_HOSTWAIT")) {
+            cudaEventSynchronize(c.up_ev[g]);
+            lap(g, "upload event (host wait)");
         }
         if (cudaStreamWaitEvent(s, c.up_ev[g], 0) != cudaSuccess) {
             set_error("cudaStreamWaitEvent failed");
@@ -1894,6 +1961,7 @@ static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols,
         }
         rc = ranks_stage_a(L);  // min / max, histograms, ranks of this group (its host syncs also end the previous group's kernels)
         if (rc != CA_OK) break;
+        lap(g, "stage A done");
         kmax_sofar = std::max(kmax_sofar, L.kmax);
         if (!engine_supports(kmax_sofar)) {
             bail = true;  // the plain path decides (pair-loop fallback)
@@ -1944,7 +2012,9 @@ static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols,
         if (rc != CA_OK) break;
         L.mpad = WL.mpad;
         L.ranked = L.prepared = true;
+        lap(g, "packed");
         rc = run_allpairs(L, weights, 0, 1, ecc_out ? d_ecc.as<double>() : nullptr, sim_out ? d_sim.as<double>() : nullptr, -1, 0, 0, /*finish_sync=*/false);
+        lap(g, "wave launched");
     }
     if (rc == CA_OK && !bail) {
         rc = launch_finish(ecc_out ? d_ecc.as<double>() : nullptr, n, ident_constant(weights, m), sim_out ? d_sim.as<double>() : nullptr, m, s);
@@ -1956,9 +2026,11 @@ static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols,
             set_error("pipelined path: device-to-host copy failed: %s", cudaGetErrorString(e));
             rc = CA_E_CUDA;
         }
+        lap(G, "results on the host");
     }
     std::string msg = g_err;
     cleanup();
+    lap(G, "released");
     if (rc != CA_OK) set_error("%s", msg.c_str());
     *handled = rc == CA_OK && !bail;
     return rc;
