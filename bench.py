@@ -289,8 +289,11 @@ def run_b200(args):
     del labels
     w = None if (weights is None or matrix_mode) else np.ascontiguousarray(weights, dtype=np.float64)
     dl = _capi.DeviceLabels(n, m).upload_pinned(host.data_ptr())  # sharded over the devices when ngpu > 1
-    ecc = np.empty(n, dtype=np.float64)
-    sim = np.empty((m, m), dtype=np.float64) if matrix_mode else None
+    # results land in pinned host memory (the contract's "device -> host read of the step's result")
+    ecc_t = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    ecc = ecc_t.numpy()
+    sim_t = torch.empty((m, m), dtype=torch.float64, pin_memory=True) if matrix_mode else None
+    sim = sim_t.numpy() if matrix_mode else None
 
     def sync_all():
         for d in range(ngpu):
@@ -343,7 +346,8 @@ def run_b200(args):
     # ---- e2e: host buffers in, host result out ----------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        out = np.empty((m, m) if matrix_mode else n, dtype=np.float64)
+        out_t = torch.empty((m, m) if matrix_mode else n, dtype=torch.float64, pin_memory=True)
+        out = out_t.numpy()
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e(out)
         ke = max(3, min(args.steps, 5))

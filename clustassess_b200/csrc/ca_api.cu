@@ -348,6 +348,10 @@ static int init_device(Dev& D, int device) {
         if (!c.ev[i]) CA_CUDA(cudaEventCreate(&c.ev[i]));
     if (!D.ev_lab) CA_CUDA(cudaEventCreateWithFlags(&D.ev_lab, cudaEventDisableTiming));
     if (!c.up_stream) CA_CUDA(cudaStreamCreateWithFlags(&c.up_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) {
+        if (!c.peer_stream[i]) CA_CUDA(cudaStreamCreateWithFlags(&c.peer_stream[i], cudaStreamNonBlocking));
+        if (!c.peer_ev[i]) CA_CUDA(cudaEventCreateWithFlags(&c.peer_ev[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 8; i++)
         if (!c.up_ev[i]) CA_CUDA(cudaEventCreateWithFlags(&c.up_ev[i], cudaEventDisableTiming));
     c.inited = true;
@@ -373,6 +377,10 @@ static void release_device(Dev& D) {
     for (int i = 0; i < 8; i++)
         if (D.c.up_ev[i]) { cudaEventDestroy(D.c.up_ev[i]); D.c.up_ev[i] = nullptr; }
     if (D.c.up_stream) { cudaStreamDestroy(D.c.up_stream); D.c.up_stream = nullptr; }
+    for (int i = 0; i < 4; i++) {
+        if (D.c.peer_ev[i]) { cudaEventDestroy(D.c.peer_ev[i]); D.c.peer_ev[i] = nullptr; }
+        if (D.c.peer_stream[i]) { cudaStreamDestroy(D.c.peer_stream[i]); D.c.peer_stream[i] = nullptr; }
+    }
     if (D.c.own_stream) { cudaStreamDestroy(D.c.own_stream); D.c.own_stream = nullptr; }
     D.c.stream = nullptr;
     D.c.inited = false;
@@ -996,6 +1004,9 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         CA_CUDA(cudaMemcpyAsync(W.items.p, W.h_items.p, (n_kind[0] + n_kind[1]) * sizeof(Item), cudaMemcpyHostToDevice, s));
 
     // ---- the wave kernel ----------------------------------------------------------------------------
+    // multi-GPU jobs: the stream waits here for the peers' stores (labels, cluster sizes) and builds the table templates; planning and
+    // sort ran meanwhile
+    if (before_wave) CA_TRY((*before_wave)());
     TileParams T;
     T.lab16 = L.lab16_all();
     T.n = n;
@@ -1044,7 +1055,6 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         }
         CA_TRY(launch_qinfo(T, W.parts.as<int32_t>(), nparts, s));
     }
-    if (before_wave) CA_TRY((*before_wave)());  // multi-GPU jobs: the stream waits here for the peers' label stores (planning and sort ran meanwhile)
     CA_CUDA(cudaEventRecord(c.ev[4], s));
     for (int kind = 1; kind >= 0; kind--) {  // the long streaming items first
         T.items = W.items.as<Item>() + (kind == 1 ? n_kind[0] : 0);
@@ -1156,7 +1166,6 @@ struct ca_labels {
     int32_t m = 0;
     std::vector<std::unique_ptr<Labels>> sh;
     std::vector<int32_t> owner_of_span;
-    PinnedBuf h_sizes_all, h_k_all;  // multi-GPU preparation: cluster sizes [m][kp] and counts [m] of the whole set, gathered on the host
 };
 namespace ca {
 Labels& labels_of(ca_labels_t* h) { return h->L; }
@@ -1261,12 +1270,19 @@ static int multi_allpairs(ca_labels* H, const double* weights, double* ecc_out, 
             }
         };
         auto t0 = std::chrono::steady_clock::now();
+        bool hook_called = false;
+        const bool dbg = getenv("CA_PIPE_DEBUG") != nullptr && (g == 0 || g == G - 1);
+        auto lap = [&](const char* what) {
+            if (dbg) fprintf(stderr, "[multi dev %d] %-28s %.3f ms\n", g, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        };
         if (need_prepare) {
             // ---- A ----
             fail(ranks_stage_a(L));
             if (my == CA_OK) fail(L.d_lab16.ensure((size_t)(n + 1) * mpad * 2));
             kmax_loc[g] = L.kmax;
+            lap("A done");
             bar.wait();
+            lap("A barrier");
             int32_t kmax_all = 0;
             for (int q = 0; q < G; q++) kmax_all = std::max(kmax_all, kmax_loc[q]);
             if (failed.load() == CA_OK && !engine_supports(kmax_all)) {
@@ -1276,57 +1292,69 @@ static int multi_allpairs(ca_labels* H, const double* weights, double* ecc_out, 
             // ---- B ----
             if (failed.load() == CA_OK) {
                 fail(ranks_stage_b(L, kmax_all));
-                if (g == 0 && my == CA_OK) {
-                    fail(H->h_sizes_all.ensure((size_t)m * L.kp * 4));
-                    fail(H->h_k_all.ensure((size_t)m * 4));
-                }
+                if (my == CA_OK) fail(L.d_sizes_g.ensure((size_t)m * L.kp * 4));
+                if (my == CA_OK) fail(L.d_kcount_g.ensure((size_t)m * 4));
             }
-            bar.wait();  // the host arrays exist
+            lap("B sizes");
+            bar.wait();  // every device's whole-set arrays exist
             if (failed.load() == CA_OK) {
-                for (int32_t k = 0; k < L.m; k++) {
-                    memcpy(H->h_sizes_all.as<int32_t>() + (size_t)L.gid[k] * L.kp, L.h_sizes.data() + (size_t)k * L.kp, (size_t)L.kp * 4);
-                    H->h_k_all.as<int32_t>()[L.gid[k]] = L.h_k[k];
-                }
                 if (L.m > 0) {
+                    // This device's rows of the size / count arrays go to EVERY device by peer stores (small).  Its slabs of the label
+                    // array are written locally by the transposition kernel and then copied into the peers' arrays by the DMA engines
+                    // (one 64 MB copy per span and peer, spread over four copy streams): SM-issued 16-byte stores into seven peers reached
+                    // 290 GB/s of NVLink egress, which put 3 ms in front of every wave kernel at 8 GPUs; the copy engines move the same
+                    // bytes at line rate while the SMs sort.  CA_PEER_STORES=1 restores the store path.
+                    static const bool by_stores = getenv("CA_PEER_STORES") != nullptr;
+                    SizeDst sd;
                     LabDst dst;
-                    dst.n = 0;
-                    dst.p[dst.n++] = L.d_lab16.as<uint16_t>();
-                    for (int q = 0; q < G; q++)
-                        if (q != g) dst.p[dst.n++] = H->sh[q]->d_lab16.as<uint16_t>();
+                    sd.n = dst.n = 0;
+                    for (int q = 0; q < G; q++) {
+                        const int qq = (g + q) % G;  // own memory first
+                        sd.sizes[sd.n] = H->sh[qq]->d_sizes_g.as<int32_t>();
+                        sd.kcount[sd.n++] = H->sh[qq]->d_kcount_g.as<int32_t>();
+                        if (by_stores || q == 0) dst.p[dst.n++] = H->sh[qq]->d_lab16.as<uint16_t>();
+                    }
+                    fail(launch_scatter_sizes(L.d_sizes.as<int32_t>(), L.d_kcount.as<int32_t>(), L.d_span.as<int32_t>(), L.m, L.kp, sd, s));
                     cudaError_t e = cudaEventRecord(c.ev[1], s);
-                    if (e == cudaSuccess)
+                    if (e == cudaSuccess && my == CA_OK)
                         fail(launch_relabel_transpose(L.d_raw, n, L.m, (int32_t)L.spans.size(), L.d_span.as<int32_t>(), L.d_min.as<int32_t>(),
                                                       L.identity ? nullptr : L.d_rank.as<uint32_t>(), L.d_roff.as<int64_t>(), L.d_kcount.as<int32_t>(), dst, s));
                     if (e == cudaSuccess) e = cudaEventRecord(c.ev[2], s);
+                    if (e == cudaSuccess && !by_stores && G > 1) {
+                        e = cudaEventRecord(c.peer_ev[0], s);  // the slabs are complete in this device's memory
+                        for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaStreamWaitEvent(c.peer_stream[k], c.peer_ev[0], 0);
+                        const size_t slab = (size_t)2 * 32 * (size_t)(n + 1);  // bytes of one span: two super-tiles of 32 (n + 1) bytes
+                        int k = 0;
+                        for (int q = 1; q < G && e == cudaSuccess; q++) {
+                            const int qq = (g + q) % G;
+                            for (size_t t = 0; t < L.spans.size() && e == cudaSuccess; t++, k++) {
+                                const size_t off = (size_t)L.spans[t] * slab;
+                                e = cudaMemcpyPeerAsync(static_cast<char*>(H->sh[qq]->d_lab16.p) + off, devs()[qq]->c.device, static_cast<const char*>(L.d_lab16.p) + off,
+                                                        c.device, slab, c.peer_stream[k & 3]);
+                            }
+                        }
+                        for (int k2 = 1; k2 < 4 && e == cudaSuccess; k2++) {  // stream 0 collects the others: one event tells the peers everything has landed
+                            e = cudaEventRecord(c.peer_ev[k2], c.peer_stream[k2]);
+                            if (e == cudaSuccess) e = cudaStreamWaitEvent(c.peer_stream[0], c.peer_ev[k2], 0);
+                        }
+                        if (e == cudaSuccess) e = cudaStreamWaitEvent(c.peer_stream[0], c.ev[2], 0);  // ... and the size stores issued on the main stream
+                        if (e == cudaSuccess) e = cudaEventRecord(D.ev_lab, c.peer_stream[0]);
+                    } else if (e == cudaSuccess) {
+                        e = cudaEventRecord(D.ev_lab, s);
+                    }
                     if (e != cudaSuccess) {
                         set_error("relabel/transpose into peer memory failed: %s", cudaGetErrorString(e));
                         fail(CA_E_CUDA);
                     }
-                }
-                // no host synchronisation: the event below is what the peers' streams wait for before their wave kernels
-                if (cudaEventRecord(D.ev_lab, s) != cudaSuccess) {
+                } else if (cudaEventRecord(D.ev_lab, s) != cudaSuccess) {  // nothing to send: the event still has to exist for the peers' waits
                     set_error("cudaEventRecord failed");
                     fail(CA_E_CUDA);
                 }
             }
-            bar.wait();  // all sizes are on the host, every device has recorded its label event
-            // ---- C ----
-            if (failed.load() == CA_OK) {
-                fail(L.d_sizes_g.ensure((size_t)m * L.kp * 4));
-                if (my == CA_OK) fail(L.d_kcount_g.ensure((size_t)m * 4));
-                if (my == CA_OK) {
-                    cudaError_t e = cudaMemcpyAsync(L.d_sizes_g.p, H->h_sizes_all.p, (size_t)m * L.kp * 4, cudaMemcpyHostToDevice, s);
-                    if (e == cudaSuccess) e = cudaMemcpyAsync(L.d_kcount_g.p, H->h_k_all.p, (size_t)m * 4, cudaMemcpyHostToDevice, s);
-                    if (e != cudaSuccess) {
-                        set_error("uploading the cluster sizes failed: %s", cudaGetErrorString(e));
-                        fail(CA_E_CUDA);
-                    }
-                }
-                if (my == CA_OK) fail(ranks_stage_c(L));
-                if (my == CA_OK) L.ranked = L.prepared = true;
-            }
+            lap("B peer stores queued");
         }
         const double prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        lap("C done");
         // ---- this device's pairs ----
         if (failed.load() == CA_OK) {
             if (ecc_out) fail(D.red_ecc.ensure((size_t)std::max<int64_t>(n, 1) * 8));
@@ -1340,17 +1368,40 @@ static int multi_allpairs(ca_labels* H, const double* weights, double* ecc_out, 
             }
             // the wave kernel reads every device's labels: its stream waits for all the label events (recorded above, or already
             // complete when the set was prepared by an earlier call); items and sort do not, they run while the stores are in flight
-            const std::function<int()> wait_labels = [&]() -> int {
+            // Everything the wave kernel reads from the peers -- compact labels, cluster sizes and counts -- arrives by their stores;
+            // its stream waits for all the peers' events (a host barrier first: an event must have been recorded before it can be waited
+            // for), then builds the table templates from the complete size arrays (stage C).  Items and sort need none of it: they
+            // were planned and queued while the stores were in flight.
+            const std::function<int()> wait_peers = [&]() -> int {
                 if (!need_prepare) return CA_OK;
+                hook_called = true;
+                bar.wait();
+                if (failed.load() != CA_OK) return failed.load();
                 for (int q = 0; q < G; q++)
                     if (q != g) CA_CUDA(cudaStreamWaitEvent(s, devs()[q]->ev_lab, 0));
+                CA_TRY(ranks_stage_c(L));
+                L.ranked = L.prepared = true;
                 return CA_OK;
             };
-            if (my == CA_OK && L.m > 0 && n > 0)
+            if (my == CA_OK && L.m > 0 && n > 0) {
+                L.prepared = need_prepare ? true : L.prepared;  // run_allpairs must not prepare a share on its own; stage C follows in the hook
                 fail(run_allpairs(L, weights, 0, 1, ecc_out ? D.red_ecc.as<double>() : nullptr, sim_out ? D.red_sim.as<double>() : nullptr, -1, 0,
-                                  plan_threads, /*finish_sync=*/false, &wait_labels));
+                                  plan_threads, /*finish_sync=*/false, &wait_peers));
+                if (my != CA_OK) L.prepared = L.ranked = false;
+            }
         }
+        if (need_prepare && !hook_called) {  // a device without pairs (or one that failed early) still meets the others at the barrier,
+            bar.wait();                       // and still builds its templates: a later call on the prepared set may give it work
+            if (failed.load() == CA_OK) {
+                for (int q = 0; q < G; q++)
+                    if (q != g && cudaStreamWaitEvent(s, devs()[q]->ev_lab, 0) != cudaSuccess) fail(CA_E_CUDA);
+                if (my == CA_OK) fail(ranks_stage_c(L));
+                if (my == CA_OK) L.ranked = L.prepared = true;
+            }
+        }
+        lap("wave queued");
         bar.wait();  // nobody enters the collective unless everybody will
+        lap("collective barrier");
         if (failed.load() != CA_OK) return my;
         // ---- reduction ----
         if (g_have_comms) {
@@ -1388,7 +1439,9 @@ static int multi_allpairs(ca_labels* H, const double* weights, double* ecc_out, 
             if (ecc_out && n > 0) CA_CUDA(cudaMemcpyAsync(ecc_out, D.red_ecc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
             if (sim_out) CA_CUDA(cudaMemcpyAsync(sim_out, D.red_sim.p, (size_t)m * m * 8, cudaMemcpyDeviceToHost, s));
         }
+        lap("reduce + finish queued");
         CA_CUDA(cudaStreamSynchronize(s));
+        lap("stream done");
         if (L.m > 0 && n > 0) CA_TRY(read_profile(c));
         if (need_prepare) c.prof[0] = prep_ms;  // stages A-C including their barriers (host clock)
         c.prof[6] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1693,8 +1746,6 @@ int ca_labels_destroy(ca_labels_t* h) {
     if (h->sharded) {
         if ((int)D.size() == (int)h->sh.size() && !D.empty() && D[0]->c.inited)
             for_each_device([&](int g) -> int { release_labels(*h->sh[g]); return CA_OK; });
-        h->h_sizes_all.release();
-        h->h_k_all.release();
     } else if (h->L.dev_index < (int)D.size() && D[h->L.dev_index]->c.inited) {
         DevScope scope(D[h->L.dev_index].get());
         release_labels(h->L);

@@ -36,6 +36,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;  // the stream everything is launched on
     cudaStream_t up_stream = nullptr;  // host -> device copies that run beside the kernels (pipelined host path)
     cudaEvent_t up_ev[8] = {};         // one per upload group
+    cudaStream_t peer_stream[4] = {};  // multi-GPU jobs: DMA copies of this device's label slabs into the peers' memory
+    cudaEvent_t peer_ev[4] = {};
     cudaEvent_t ev[10] = {};
     double prof[10] = {};
     long launches = 0;  // kernels launched since the counter was last reset
@@ -154,6 +156,13 @@ struct LabDst {  // the lab16 arrays a transposition stores into: the device's o
     uint16_t* p[CA_MAX_DEVICES];
     int n;
 };
+struct SizeDst {  // the whole-set cluster-size and cluster-count arrays of every device (sharded label sets)
+    int32_t* sizes[CA_MAX_DEVICES];
+    int32_t* kcount[CA_MAX_DEVICES];
+    int n;
+};
+int launch_scatter_sizes(const int32_t* sizes_loc, const int32_t* kcount_loc, const int32_t* d_span_of_block, int32_t m_loc, int32_t kp, const SizeDst& dst,
+                         cudaStream_t s);
 int launch_relabel_transpose(const int32_t* raw, int64_t n, int32_t m, int32_t nblocks, const int32_t* d_span_of_block, const int32_t* d_min,
                              const uint32_t* d_rank, const int64_t* d_roff, const int32_t* d_kcount, const LabDst& dst, cudaStream_t s);
 int launch_sort(const int32_t* raw, int64_t n, const int32_t* d_min, const uint32_t* d_rank, const int64_t* d_roff,

@@ -244,6 +244,27 @@ int launch_spack(const int32_t* d_sizes, const int32_t* d_kcount, int32_t m, int
     return CA_OK;
 }
 
+// Sharded label sets: a device's rows of the cluster-size array (and its cluster counts) go into the whole-set arrays of EVERY device
+// (peer stores).  Local partition k is global partition span_of_block[k / 32] * 32 + k % 32.
+__global__ void __launch_bounds__(256) scatter_sizes_kernel(const int32_t* __restrict__ sizes_loc, const int32_t* __restrict__ kcount_loc,
+                                                            const int32_t* __restrict__ span_of_block, int32_t kp, const SizeDst dst) {
+    const int k = blockIdx.x;
+    const int gid = span_of_block[k >> 5] * 32 + (k & 31);
+    const int32_t* src = sizes_loc + (int64_t)k * kp;
+    for (int d = 0; d < dst.n; d++) {
+        int32_t* o = dst.sizes[d] + (int64_t)gid * kp;
+        for (int w = threadIdx.x; w < kp; w += blockDim.x) o[w] = src[w];
+        if (threadIdx.x == 0) dst.kcount[d][gid] = kcount_loc[k];
+    }
+}
+int launch_scatter_sizes(const int32_t* sizes_loc, const int32_t* kcount_loc, const int32_t* d_span_of_block, int32_t m_loc, int32_t kp, const SizeDst& dst,
+                         cudaStream_t s) {
+    if (m_loc <= 0) return CA_OK;
+    scatter_sizes_kernel<<<(unsigned)m_loc, 256, 0, s>>>(sizes_loc, kcount_loc, d_span_of_block, kp, dst);
+    CA_CUDA(cudaGetLastError()); ca::ctx().launches++;
+    return CA_OK;
+}
+
 // Table templates for the wave kernel: partition p's template is its table row (K_p entries min(size, 65535) << 16,
 // then 1 << 16 up to the row stride round4(K_p + 1)) repeated for as many rows as fit into `tmpl_bytes` (at most
 // max_rows), so that ONE bulk copy of R * row bytes initialises a whole R-row table (size : count = 0 in every entry).

@@ -25,8 +25,12 @@
  *     bit-identical to the reference.  The BATCHED entries evaluate count / max as count * (1 / max) with a
  *     Newton-refined reciprocal (relative error < 1e-13) and sum in another order than the reference: set-level
  *     results (ecc, matrix, agreement) are within 1e-9 absolute of it, not bit-identical to it.
- *   - Set-level results are REPRODUCIBLE: the sums are accumulated as 64-bit fixed-point integers, so two runs -- on
- *     one GPU or sharded over several -- return identical bits.
+ *   - Set-level results are REPRODUCIBLE: the sums are accumulated as 64-bit fixed-point integers, so two runs of the same
+ *     call -- on one GPU or sharded over several, from resident labels or from host buffers -- return identical bits.
+ *     (Different calls, e.g. with and without the matrix or with and without weights, run different kernel instantiations
+ *     and may differ from each other in the last bits, far below the 1e-9 bound.)
+ *   - Host buffers: large jobs on one device overlap their upload with the computation (the partitions are uploaded in
+ *     groups from the last one down; owner i only meets partners j > i).  CA_NO_PIPELINE=1 disables that.
  *   - Cluster counts: the batched engine takes up to 24 799 clusters per partition; beyond that (any count that fits
  *     memory, like the reference) the single-device entries loop over the pairs with a hashed contingency table.
  */
