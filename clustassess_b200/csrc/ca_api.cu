@@ -1467,6 +1467,20 @@ int ca_init(const int* devices, int ndev) {
     const int zero = 0;
     return init_devices(&zero, 1);
 }
+// host-only: how a set of m partitions is dealt to ndev devices (the span -> device map of sharded label sets), for CPU tests
+int ca_plan_spans(int32_t m, int32_t ndev, int32_t* owner_out, int32_t cap) {
+    if (m < 1 || ndev < 1 || ndev > CA_MAX_DEVICES || !owner_out) {
+        set_error("ca_plan_spans: bad argument");
+        return CA_E_ARG;
+    }
+    const std::vector<int32_t> o = assign_spans(m, ndev);
+    if ((int32_t)o.size() > cap) {
+        set_error("ca_plan_spans: %d spans exceed cap=%d", (int)o.size(), cap);
+        return CA_E_ARG;
+    }
+    for (size_t i = 0; i < o.size(); i++) owner_out[i] = o[i];
+    return (int)o.size();
+}
 int ca_device_count(void) {
     auto& D = devs();
     return (!D.empty() && D[0]->c.inited) ? (int)D.size() : 0;

@@ -210,6 +210,10 @@ int ca_get_profile_dev(int device_index, double *ms_out, int cap); /* the same f
 int ca_plan_blocks(const int32_t *sizes, int32_t k, int32_t align, int32_t cap, int32_t max_rows,
                    int32_t *cstart, int32_t *crow, int32_t *items, int32_t max_items, int64_t *npos_out);
 
+/* How a sharded label set deals its 32-partition spans to the devices: owner_out[s] = index of the device that holds span s and
+ * runs the pairs (i, j > i) of its partitions i.  Returns the number of spans (<= cap) or a negative error.  Needs no GPU. */
+int ca_plan_spans(int32_t m, int32_t ndev, int32_t *owner_out, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,3 +127,34 @@ def test_compute_fails_loudly_without_a_device():
         ecs.element_sim_elscore([1, 1, 2], [2, 2, 2])
     with pytest.raises(_capi.ClustAssessError):
         ecs.element_consistency([[1, 1, 2], [2, 2, 2]])
+
+
+def test_span_sharding_of_the_in_library_multi_gpu_path():
+    """One process, several GPUs: partitions are dealt to devices in 32-partition spans, longest processing
+    time first on the pair counts sum_{i in span} (m - 1 - i).  Every span has exactly one owner, every device gets work when there
+    are enough spans, and the pair counts are balanced -- at config 5 (500 partitions, 8 devices) within 1 %."""
+    lib = _capi.lib()
+
+    def owners(m, g):
+        out = np.zeros((m + 31) // 32, dtype=np.int32)
+        ns = lib.ca_plan_spans(m, g, out, out.size)
+        assert ns == out.size
+        return out
+
+    def loads(m, g):
+        o = owners(m, g)
+        load = np.zeros(g, dtype=np.int64)
+        for i in range(m - 1):
+            load[o[i // 32]] += m - 1 - i
+        return o, load
+
+    o, load = loads(500, 8)
+    assert sorted(set(o.tolist())) == list(range(8)) and load.sum() == 500 * 499 // 2
+    assert load.max() / load.mean() < 1.01
+    assert all(sorted(np.flatnonzero(o == d).tolist()) == [d, 15 - d] for d in range(8))  # the zigzag of ca_shard_owner, at span granularity
+    for m, g, bound in [(1000, 8, 1.01), (1000, 4, 1.01), (500, 2, 1.01), (257, 3, 1.1), (100, 2, 1.1), (64, 2, 1.6)]:
+        o, load = loads(m, g)  # two spans on two devices (64, 2) cannot be balanced at span granularity: 3 : 1 pairs
+        assert o.min() >= 0 and o.max() < g and load.sum() == m * (m - 1) // 2
+        assert load.max() / load.mean() < bound, (m, g, load)
+    assert owners(33, 8).tolist()[0] != owners(33, 8).tolist()[1]  # two spans, two devices; the other six stay idle
+    assert lib.ca_plan_spans(0, 2, np.zeros(1, dtype=np.int32), 1) < 0 and lib.ca_plan_spans(100, 99, np.zeros(4, dtype=np.int32), 4) < 0
