@@ -672,7 +672,9 @@ bool is_pageable(const void* p) {
 }
 }  // namespace
 
-static int upload_segments(const UploadSeg* segs, size_t nseg, cudaStream_t s, int max_threads = Stager::MAXT) {
+// paced = true (the pipelined path): at most PACE_BATCH chunks are handed to the copy engine before it is allowed to run empty,
+// so that small copies other streams issue meanwhile are served between two batches (see upload_throttled).
+static int upload_segments(const UploadSeg* segs, size_t nseg, cudaStream_t s, int max_threads = Stager::MAXT, bool paced = false) {
     size_t total = 0;
     for (size_t i = 0; i < nseg; i++) total += segs[i].bytes;
     if (total == 0) return CA_OK;
@@ -697,16 +699,36 @@ static int upload_segments(const UploadSeg* segs, size_t nseg, cudaStream_t s, i
     const int device = D.c.device;
     std::atomic<size_t> next{0};
     std::atomic<int> failed{(int)cudaSuccess};
+    static const int PACE_BATCH = getenv("CA_PIPE_BATCH") ? std::max(1, atoi(getenv("CA_PIPE_BATCH"))) : 4;
+    std::mutex pace_mu;  // paced uploads: one thread at a time talks to the copy engine
+    cudaEvent_t pace_last = nullptr;
+    int pace_count = 0;
     auto work = [&](int t) {
         if (cudaError_t e0 = cudaSetDevice(device)) { failed = (int)e0; return; }
         int k = 0;
         for (size_t c; (c = next.fetch_add(1)) < chunks.size() && failed == (int)cudaSuccess; k ^= 1) {
-            cudaError_t e = S.used[t][k] ? cudaEventSynchronize(S.ev[t][k]) : cudaSuccess;  // the slot's previous DMA has read it
+            cudaError_t e = cudaSuccess;
+            if (S.used[t][k]) {  // the slot's previous DMA has read it
+                if (paced)
+                    while ((e = cudaEventQuery(S.ev[t][k])) == cudaErrorNotReady) std::this_thread::sleep_for(std::chrono::microseconds(20));
+                else
+                    e = cudaEventSynchronize(S.ev[t][k]);
+            }
             if (e == cudaSuccess) {
                 memcpy(S.slot(t, k), chunks[c].src, chunks[c].bytes);
-                e = cudaMemcpyAsync(chunks[c].dst, S.slot(t, k), chunks[c].bytes, cudaMemcpyHostToDevice, s);
+                std::unique_lock<std::mutex> lk(pace_mu, std::defer_lock);
+                if (paced) {
+                    lk.lock();
+                    if (pace_count >= PACE_BATCH) {  // let the engine drain
+                        while ((e = cudaEventQuery(pace_last)) == cudaErrorNotReady) std::this_thread::sleep_for(std::chrono::microseconds(20));
+                        pace_count = 0;
+                    }
+                }
+                if (e == cudaSuccess) e = cudaMemcpyAsync(chunks[c].dst, S.slot(t, k), chunks[c].bytes, cudaMemcpyHostToDevice, s);
+                if (e == cudaSuccess) e = cudaEventRecord(S.ev[t][k], s);
+                pace_last = S.ev[t][k];
+                pace_count++;
             }
-            if (e == cudaSuccess) e = cudaEventRecord(S.ev[t][k], s);
             if (e != cudaSuccess) { failed = (int)e; return; }
             S.used[t][k] = true;
         }
@@ -1830,7 +1852,8 @@ static int set_allpairs(ca_labels_t* h, const double* weights, double* ecc_out, 
 // shares all live on this device: as soon as its upload event fires it is packed (ranks, sizes, templates, its slabs of the compact
 // label array -- all into the whole-set arrays of the container) and the pairs of ITS owners against every partition above them run
 // as one launch set of the wave kernel.  The work available after a fraction f of the upload is f^2 of the job, so the engine stops
-// waiting after the first few milliseconds.  Partner rows of the sizes / template arrays have one stride for the whole job; it is
+// waiting after the first few milliseconds (pageable sources, which upload at half the rate, get six finer groups).  Partner rows
+// of the sizes / template arrays have one stride for the whole job; it is
 // fixed from the first group with a 2x margin, and a later group that needs more makes the function bail out (handled = false)
 // so that the caller takes the plain path.  Results are bit-identical to the plain path (integer sums).
 // A host -> device copy that leaves room for others: the DMA engine serves copies in the order they were SUBMITTED, whatever
@@ -1840,12 +1863,14 @@ static int set_allpairs(ca_labels_t* h, const double* weights, double* ecc_out, 
 // it is short (four 8 MB pieces in flight: still 16.7 ms, the engine only switches channels when the active one idles).
 // Pinned sources therefore go out in 16 MB pieces, ONE in flight: the few microseconds between two pieces are where the small
 // copies get in (measured at config 5: 247 -> 220 ms end to end; CA_PIPE_DEPTH / CA_PIPE_PIECE_MB to experiment).  Pageable
-// sources are staged through the pinned slots of upload_segments.
+// sources are staged through the pinned slots of upload_segments in its paced mode, which lets the engine run empty after every
+// four 4 MB chunks for the same reason (eight staging threads keep the queue full otherwise, and the groups' wave kernels -- whose
+// item lists are small copies -- did not start before the whole upload had finished: 256 -> 225 ms; CA_PIPE_BATCH, CA_PIPE_UNPACED).
 static int upload_throttled(const UploadSeg* segs, size_t nseg, cudaStream_t s, int max_threads) {
     bool pinned = true;
     for (size_t i = 0; i < nseg; i++)
         if (segs[i].bytes && is_pageable(segs[i].src)) pinned = false;
-    if (!pinned) return upload_segments(segs, nseg, s, max_threads);
+    if (!pinned) return upload_segments(segs, nseg, s, max_threads, /*paced=*/getenv("CA_PIPE_UNPACED") == nullptr);
     static const size_t PIECE = (size_t)(getenv("CA_PIPE_PIECE_MB") ? atoi(getenv("CA_PIPE_PIECE_MB")) : 16) << 20;
     static const int DEPTH_ENV = getenv("CA_PIPE_DEPTH") ? atoi(getenv("CA_PIPE_DEPTH")) : 1;
     constexpr int MAXDEPTH = 8;
@@ -1887,9 +1912,23 @@ static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols,
     Dev& D = cur();
     Ctx& c = D.c;
     cudaStream_t s = c.stream;
-    // groups of spans from the top: 1, 2, 4, then the rest
+    // Groups of spans from the top.  Pinned sources cross PCIe at the link rate (36 ms for config 5's 2 GB): 1, 2, 4 spans, then the rest --
+    // the engine stops waiting after the third group.  Pageable sources (R's vectors) are staged through pinned slots by host threads
+    // at about half that rate, so the LAST group must not hold most of the work: six groups of nspan x (1, 2, 3, 3, 3, 4) / 16, which leaves
+    // 44 % of the pairs instead of 82 % for after the upload.
+    const bool pageable_src = is_pageable(labels ? (const void*)labels : (const void*)cols[m - 1]);
     std::vector<std::pair<int32_t, int32_t>> groups;  // [first span, last span + 1)
-    {
+    const bool fine = getenv("CA_PIPE_FINE") ? atoi(getenv("CA_PIPE_FINE")) != 0 : pageable_src;
+    if (fine && nspan >= 16) {
+        const int parts16[5] = {1, 2, 3, 3, 3};
+        int32_t hi = nspan;
+        for (int k = 0; k < 5; k++) {
+            const int32_t sz = std::max(1, nspan * parts16[k] / 16);
+            groups.push_back({hi - sz, hi});
+            hi -= sz;
+        }
+        groups.push_back({0, hi});
+    } else {
         int32_t hi = nspan, sz = 1;
         while (hi > 0 && (int)groups.size() < 3 && hi - sz >= nspan / 2) {
             groups.push_back({hi - sz, hi});
