@@ -13,6 +13,7 @@
 #include <condition_variable>
 #include <functional>
 #include <memory>
+#include <cmath>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -1055,6 +1056,18 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     T.sim = reinterpret_cast<unsigned long long*>(d_sim);
     T.sim_magic = sim_fix_magic(n);
     T.sim_scale = sim_fix_scale(n);
+    // The matrix from the table entries or from the cells?  Reading the tables costs about (ceil(K / 32) * 42 + 30) warp
+    // instructions per (partner, row), i.e. per n / K cells; the per-cell way costs about 8 per 32 (cell, partner) units on top of
+    // a gather that element_sim_matrix (no ecc) would not need at all (17 more).  CA_SIM_SCAN=0/1 forces one of them.
+    T.sim_scan = 0;
+    if (d_sim) {
+        if (const char* e = getenv("CA_SIM_SCAN")) {
+            T.sim_scan = atoi(e) != 0;
+        } else {
+            const double est = (std::ceil(L.kmax / 32.0) * 42.0 + 30.0) * 32.0 * (double)std::max(L.kmax, 1) / (double)n;
+            T.sim_scan = est < (d_ecc ? 6.0 : 18.0);
+        }
+    }
     T.perm_stride = perm_stride;
     T.m = m;
     T.mpad = L.mpad;

@@ -219,6 +219,7 @@ struct TileParams {
     unsigned long long* sim;  // [m*m] fixed-point sums of ECS over the cells (units of 1 / sim_fix_scale(n)) (may be null)
     double sim_magic;         // 1.5 * 2^(52 - F): (v + sim_magic) - sim_magic rounds v to the grid 2^-F (sim_fix_magic(n))
     double sim_scale;         // 2^F (sim_fix_scale(n))
+    int32_t sim_scan;         // the matrix entries are summed over the table entries (few clusters) instead of per (cell, partner), ca_tile.cu scan_sim
     int64_t perm_stride;
     int32_t m, mpad, kp;
     int32_t nsuper, nwu;      // super-tiles, work units

@@ -363,6 +363,58 @@ __device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, 
         sts_b64(simacc + t * 8u, 0ull);
     }
 }
+// ---- the ECS matrix from the TABLES (P.sim_scan: partitions with few clusters) -----------------------------------------------
+// sum_n ECS_ij[n] = sum_{a,b} T[a][b]^2 / max(S_i[a], S_j[b]) -- the reference's own formula for the average of a pair
+// (disjointECSaverage, src/calculate_ecs.cpp:58-67): every non-empty table entry stands for T[a][b] cells with the same ratio.
+// With K clusters a table row has K entries but n / K cells, so for small K reading the finished tables is far cheaper than
+// rounding and reducing one term per (cell, partner) in the gather (element_sim_matrix then needs no gather at all).  The
+// consumer warps share the (partner, row) pairs of the phase; a warp's lanes stride over the row's columns.  The row's own
+// cluster size is the sum of its counts (every cell of the cluster sits in exactly one real column; padding positions sit in
+// the pad column K_j, which is not read).  Every term is converted to fixed point on its own and the integers are added, so
+// the result does not depend on which warp or block reads which row.  WIDE: 32-bit counters, partner sizes from global memory.
+template <bool WIDE>
+__device__ __forceinline__ void scan_sim(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, int R, uint32_t sa_item,
+                                         int wc, int nw, int lane) {
+    const uint32_t kk = lane < 8 ? (uint32_t)__ldg(P.kinfo + ph.j0 + lane) : 0u;  // K_j | flags of the tile's partners
+    const int npairs = ph.cnt * R;
+#pragma unroll 1
+    for (int q = wc; q < npairs; q += nw) {  // warp-uniform
+        const int sl = q / R, row = q - sl * R, jt = ph.g0 + sl;
+        const uint32_t K = __shfl_sync(FULL, kk, jt) & 0xffffffu;
+        const uint2 tr = lds_u64(meta + META_TR + jt * 8);
+        const uint32_t rb = tr.x + (uint32_t)row * tr.y;
+        uint32_t sa = sa_item;
+        if (sa == 0u) {
+            uint32_t cs = 0u;
+            for (uint32_t col = (uint32_t)lane; col < K; col += 32u) {
+                const uint32_t e = lds_u32(rb + col * 4u);
+                cs += WIDE ? e : (e & 0xffffu);
+            }
+            sa = __reduce_add_sync(FULL, cs);
+            if (sa == 0u) continue;  // warp-uniform
+        }
+        const int32_t* szg = P.sizes + (int64_t)(ph.j0 + jt) * P.kp;
+        unsigned long long sum = 0ull;
+        for (uint32_t col = (uint32_t)lane; col < K; col += 32u) {
+            const uint32_t e = lds_u32(rb + col * 4u);
+            const uint32_t count = WIDE ? e : (e & 0xffffu);
+            if (count != 0u) {
+                uint32_t sb = WIDE ? 0xffffu : (e >> 16);
+                if (sb == 0xffffu) sb = (uint32_t)__ldg(szg + col);
+                const double mx = u32_to_f64(max(sa, sb));
+                double r;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mx));
+                r = fma(fma(-mx, r, 1.0), r, r);
+                const double c = u32_to_f64(count);
+                sum += to_fix((c * c) * r, P.sim_scale);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        if (lane == 0 && sum != 0ull) red_add_u64(simacc + (uint32_t)jt * 8u, sum);
+    }
+}
+
 // a cell's sum over the partners of a work unit (already scaled by w_i / norm) joins its fixed-point accumulator
 __device__ __forceinline__ void ecc_add(const TileParams& P, int cell, double v) {
     atomicAdd(P.ecc + cell, to_fix(v, ECC_FIX_SCALE));
@@ -628,6 +680,8 @@ __device__ __forceinline__ void consume_resident(const TileParams& P, const uint
     uint32_t vmask = 0;
     bool wactive = false;
     uint32_t rowidx = 0, sa = 0;
+    int nrows = 1;          // WANT_SIM: table rows of the item
+    uint32_t sa_item = 0;   // WANT_SIM: the cluster size of a single-row item (0 = several rows: scan_sim sums the row)
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     uint4 L[4], Lh[4];  // labels of the current tile for this thread's quad; Lh: the super-tile's upper tile
     int cur_j0 = -1;
@@ -663,6 +717,10 @@ __device__ __forceinline__ void consume_resident(const TileParams& P, const uint
             const uint2 w0 = lds_u64(wurec + WU_M), w1 = lds_u64(wurec + WU_NPOS), w2 = lds_u64(wurec + WU_SA);
             m = (int)w0.x;
             const int npos = (int)w1.x;
+            if (WANT_SIM) {
+                nrows = (int)(w1.y & 0xffffu);
+                sa_item = nrows == 1 ? w2.x : 0u;
+            }
             const int64_t off = (int64_t)w2.y * P.perm_stride + (int)w0.y;
             cur_j0 = -1;
             cell = make_int4(-1, -1, -1, -1);
@@ -699,7 +757,11 @@ __device__ __forceinline__ void consume_resident(const TileParams& P, const uint
         if (!CA_DBG(P, 5)) consumer_sync<NC_RES>();  // the tables of phase p are complete; every consumer has left phase p-1
         if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
         // ---- gather ----
-        if (wactive && !CA_DBG(P, 4)) gather_cells<4, false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, rowidx, sa, vmask, 1, lane, acc);
+        if (WANT_SIM && P.sim_scan) {  // the matrix from the tables; per-cell sums only when ecc is wanted
+            scan_sim<false>(P, meta, simacc, ph, nrows, sa_item, warp - 1, NC_RES / 32, lane);
+            if (WANT_ECC && wactive) gather_cells<4, false, false, UNITW>(P, meta, simacc, ph, big, L, rowidx, sa, vmask, 1, lane, acc);
+        } else if (wactive && !CA_DBG(P, 4))
+            gather_cells<4, false, WANT_SIM, UNITW>(P, meta, simacc, ph, big, L, rowidx, sa, vmask, 1, lane, acc);
         prev = ph;
         prev_m = m;
         __syncwarp();
@@ -928,28 +990,40 @@ __device__ __forceinline__ void consume_streaming(const TileParams& P, const uin
         consumer_sync<NC_STR>();
         if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
         // ---- gather ----
-        if (npos <= 2 * SCHUNK) {
+        auto gather_item = [&](auto simcell) {  // simcell: the matrix terms are formed per (cell, partner) in the gather
+            constexpr bool SC = decltype(simcell)::value;
+            if (npos <= 2 * SCHUNK) {
 #pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-                if (hh && !second) break;  // warp-uniform
-                const int4 cl = hh ? cell2 : cell;
-                double a4[4] = {0.0, 0.0, 0.0, 0.0};
-                gather_cells<4, false, WANT_SIM, UNITW>(P, meta, simacc, ph, h.big, hh ? Lh : L, 0u, sa, vmask_of(cl), 1, lane, a4);
-                flush4(cl, a4);
+                for (int hh = 0; hh < 2; hh++) {
+                    if (hh && !second) break;  // warp-uniform
+                    const int4 cl = hh ? cell2 : cell;
+                    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+                    gather_cells<4, false, SC, UNITW>(P, meta, simacc, ph, h.big, hh ? Lh : L, 0u, sa, vmask_of(cl), 1, lane, a4);
+                    flush4(cl, a4);
+                }
+            } else {
+                for (int cb0 = 0; cb0 < npos; cb0 += SCHUNK) {  // block-uniform trip count: gather_cells shuffles when SC
+                    const int cb = cb0 + tid * 4;
+                    int4 cl = make_int4(-1, -1, -1, -1);
+                    if (cb < npos) cl = __ldg(reinterpret_cast<const int4*>(perm + cb));
+                    load_quad(labj, (uint32_t)P.n, cl, L);
+                    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (wide)
+                        gather_cells<4, true, SC, UNITW>(P, meta, simacc, ph, h.big, L, 0u, sa, vmask_of(cl), 1, lane, a4);
+                    else
+                        gather_cells<4, false, SC, UNITW>(P, meta, simacc, ph, h.big, L, 0u, sa, vmask_of(cl), 1, lane, a4);
+                    flush4(cl, a4);
+                }
             }
+        };
+        if (WANT_SIM && P.sim_scan) {  // the matrix from the tables (one row per partner here)
+            if (wide)
+                scan_sim<true>(P, meta, simacc, ph, 1, sa, warp - 1, NC_STR / 32, lane);
+            else
+                scan_sim<false>(P, meta, simacc, ph, 1, sa, warp - 1, NC_STR / 32, lane);
+            if (WANT_ECC) gather_item(Slot<0>{});
         } else {
-            for (int cb0 = 0; cb0 < npos; cb0 += SCHUNK) {  // block-uniform trip count: gather_cells shuffles when WANT_SIM
-                const int cb = cb0 + tid * 4;
-                int4 cl = make_int4(-1, -1, -1, -1);
-                if (cb < npos) cl = __ldg(reinterpret_cast<const int4*>(perm + cb));
-                load_quad(labj, (uint32_t)P.n, cl, L);
-                double a4[4] = {0.0, 0.0, 0.0, 0.0};
-                if (wide)
-                    gather_cells<4, true, WANT_SIM, UNITW>(P, meta, simacc, ph, h.big, L, 0u, sa, vmask_of(cl), 1, lane, a4);
-                else
-                    gather_cells<4, false, WANT_SIM, UNITW>(P, meta, simacc, ph, h.big, L, 0u, sa, vmask_of(cl), 1, lane, a4);
-                flush4(cl, a4);
-            }
+            gather_item(Slot<WANT_SIM ? 1 : 0>{});
         }
         prev = ph;
         prev_m = m;

@@ -684,3 +684,44 @@ def test_pipelined_host_path_bails_out_when_later_groups_have_many_more_clusters
     pj = np.array([6, 40, 100, 200, 254, 255, 5, 255, 255])
     _, _, means, _ = oracle.pairs_detail(L, pi, pj, nthreads=4)
     assert np.abs(got[pi, pj] - means).max() < TOL and np.array_equal(got, got.T)
+
+
+@pytest.mark.parametrize("shape", ["few clusters", "many clusters", "giant clusters"])
+def test_matrix_from_table_entries_equals_matrix_from_cells(monkeypatch, shape):
+    """The ECS matrix has two routes through the wave kernel: summed over the non-empty TABLE entries, T^2 / max(S_a, S_b) -- the
+    reference's own formula for a pair's average (src/calculate_ecs.cpp:58-67), taken when the partitions have few clusters --
+    or per (cell, partner) in the gather.  Both against the oracle, against each other, with and without ecc, weighted and not;
+    the table route twice for identical bits.  'giant clusters': a partner cluster of >= 65535 cells (size looked up in global
+    memory) and an owner cluster of > 65535 cells (streaming item with 32-bit counters)."""
+    rng = np.random.default_rng(91)
+    if shape == "few clusters":
+        L = _louvainish(24, 6000, 5, 15, seed=92)
+    elif shape == "many clusters":
+        L = _louvainish(12, 20_000, 250, 400, seed=93)
+    else:
+        n = 200_000
+        L = _louvainish(10, n, 8, 20, seed=94)
+        L[0] = np.where(rng.random(n) < 0.75, 1, L[0] + 1)      # one cluster of ~150k cells in the first owner
+        L[7] = np.where(rng.random(n) < 0.40, 3, L[7] + 5)      # ~80k cells in a partner
+    m, n = L.shape
+    w = (1 + rng.poisson(1.0, size=m)).astype(np.float64)
+    cols = [np.ascontiguousarray(r) for r in L]
+    pi, pj = np.triu_indices(m, k=1)
+    _, _, means, _ = oracle.pairs_detail(L, pi, pj, nthreads=_host_threads())
+    ecc_ref, sim_ref = oracle.weighted_element_consistency(L, w, calculate_sim_matrix=True)
+    got = {}
+    for scan in ("0", "1"):
+        monkeypatch.setenv("CA_SIM_SCAN", scan)
+        got[scan] = (ecs.element_sim_matrix(cols), ecs.weighted_element_consistency(cols, weights=w, calculate_sim_matrix=True),
+                     ecs.weighted_element_consistency(cols, calculate_sim_matrix=True))
+        sim, wres, ures = got[scan]
+        assert np.abs(sim[pi, pj] - means).max() < TOL and np.array_equal(sim, sim.T) and np.all(np.diag(sim) == 1.0)
+        assert np.abs(wres["ecs_matrix"] - sim_ref).max() < TOL and np.abs(wres["ecc"] - ecc_ref).max() < TOL
+        assert np.abs(ures["ecs_matrix"] - sim).max() < 1e-12
+    assert np.abs(got["0"][0] - got["1"][0]).max() < 1e-12
+    assert np.abs(got["0"][1]["ecc"] - got["1"][1]["ecc"]).max() < 1e-13
+    again = ecs.element_sim_matrix(cols)  # CA_SIM_SCAN is still 1
+    assert np.array_equal(again, got["1"][0])
+    monkeypatch.delenv("CA_SIM_SCAN")
+    chosen = ecs.element_sim_matrix(cols)  # the library's own choice is one of the two
+    assert np.array_equal(chosen, got["0"][0]) or np.array_equal(chosen, got["1"][0])
