@@ -787,8 +787,20 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     auto lap = [&](const char* what) {
         if (plan_dbg) fprintf(stderr, "[plan dev %d] %-28s %.3f ms\n", c.device, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count());
     };
+    // Ratio tables (ca_tile.cu, convert_tables): one division per table ENTRY and a gather that only adds, instead of a ratio per
+    // (cell, partner).  Measured (tools/sim_scan_sweep.py, profiles/r2_table_routes.txt): the extra pass and barrier per phase cost
+    // what the shorter gather saves -- except where clusters are HUGE (few clusters, many cells: 64 x 1M cells with K = 8 .. 64,
+    // 14.1 -> 9.5 ms): there most partners have clusters beyond the 16-bit size field and most owner clusters need 32-bit
+    // counters, and the plain gather looks every size up in global memory.  So: few clusters of more than 8192 cells on average.
+    // Needs ecc (the matrix alone has no gather).  CA_RT=0/1 forces it off / on.
+    bool use_rt = d_ecc != nullptr && L.kmax <= 96 && (int64_t)L.kmax * 8192 <= n;
+    if (const char* e = getenv("CA_RT")) use_rt = d_ecc != nullptr && atoi(e) != 0;
     int32_t max_rows = 0;
-    const int smem_bytes = tile_smem_budget(L.kmax, &max_rows);
+    int smem_bytes = tile_smem_budget(L.kmax, &max_rows, nullptr, use_rt);
+    if (use_rt && max_rows < 1) {
+        use_rt = false;
+        smem_bytes = tile_smem_budget(L.kmax, &max_rows);
+    }
     if (max_rows < 1) {
         set_error("%d clusters per partition need more shared memory per table row than one SM has", L.kmax);
         return CA_E_UNSUPPORTED;
@@ -1059,8 +1071,9 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     // The matrix from the table entries or from the cells?  Reading the tables costs about (ceil(K / 32) * 42 + 30) warp
     // instructions per (partner, row), i.e. per n / K cells; the per-cell way costs about 8 per 32 (cell, partner) units on top of
     // a gather that element_sim_matrix (no ecc) would not need at all (17 more).  CA_SIM_SCAN=0/1 forces one of them.
+    T.rt = use_rt ? 1 : 0;
     T.sim_scan = 0;
-    if (d_sim) {
+    if (d_sim && !use_rt) {  // (ratio-table launches sum the matrix while they convert the tables)
         if (const char* e = getenv("CA_SIM_SCAN")) {
             T.sim_scan = atoi(e) != 0;
         } else {

@@ -219,6 +219,7 @@ struct TileParams {
     unsigned long long* sim;  // [m*m] fixed-point sums of ECS over the cells (units of 1 / sim_fix_scale(n)) (may be null)
     double sim_magic;         // 1.5 * 2^(52 - F): (v + sim_magic) - sim_magic rounds v to the grid 2^-F (sim_fix_magic(n))
     double sim_scale;         // 2^F (sim_fix_scale(n))
+    int32_t rt;               // ratio tables: one division per table entry, the gather adds finished ratios (few clusters; ca_tile.cu convert_tables)
     int32_t sim_scan;         // the matrix entries are summed over the table entries (few clusters) instead of per (cell, partner), ca_tile.cu scan_sim
     int64_t perm_stride;
     int32_t m, mpad, kp;
@@ -232,7 +233,7 @@ struct TileParams {
 };
 int launch_tile(const TileParams& p, cudaStream_t s);
 int launch_qinfo(const TileParams& p, const int32_t* d_parts, int32_t nparts, cudaStream_t s);
-int tile_smem_budget(int32_t kmax, int32_t* max_rows_out, int32_t* half_out = nullptr);
+int tile_smem_budget(int32_t kmax, int32_t* max_rows_out, int32_t* half_out = nullptr, bool rt = false);
 
 // ca_pair.cu
 int pair_contingency(const int32_t* d_a, const int32_t* d_b, int64_t n, int32_t min_a, int32_t min_b, int32_t ka,

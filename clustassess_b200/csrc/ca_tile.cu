@@ -44,6 +44,11 @@
 //     stream the cells from global memory in both passes; labels are loaded per 8-partner tile (16 bytes per cell), sums
 //     are added per phase.  More than 65535 cells: plain 32-bit counters, partner sizes from global memory.
 //
+// The ECS matrix (mean of a pair's ECS) has two routes, chosen per job by the host (TileParams::sim_scan): per (cell, partner) in
+// the gather, or -- partitions with few clusters -- summed over the non-empty table entries after the histogram (scan_sim), in
+// which case element_sim_matrix runs no gather at all.  A third set of instantiations (RT, TileParams::rt) serves jobs with few
+// but huge clusters: one division per table entry into a table of doubles, and a gather that only adds (convert_tables).
+//
 // The division is T * r with r = 1/max from rcp.approx.ftz.f64 + one Newton step (relative error < 1e-13);
 // the batched path has to meet 1e-9 absolute, the per-pair entry points (ca_pair.cu) keep the IEEE division.
 // Sums leave the kernel as 64-bit fixed-point integers (ca_internal.h): integer atomics make the result independent
@@ -87,6 +92,8 @@ static constexpr int SM_PLANW = 960;    //   bytes inside the 8-partner tile}; [
 static constexpr int SM_DYN = 1280;     // two table buffers
 static_assert(SM_WUREC + 2 * WUREC_BYTES <= SM_PLAN && SM_PLAN + 256 <= SM_PLANW && SM_PLANW + 256 <= SM_DYN, "shared-memory map");
 static constexpr uint32_t KK_BIG = 1u << 30;  // partner has a cluster with >= 65535 cells
+// ratio-table launches (RT): bytes of a table buffer the count tables may use; the ratio tables (8 bytes per entry) follow them
+__host__ __device__ __forceinline__ int rt_count_bytes(int half) { return (half / 3) & ~127; }
 
 // ---- shared-space accessors ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -415,6 +422,73 @@ __device__ __forceinline__ void scan_sim(const TileParams& P, uint32_t meta, uin
     }
 }
 
+// ---- ratio tables (RT kernels: partitions with few clusters) ------------------------------------------------------------------
+// With K clusters a table has R x K entries for the item's ~n R / K cells, so for small K the ratio T[a][b] / max(S_a, S_b) is
+// computed once per ENTRY instead of once per (cell, partner): after the histogram the consumer warps share the (partner, row)
+// pairs of the phase and write, next to every count table, a table of doubles holding the finished ratio (IEEE division: each
+// term is bit-identical to the reference's (double) T / max, src/calculate_ecs.cpp:35); after a second barrier the gather is one
+// 8-byte shared load and one add per (cell, partner) instead of a load and 14 arithmetic instructions.  The count tables get a
+// third of the buffer, the ratio tables the rest: ratio entry address = rbase + 2 * (count entry address - cbase).  The pad
+// column gets 0 (padding positions read it).  The ECS matrix comes from the same pass (sum of T * ratio over the entries).
+template <bool WIDE, bool WANT_SIM>
+__device__ __forceinline__ void convert_tables(const TileParams& P, uint32_t meta, uint32_t simacc, const Phase ph, int R, uint32_t sa_item,
+                                               uint32_t cbase, uint32_t rbase, int wc, int nw, int lane) {
+    const uint32_t kk = lane < 8 ? (uint32_t)__ldg(P.kinfo + ph.j0 + lane) : 0u;  // K_j | flags of the tile's partners
+    const int npairs = ph.cnt * R;
+#pragma unroll 1
+    for (int q = wc; q < npairs; q += nw) {  // warp-uniform
+        const int sl = q / R, row = q - sl * R, jt = ph.g0 + sl;
+        const uint32_t K = __shfl_sync(FULL, kk, jt) & 0xffffffu;
+        const uint2 tr = lds_u64(meta + META_TR + jt * 8);
+        const uint32_t rb = tr.x + (uint32_t)row * tr.y;
+        const uint32_t rr = rbase + (rb - cbase) * 2u;
+        uint32_t sa = sa_item;
+        if (sa == 0u) {  // the row's cluster size = the sum of its counts
+            uint32_t cs = 0u;
+            for (uint32_t col = (uint32_t)lane; col < K; col += 32u) {
+                const uint32_t e = lds_u32(rb + col * 4u);
+                cs += WIDE ? e : (e & 0xffffu);
+            }
+            sa = __reduce_add_sync(FULL, cs);
+        }
+        const int32_t* szg = P.sizes + (int64_t)(ph.j0 + jt) * P.kp;
+        unsigned long long sum = 0ull;
+        for (uint32_t col = (uint32_t)lane; col <= K; col += 32u) {
+            const uint32_t e = lds_u32(rb + col * 4u);
+            const uint32_t count = WIDE ? e : (e & 0xffffu);
+            double v = 0.0;
+            if (count != 0u && col < K) {
+                uint32_t sb = WIDE ? 0xffffu : (e >> 16);
+                if (sb == 0xffffu) sb = (uint32_t)__ldg(szg + col);
+                const double c = u32_to_f64(count);
+                v = __ddiv_rn(c, u32_to_f64(max(sa, sb)));
+                if (WANT_SIM) sum += to_fix(c * v, P.sim_scale);
+            }
+            sts_f64(rr + col * 8u, v);
+        }
+        if (WANT_SIM) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+            if (lane == 0 && sum != 0ull) red_add_u64(simacc + (uint32_t)jt * 8u, sum);
+        }
+    }
+}
+template <bool UNITW>
+__device__ __forceinline__ void gather_ratio(const TileParams& P, uint32_t meta, const Phase ph, const uint4 (&L)[4], uint32_t rowidx,
+                                             uint32_t cbase, uint32_t rbase, double (&acc)[4]) {
+    for_slots(ph.g0, ph.cnt, [&](auto slot) {
+        constexpr int JT = decltype(slot)::value;
+        const uint2 tr = lds_u64(meta + META_TR + JT * 8);
+        const uint32_t rr = rbase + (tr.x - cbase + rowidx * tr.y) * 2u;
+        const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + JT * 8);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double v = lds_f64(rr + slot_label<JT>(P, L[c]) * 8u);
+            acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
+        }
+    });
+}
+
 // a cell's sum over the partners of a work unit (already scaled by w_i / norm) joins its fixed-point accumulator
 __device__ __forceinline__ void ecc_add(const TileParams& P, int cell, double v) {
     atomicAdd(P.ecc + cell, to_fix(v, ECC_FIX_SCALE));
@@ -625,14 +699,14 @@ __device__ __forceinline__ void plan_advance(const TileParams& P, Planner& pl, c
 }
 
 template <bool UNITW>
-__device__ __forceinline__ void producer_loop(const TileParams& P, uint32_t sbase, int half, int lane) {
-    Planner pl;
+__device__ __forceinline__ void producer_loop(const TileParams& P, uint32_t sbase, int half, int budget, int lane) {
+    Planner pl;  // budget = bytes of a buffer the count tables may use (all of it, or a third when ratio tables follow them)
     planner_init(P, pl, lane, sbase);
     for (uint32_t p = 0;; p++) {
         const uint32_t b = p & 1u;
         const bool last = pl.w >= P.nwu;
         PhasePlan pp;
-        if (!last) pp = plan_compute(P, sbase, half, lane, pl);
+        if (!last) pp = plan_compute(P, sbase, budget, lane, pl);
         if (p >= 2) mbar_wait<true>(sbase + SM_MBAR + 16 + b * 8u, ((p >> 1) - 1u) & 1u);  // consumers are done with buffer b
         if (last) {
             plan_terminal(sbase, b, lane);
@@ -673,8 +747,10 @@ __device__ __forceinline__ PhaseHdr read_hdr(uint32_t sbase, uint32_t meta) {
 // ---- resident items: a quad of consecutive positions per thread -------------------------------------------------
 // The plain consumer: the 16 labels of a cell for a whole super-tile come with ONE 32-byte load when the work unit reaches
 // the super-tile (L = its lower tile, Lh = its upper tile).
-template <bool WANT_ECC, bool WANT_SIM, bool UNITW>
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool RT>
 __device__ __forceinline__ void consume_resident(const TileParams& P, const uint32_t sbase, const int tid, const int lane, const int warp) {
+    const int half = ((P.smem_bytes - SM_DYN) / 2) & ~127;  // RT: a buffer = count tables (a third) + ratio tables
+    const uint32_t third = (uint32_t)rt_count_bytes(half);
     int m = -1;
     int4 cell = make_int4(-1, -1, -1, -1);
     uint32_t vmask = 0;
@@ -717,7 +793,7 @@ __device__ __forceinline__ void consume_resident(const TileParams& P, const uint
             const uint2 w0 = lds_u64(wurec + WU_M), w1 = lds_u64(wurec + WU_NPOS), w2 = lds_u64(wurec + WU_SA);
             m = (int)w0.x;
             const int npos = (int)w1.x;
-            if (WANT_SIM) {
+            if (WANT_SIM || RT) {
                 nrows = (int)(w1.y & 0xffffu);
                 sa_item = nrows == 1 ? w2.x : 0u;
             }
@@ -757,7 +833,12 @@ __device__ __forceinline__ void consume_resident(const TileParams& P, const uint
         if (!CA_DBG(P, 5)) consumer_sync<NC_RES>();  // the tables of phase p are complete; every consumer has left phase p-1
         if (WANT_SIM && warp == 1) flush_sim(P, sbase + SM_SIMACC + (b ^ 1u) * 64u, prev, prev_m, lane);
         // ---- gather ----
-        if (WANT_SIM && P.sim_scan) {  // the matrix from the tables; per-cell sums only when ecc is wanted
+        if (RT) {  // ratio tables: one division per table entry, then one load and one add per (cell, partner)
+            const uint32_t cbase = sbase + SM_DYN + b * (uint32_t)half, rbase = cbase + third;
+            convert_tables<false, WANT_SIM>(P, meta, simacc, ph, nrows, sa_item, cbase, rbase, warp - 1, NC_RES / 32, lane);
+            consumer_sync<NC_RES>();
+            if (wactive) gather_ratio<UNITW>(P, meta, ph, L, rowidx, cbase, rbase, acc);
+        } else if (WANT_SIM && P.sim_scan) {  // the matrix from the tables; per-cell sums only when ecc is wanted
             scan_sim<false>(P, meta, simacc, ph, nrows, sa_item, warp - 1, NC_RES / 32, lane);
             if (WANT_ECC && wactive) gather_cells<4, false, false, UNITW>(P, meta, simacc, ph, big, L, rowidx, sa, vmask, 1, lane, acc);
         } else if (wactive && !CA_DBG(P, 4))
@@ -924,9 +1005,11 @@ __device__ __forceinline__ void consume_resident_prefetch(const TileParams& P, c
 // a longer one streams the cells from global memory in both passes.  A warp whose quad of the second chunk lies beyond the
 // item skips it (warp-uniform), so the work is counted in warps x chunks, not in whole chunks.  Labels are loaded per
 // 8-partner tile (16 bytes per cell); the sums go to ecc per phase.
-template <bool WANT_ECC, bool WANT_SIM, bool UNITW>
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool RT>
 __device__ __forceinline__ void consume_streaming(const TileParams& P, const uint32_t sbase, const int tid, const int lane, const int warp) {
     constexpr int SCHUNK = 4 * NC_STR;
+    const int half = ((P.smem_bytes - SM_DYN) / 2) & ~127;  // RT: a buffer = count tables (a third) + ratio tables
+    const uint32_t third = (uint32_t)rt_count_bytes(half);
     int m = -1, npos = 0;
     bool wide = false;
     const int32_t* perm = P.perm;
@@ -1016,7 +1099,32 @@ __device__ __forceinline__ void consume_streaming(const TileParams& P, const uin
                 }
             }
         };
-        if (WANT_SIM && P.sim_scan) {  // the matrix from the tables (one row per partner here)
+        if (RT) {
+            const uint32_t cbase = sbase + SM_DYN + b * (uint32_t)half, rbase = cbase + third;
+            if (wide)
+                convert_tables<true, WANT_SIM>(P, meta, simacc, ph, 1, sa, cbase, rbase, warp - 1, NC_STR / 32, lane);
+            else
+                convert_tables<false, WANT_SIM>(P, meta, simacc, ph, 1, sa, cbase, rbase, warp - 1, NC_STR / 32, lane);
+            consumer_sync<NC_STR>();
+            if (npos <= 2 * SCHUNK) {
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    if (hh && !second) break;  // warp-uniform
+                    const int4 cl = hh ? cell2 : cell;
+                    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+                    gather_ratio<UNITW>(P, meta, ph, hh ? Lh : L, 0u, cbase, rbase, a4);
+                    flush4(cl, a4);
+                }
+            } else {
+                for (int cb = tid * 4; cb < npos; cb += SCHUNK) {
+                    const int4 cl = __ldg(reinterpret_cast<const int4*>(perm + cb));
+                    load_quad(labj, (uint32_t)P.n, cl, L);
+                    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+                    gather_ratio<UNITW>(P, meta, ph, L, 0u, cbase, rbase, a4);
+                    flush4(cl, a4);
+                }
+            }
+        } else if (WANT_SIM && P.sim_scan) {  // the matrix from the tables (one row per partner here)
             if (wide)
                 scan_sim<true>(P, meta, simacc, ph, 1, sa, warp - 1, NC_STR / 32, lane);
             else
@@ -1036,7 +1144,7 @@ __device__ __forceinline__ void consume_streaming(const TileParams& P, const uin
     }
 }
 
-template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool STREAMING>
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool STREAMING, bool RT>
 __global__ void __launch_bounds__((STREAMING ? NC_STR : NC_RES) + 32, 1) wave_kernel(const TileParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NCT = STREAMING ? NC_STR : NC_RES;
@@ -1053,21 +1161,21 @@ __global__ void __launch_bounds__((STREAMING ? NC_STR : NC_RES) + 32, 1) wave_ke
     if (threadIdx.x < 16) sts_b64(sbase + SM_SIMACC + threadIdx.x * 8u, 0ull);
     __syncthreads();
     if (warp == 0) {
-        producer_loop<UNITW>(P, sbase, half, lane);
+        producer_loop<UNITW>(P, sbase, half, RT ? rt_count_bytes(half) : half, lane);
         return;
     }
     const int tid = (int)threadIdx.x - 32;
     if (STREAMING)
-        consume_streaming<WANT_ECC, WANT_SIM, UNITW>(P, sbase, tid, lane, warp);
-    else if (CA_TL_PREFETCH)
+        consume_streaming<WANT_ECC, WANT_SIM, UNITW, RT>(P, sbase, tid, lane, warp);
+    else if (CA_TL_PREFETCH && !RT)
         consume_resident_prefetch<WANT_ECC, WANT_SIM, UNITW>(P, sbase, tid, lane, warp);
     else
-        consume_resident<WANT_ECC, WANT_SIM, UNITW>(P, sbase, tid, lane, warp);
+        consume_resident<WANT_ECC, WANT_SIM, UNITW, RT>(P, sbase, tid, lane, warp);
 }
 
 // Shared memory one block asks for and the number of table rows a resident block may own so that at least one
 // partner with kmax clusters fits into one of the two buffers (R rows of kmax + 1 32-bit entries, rounded to 4).
-int tile_smem_budget(int32_t kmax, int32_t* max_rows_out, int32_t* half_out) {
+int tile_smem_budget(int32_t kmax, int32_t* max_rows_out, int32_t* half_out, bool rt) {
     Ctx& c = ctx();
     const size_t optin = c.smem_optin ? c.smem_optin : 227 * 1024;
     const int budget = (int)optin;
@@ -1079,7 +1187,7 @@ int tile_smem_budget(int32_t kmax, int32_t* max_rows_out, int32_t* half_out) {
     const int budget_eff = budget_kb > 0 ? std::min(budget, budget_kb * 1024) : budget;
     const long long half = (((long long)budget_eff - SM_DYN) / 2) & ~127LL;
     const long long rowb = (((long long)(kmax > 0 ? kmax : 1) + 1 + 3) & ~3LL) * 4;  // + the pad column
-    long long rows = half / rowb;
+    long long rows = (rt ? rt_count_bytes((int)half) : half) / rowb;  // ratio-table launches: the count tables get a third of a buffer
     if (rows > TL_MAX_ROWS) rows = TL_MAX_ROWS;
     if (max_rows_out) *max_rows_out = (int32_t)(rows < 0 ? 0 : rows);
     if (half_out) *half_out = (int32_t)half;
@@ -1113,10 +1221,10 @@ int launch_qinfo(const TileParams& p, const int32_t* d_parts, int32_t nparts, cu
     return CA_OK;
 }
 
-template <bool E, bool S, bool U, bool STREAMING>
+template <bool E, bool S, bool U, bool STREAMING, bool RT>
 static int launch_wave_k(const TileParams& p, cudaStream_t s) {
     if (p.nwu <= 0) return CA_OK;
-    auto kern = wave_kernel<E, S, U, STREAMING>;
+    auto kern = wave_kernel<E, S, U, STREAMING, RT>;
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
     const int grid = std::min<int>(ca::ctx().sm_count, p.nwu);
     kern<<<(unsigned)grid, (STREAMING ? NC_STR : NC_RES) + 32, (size_t)p.smem_bytes, s>>>(p);
@@ -1128,7 +1236,8 @@ static int launch_wave_k(const TileParams& p, cudaStream_t s) {
 // p.streaming selects the kind of work units in p.items: the streaming kernel first (long items), then the resident one
 template <bool E, bool S, bool U>
 static int launch_wave_t(const TileParams& p, cudaStream_t s) {
-    return p.streaming ? launch_wave_k<E, S, U, true>(p, s) : launch_wave_k<E, S, U, false>(p, s);
+    if (E && p.rt) return p.streaming ? launch_wave_k<E, S, U, true, E>(p, s) : launch_wave_k<E, S, U, false, E>(p, s);  // ratio tables need ecc
+    return p.streaming ? launch_wave_k<E, S, U, true, false>(p, s) : launch_wave_k<E, S, U, false, false>(p, s);
 }
 
 int launch_tile(const TileParams& p, cudaStream_t s) {

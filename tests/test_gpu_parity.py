@@ -652,7 +652,7 @@ def test_pipelined_host_path_equals_plain_path_and_oracle(monkeypatch):
     assert np.array_equal(packed, only_ecc)  # matrix form == column form of the same entry
     assert np.abs(only_ecc - plain["ecc"]).max() < 1e-13  # another kernel instantiation (no matrix): same numbers, not necessarily the same bits
     unit = ecs.element_sim_matrix(cols)
-    assert np.array_equal(sim_only, unit) and np.abs(sim_only - plain["ecs_matrix"]).max() < 1e-13
+    assert np.array_equal(sim_only, unit) and np.abs(sim_only - plain["ecs_matrix"]).max() < 1e-12  # possibly another route to the matrix
     ecc_ref, sim_ref = oracle.weighted_element_consistency(L[:64], w[:64], calculate_sim_matrix=True)
     sub = ecs.weighted_element_consistency(cols[:64], weights=w[:64], calculate_sim_matrix=True)  # 64 partitions: the plain path
     assert np.abs(sub["ecc"] - ecc_ref).max() < TOL and np.abs(sub["ecs_matrix"] - sim_ref).max() < TOL
@@ -686,6 +686,13 @@ def test_pipelined_host_path_bails_out_when_later_groups_have_many_more_clusters
     assert np.abs(got[pi, pj] - means).max() < TOL and np.array_equal(got, got.T)
 
 
+def ecs_plain_ecc(cols, w, monkeypatch):
+    monkeypatch.setenv("CA_RT", "0")
+    out = ecs.weighted_element_consistency(cols, weights=w)
+    monkeypatch.delenv("CA_RT")
+    return out
+
+
 @pytest.mark.parametrize("shape", ["few clusters", "many clusters", "giant clusters"])
 def test_matrix_from_table_entries_equals_matrix_from_cells(monkeypatch, shape):
     """The ECS matrix has two routes through the wave kernel: summed over the non-empty TABLE entries, T^2 / max(S_a, S_b) -- the
@@ -699,7 +706,7 @@ def test_matrix_from_table_entries_equals_matrix_from_cells(monkeypatch, shape):
     elif shape == "many clusters":
         L = _louvainish(12, 20_000, 250, 400, seed=93)
     else:
-        n = 200_000
+        n = 240_000  # few clusters of more than 8192 cells on average: the library picks the ratio tables by itself here
         L = _louvainish(10, n, 8, 20, seed=94)
         L[0] = np.where(rng.random(n) < 0.75, 1, L[0] + 1)      # one cluster of ~150k cells in the first owner
         L[7] = np.where(rng.random(n) < 0.40, 3, L[7] + 5)      # ~80k cells in a partner
@@ -722,6 +729,19 @@ def test_matrix_from_table_entries_equals_matrix_from_cells(monkeypatch, shape):
     assert np.abs(got["0"][1]["ecc"] - got["1"][1]["ecc"]).max() < 1e-13
     again = ecs.element_sim_matrix(cols)  # CA_SIM_SCAN is still 1
     assert np.array_equal(again, got["1"][0])
+    # ratio tables (one IEEE division per table entry, the gather only adds; chosen for few, huge clusters): same numbers again
+    monkeypatch.setenv("CA_RT", "1")
+    rt = ecs.weighted_element_consistency(cols, weights=w, calculate_sim_matrix=True)
+    rt_ecc_only = ecs.weighted_element_consistency(cols, weights=w)
+    assert np.abs(rt["ecc"] - ecc_ref).max() < TOL and np.abs(rt["ecs_matrix"] - sim_ref).max() < TOL
+    assert np.abs(rt["ecc"] - got["1"][1]["ecc"]).max() < 1e-12 and np.abs(rt["ecs_matrix"] - got["1"][1]["ecs_matrix"]).max() < 1e-11
+    assert np.abs(rt_ecc_only - rt["ecc"]).max() < 1e-13
+    assert np.array_equal(ecs.weighted_element_consistency(cols, weights=w, calculate_sim_matrix=True)["ecc"], rt["ecc"])  # same bits twice
+    monkeypatch.delenv("CA_RT")
     monkeypatch.delenv("CA_SIM_SCAN")
     chosen = ecs.element_sim_matrix(cols)  # the library's own choice is one of the two
     assert np.array_equal(chosen, got["0"][0]) or np.array_equal(chosen, got["1"][0])
+    own = ecs.weighted_element_consistency(cols, weights=w)
+    assert np.array_equal(own, rt_ecc_only) or np.array_equal(own, ecs_plain_ecc(cols, w, monkeypatch))
+    if shape == "giant clusters":
+        assert np.array_equal(own, rt_ecc_only)

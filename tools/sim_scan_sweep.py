@@ -28,6 +28,7 @@ def run(name, L):
     dev = _capi.DeviceLabels(n, m).upload(np.ascontiguousarray(L))
     kmax = int(max(len(np.unique(r)) for r in L[: min(m, 8)]))
     out = {}
+    os.environ["CA_RT"] = "0"  # first the two routes to the matrix without ratio tables
     for mode, f in (("ecc+matrix", lambda: dev.consistency(None, None, True)), ("matrix only", lambda: dev.sim_matrix()), ("ecc only", lambda: dev.consistency())):
         for scan in ("0", "1", None):
             if scan is None:
@@ -37,6 +38,22 @@ def run(name, L):
             if mode == "ecc only" and scan is not None:
                 continue
             out[(mode, scan)] = med_ms(f)
+    rt = {}
+    for mode, f in (("ecc+matrix", lambda: dev.consistency(None, None, True)), ("ecc only", lambda: dev.consistency())):
+        for v in ("0", "1", None):
+            if v is None:
+                os.environ.pop("CA_RT", None)
+            else:
+                os.environ["CA_RT"] = v
+            rt[(mode, v)] = med_ms(f)
+    os.environ["CA_RT"] = "0"
+    e0, s0 = dev.consistency(None, None, True)
+    os.environ["CA_RT"] = "1"
+    e1, s1 = dev.consistency(None, None, True)
+    os.environ.pop("CA_RT", None)
+    print("%-34s ratio tables: ecc only off %8.3f on %8.3f chosen %8.3f | ecc+matrix off %8.3f on %8.3f chosen %8.3f ms | max |on - off| ecc %.2g matrix %.2g"
+          % (name, rt[("ecc only", "0")], rt[("ecc only", "1")], rt[("ecc only", None)], rt[("ecc+matrix", "0")], rt[("ecc+matrix", "1")],
+             rt[("ecc+matrix", None)], float(np.abs(e0 - e1).max()), float(np.abs(s0 - s1).max())), flush=True)
     os.environ["CA_SIM_SCAN"] = "0"
     a = dev.sim_matrix()
     os.environ["CA_SIM_SCAN"] = "1"
