@@ -65,6 +65,22 @@ namespace ca {
 #ifndef CA_BACKOFF_NS
 #define CA_BACKOFF_NS 200  // the producer's sleep between probes of a buffer that is still in use (tuning builds)
 #endif
+// Checked builds (tools/build_variant.sh checked -DCA_CHECK; compute-sanitizer is not available on the GPU pool): every raw
+// shared-memory address the consumers form, every cell id, label and row index is tested against its bounds; a violation prints
+// where and traps, so the call fails loudly.  The GPU test suite runs against such a build with CLUSTASSESS_B200_LIB.
+#ifdef CA_CHECK
+#define CA_CHK(cond, what)                                                                                                          \
+    do {                                                                                                                            \
+        if (!(cond)) {                                                                                                              \
+            printf("CA_CHECK failed: %s (%s:%d) block %d thread %d\n", what, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+            __trap();                                                                                                               \
+        }                                                                                                                           \
+    } while (0)
+#else
+#define CA_CHK(cond, what) \
+    do {                   \
+    } while (0)
+#endif
 static constexpr unsigned FULL = 0xffffffffu;
 static constexpr int NC_RES = TL_THREADS;      // consumer threads of the resident kernel (a quad of cells each)
 static constexpr int NC_STR = TL_STR_THREADS;  // consumer threads of the streaming kernel
@@ -240,6 +256,17 @@ __device__ __forceinline__ uint32_t slot_label_rt(const uint4& l, int jt) {
     return (jt & 1) ? (w >> 16) : (w & 0xffffu);
 }
 
+// address of entry `lab` of the table row at rb (row bytes rowb, entry bytes esz); checked builds test it
+__device__ __forceinline__ uint32_t entry_addr(const TileParams& P, uint32_t rb, uint32_t rowb, uint32_t lab, uint32_t esz) {
+#ifdef CA_CHECK
+    extern __shared__ __align__(128) unsigned char smem_chk[];
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_chk);
+    CA_CHK(lab * 4u + 4u <= rowb, "label beyond the table row");
+    CA_CHK(rb + lab * esz >= sb + SM_DYN && rb + lab * esz + esz <= sb + (uint32_t)P.smem_bytes, "table entry outside the table buffers");
+#endif
+    return rb + lab * esz;
+}
+
 template <int NCELL>
 __device__ __forceinline__ void hist_cells(const TileParams& P, uint32_t meta, const Phase ph, const uint4 (&L)[NCELL], uint32_t rowidx, int ng) {
     for_slots(ph.g0, ph.cnt, [&](auto slot) {
@@ -249,10 +276,10 @@ __device__ __forceinline__ void hist_cells(const TileParams& P, uint32_t meta, c
 #pragma unroll
         for (int g = 0; g < NCELL / 4; g++) {
             if (NCELL == 4 || g < ng) {
-                red_inc(rb + slot_label<JT>(P, L[4 * g + 0]) * 4u);
-                red_inc(rb + slot_label<JT>(P, L[4 * g + 1]) * 4u);
-                red_inc(rb + slot_label<JT>(P, L[4 * g + 2]) * 4u);
-                red_inc(rb + slot_label<JT>(P, L[4 * g + 3]) * 4u);
+                red_inc(entry_addr(P, rb, tr.y, slot_label<JT>(P, L[4 * g + 0]), 4u));
+                red_inc(entry_addr(P, rb, tr.y, slot_label<JT>(P, L[4 * g + 1]), 4u));
+                red_inc(entry_addr(P, rb, tr.y, slot_label<JT>(P, L[4 * g + 2]), 4u));
+                red_inc(entry_addr(P, rb, tr.y, slot_label<JT>(P, L[4 * g + 3]), 4u));
             }
         }
     });
@@ -308,7 +335,7 @@ __device__ __forceinline__ void gather_cells(const TileParams& P, uint32_t meta,
                 if (NCELL == 4 || g < ng) {
 #pragma unroll
                     for (int c = 4 * g; c < 4 * g + 4; c++) {
-                        const uint32_t e = lds_u32(rb + slot_label<JT>(P, L[c]) * 4u);
+                        const uint32_t e = lds_u32(entry_addr(P, rb, tr.y, slot_label<JT>(P, L[c]), 4u));
                         const uint32_t count = e & 0xffffu, sb = e >> 16;
                         if (UNITW && !WANT_SIM) {
                             const double mx = u32_to_f64(max(sa, sb));
@@ -341,7 +368,7 @@ __device__ __forceinline__ void gather_cells(const TileParams& P, uint32_t meta,
 #pragma unroll
                 for (int c = 4 * g; c < 4 * g + 4; c++) {
                     const uint32_t lab = slot_label_rt(L[c], jt);
-                    const uint32_t e = lds_u32(rb + lab * 4u);
+                    const uint32_t e = lds_u32(entry_addr(P, rb, tr.y, lab, 4u));
                     uint32_t count, sb;
                     if (WIDE) {
                         count = e;
@@ -366,6 +393,7 @@ __device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, 
     if (m < 0) return;
     if (t >= ph.g0 && t < ph.g0 + ph.cnt) {  // t = tile slot
         const unsigned long long v = lds_b64(simacc + t * 8u);
+        CA_CHK(m < P.m && ph.j0 + t < P.m, "matrix entry outside [0, m) x [0, m)");
         if (v != 0ull) atomicAdd(P.sim + (int64_t)m * P.m + (ph.j0 + t), v);
         sts_b64(simacc + t * 8u, 0ull);
     }
@@ -483,7 +511,7 @@ __device__ __forceinline__ void gather_ratio(const TileParams& P, uint32_t meta,
         const double wj = UNITW ? 1.0 : lds_f64(meta + META_W + JT * 8);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const double v = lds_f64(rr + slot_label<JT>(P, L[c]) * 8u);
+            const double v = lds_f64(entry_addr(P, rr, tr.y, slot_label<JT>(P, L[c]), 8u));
             acc[c] = UNITW ? acc[c] + v : fma(v, wj, acc[c]);
         }
     });
@@ -491,6 +519,7 @@ __device__ __forceinline__ void gather_ratio(const TileParams& P, uint32_t meta,
 
 // a cell's sum over the partners of a work unit (already scaled by w_i / norm) joins its fixed-point accumulator
 __device__ __forceinline__ void ecc_add(const TileParams& P, int cell, double v) {
+    CA_CHK(cell >= 0 && (int64_t)cell < P.n, "cell id outside [0, n)");
     atomicAdd(P.ecc + cell, to_fix(v, ECC_FIX_SCALE));
 }
 
@@ -510,6 +539,7 @@ static constexpr int WSPAN = TL_WU_SPAN;  // partners per work unit (one or two 
 #define CA_DBG(P, bit) 0
 #endif
 static constexpr uint32_t NROWS_WIDE = 1u << 30;  // Item::nrows flag: more than 65535 cells, 32-bit counters
+
 
 struct Planner {          // the producer warp's registers (all values warp-uniform)
     int w;                // current WU
@@ -632,6 +662,9 @@ __device__ __forceinline__ PhasePlan plan_compute(const TileParams& P, uint32_t 
     pp.ttot = __shfl_sync(FULL, pre, pp.cnt - 1);
     pp.toff = pre - pp.rowb * (uint32_t)pp.R;
     pp.big = ((pl.bigmask >> sq0) & ((1u << pp.cnt) - 1u)) != 0;
+    CA_CHK(pp.ttot <= (uint32_t)half && pp.toff + pp.rowb * (uint32_t)pp.R <= (uint32_t)half || lane >= pp.cnt, "phase tables beyond the buffer");
+    CA_CHK(pl.it.m >= 0 && pl.it.m < P.m && pl.j0 + pl.g0 + pp.cnt <= P.m, "work unit outside the partition range");
+    CA_CHK((int64_t)pl.it.pos0 + pl.it.npos <= P.perm_stride && pl.it.pos0 >= 0 && pl.it.npos > 0, "item outside its partition's sorted order");
     return pp;
 }
 template <bool UNITW>
@@ -809,6 +842,8 @@ __device__ __forceinline__ void consume_resident(const TileParams& P, const uint
             vmask = (1u << ((cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0))) - 1u;  // padding sits at the end of a cluster
             rowidx = qi.x;
             sa = qi.y;
+            CA_CHK(min(min(cell.x, cell.y), min(cell.z, cell.w)) >= -1 && (int64_t)max(max(cell.x, cell.y), max(cell.z, cell.w)) < P.n, "cell id outside [-1, n)");
+            CA_CHK(rowidx < (w1.y & 0xffffu) && (tid * 4 >= npos || sa > 0u), "quad info: row beyond the item's rows, or an empty cluster");
             acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
         }
         // ---- histogram ----
