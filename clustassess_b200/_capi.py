@@ -62,6 +62,7 @@ SYMBOLS = {
     "ca_get_profile": (C.c_int, [_F64, C.c_int]),
     "ca_get_profile_dev": (C.c_int, [C.c_int, _F64, C.c_int]),
     "ca_plan_spans": (C.c_int, [C.c_int32, C.c_int32, _I32, C.c_int32]),
+    "ca_plan_route": (C.c_int, [C.c_int32, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ca_plan_blocks": (C.c_int, [_I32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _I32, _I32, C.c_int32,
                                  C.POINTER(C.c_int64)]),
 }

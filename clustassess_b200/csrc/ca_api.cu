@@ -750,6 +750,45 @@ static int upload_segments(const UploadSeg* segs, size_t nseg, cudaStream_t s, i
     return CA_OK;
 }
 
+// ---- which way through the wave kernel (ca_tile.cu) a job takes: pure host logic, also exported for the CPU tests (ca_plan_route) ----
+// rt       ratio tables (convert_tables): one division per table ENTRY and a gather that only adds.  Measured (tools/sim_scan_sweep.py,
+//          profiles/r2_table_routes.txt): the extra pass and barrier per phase cost what the shorter gather saves -- except where
+//          clusters are HUGE (64 x 1M cells with K = 8 .. 64: 14.1 -> 9.5 ms): there most partners have clusters beyond the 16-bit
+//          size field and most owner clusters need 32-bit counters, and the plain gather looks every size up in global memory.
+//          So: at most 96 clusters of more than 8192 cells on average.  Needs ecc (the matrix alone has no gather).  CA_RT=0/1 forces it.
+// sim_scan the ECS matrix summed over the table entries (scan_sim) instead of per (cell, partner).  Reading the tables costs about
+//          (ceil(K / 32) * 42 + 30) warp instructions per (partner, row), i.e. per n / K cells; the per-cell way about 8 per 32
+//          (cell, partner) units on top of a gather that element_sim_matrix (no ecc) would not need at all (17 more).
+//          CA_SIM_SCAN=0/1 forces it.  Ratio-table launches sum the matrix while they convert the tables.
+struct Route {
+    bool rt, sim_scan;
+};
+static Route route_for(int32_t kmax, int64_t n, bool want_ecc, bool want_sim, bool allow_rt = true) {
+    Route r{false, false};
+    r.rt = want_ecc && kmax >= 1 && kmax <= 96 && (int64_t)kmax * 8192 <= n;
+    if (const char* e = getenv("CA_RT")) r.rt = want_ecc && atoi(e) != 0;
+    if (!allow_rt) r.rt = false;  // (the tables of one partner do not fit a third of a buffer)
+    if (want_sim && !r.rt) {
+        if (const char* e = getenv("CA_SIM_SCAN")) {
+            r.sim_scan = atoi(e) != 0;
+        } else {
+            const double est = (std::ceil(kmax / 32.0) * 42.0 + 30.0) * 32.0 * (double)std::max(kmax, 1) / (double)std::max<int64_t>(n, 1);
+            r.sim_scan = est < (want_ecc ? 6.0 : 18.0);
+        }
+    }
+    return r;
+}
+extern "C" int ca_plan_route(int32_t kmax, int64_t n, int want_ecc, int want_sim, int* ratio_tables_out, int* sim_from_tables_out) {
+    if (kmax < 0 || n < 0 || !ratio_tables_out || !sim_from_tables_out) {
+        set_error("ca_plan_route: bad argument");
+        return CA_E_ARG;
+    }
+    const Route r = route_for(kmax, n, want_ecc != 0, want_sim != 0);
+    *ratio_tables_out = r.rt;
+    *sim_from_tables_out = r.sim_scan;
+    return CA_OK;
+}
+
 // The all-pairs job of one device: every owned partition i against its partners j in (i, m) -- or, in agreement mode,
 // partition `ref_only` against all j in [0, m_partners).  Owned = the partitions i with zigzag(i) == rank of a whole label
 // set, or every partition a SHARD holds (one process, several GPUs).  Sums are added to d_ecc / d_sim as fixed-point
@@ -787,14 +826,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     auto lap = [&](const char* what) {
         if (plan_dbg) fprintf(stderr, "[plan dev %d] %-28s %.3f ms\n", c.device, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count());
     };
-    // Ratio tables (ca_tile.cu, convert_tables): one division per table ENTRY and a gather that only adds, instead of a ratio per
-    // (cell, partner).  Measured (tools/sim_scan_sweep.py, profiles/r2_table_routes.txt): the extra pass and barrier per phase cost
-    // what the shorter gather saves -- except where clusters are HUGE (few clusters, many cells: 64 x 1M cells with K = 8 .. 64,
-    // 14.1 -> 9.5 ms): there most partners have clusters beyond the 16-bit size field and most owner clusters need 32-bit
-    // counters, and the plain gather looks every size up in global memory.  So: few clusters of more than 8192 cells on average.
-    // Needs ecc (the matrix alone has no gather).  CA_RT=0/1 forces it off / on.
-    bool use_rt = d_ecc != nullptr && L.kmax <= 96 && (int64_t)L.kmax * 8192 <= n;
-    if (const char* e = getenv("CA_RT")) use_rt = d_ecc != nullptr && atoi(e) != 0;
+    const Route route = route_for(L.kmax, n, d_ecc != nullptr, d_sim != nullptr);
+    bool use_rt = route.rt;
     int32_t max_rows = 0;
     int smem_bytes = tile_smem_budget(L.kmax, &max_rows, nullptr, use_rt);
     if (use_rt && max_rows < 1) {
@@ -1068,19 +1101,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
     T.sim = reinterpret_cast<unsigned long long*>(d_sim);
     T.sim_magic = sim_fix_magic(n);
     T.sim_scale = sim_fix_scale(n);
-    // The matrix from the table entries or from the cells?  Reading the tables costs about (ceil(K / 32) * 42 + 30) warp
-    // instructions per (partner, row), i.e. per n / K cells; the per-cell way costs about 8 per 32 (cell, partner) units on top of
-    // a gather that element_sim_matrix (no ecc) would not need at all (17 more).  CA_SIM_SCAN=0/1 forces one of them.
     T.rt = use_rt ? 1 : 0;
-    T.sim_scan = 0;
-    if (d_sim && !use_rt) {  // (ratio-table launches sum the matrix while they convert the tables)
-        if (const char* e = getenv("CA_SIM_SCAN")) {
-            T.sim_scan = atoi(e) != 0;
-        } else {
-            const double est = (std::ceil(L.kmax / 32.0) * 42.0 + 30.0) * 32.0 * (double)std::max(L.kmax, 1) / (double)n;
-            T.sim_scan = est < (d_ecc ? 6.0 : 18.0);
-        }
-    }
+    T.sim_scan = route_for(L.kmax, n, d_ecc != nullptr, d_sim != nullptr, use_rt).sim_scan ? 1 : 0;
     T.perm_stride = perm_stride;
     T.m = m;
     T.mpad = L.mpad;

@@ -214,6 +214,13 @@ int ca_plan_blocks(const int32_t *sizes, int32_t k, int32_t align, int32_t cap, 
  * runs the pairs (i, j > i) of its partitions i.  Returns the number of spans (<= cap) or a negative error.  Needs no GPU. */
 int ca_plan_spans(int32_t m, int32_t ndev, int32_t *owner_out, int32_t cap);
 
+/* Which way through the engine a batched job takes, from its largest cluster count and its number of cells: *ratio_tables_out = one
+ * IEEE division per contingency-table entry and a gather that only adds (few, huge clusters; needs ecc); *sim_from_tables_out = the
+ * ECS matrix is summed over the non-empty table entries, T^2 / max(S_a, S_b) -- the reference's formula for a pair's average
+ * (src/calculate_ecs.cpp:58-67) -- instead of per (cell, partner).  All routes give the same numbers to 1e-12 (different rounding
+ * of the last bits); each is bit-reproducible.  CA_RT=0/1 and CA_SIM_SCAN=0/1 in the environment force them.  Needs no GPU. */
+int ca_plan_route(int32_t kmax, int64_t n, int want_ecc, int want_sim, int *ratio_tables_out, int *sim_from_tables_out);
+
 #ifdef __cplusplus
 }
 #endif

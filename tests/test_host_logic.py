@@ -158,3 +158,42 @@ def test_span_sharding_of_the_in_library_multi_gpu_path():
         assert load.max() / load.mean() < bound, (m, g, load)
     assert owners(33, 8).tolist()[0] != owners(33, 8).tolist()[1]  # two spans, two devices; the other six stay idle
     assert lib.ca_plan_spans(0, 2, np.zeros(1, dtype=np.int32), 1) < 0 and lib.ca_plan_spans(100, 99, np.zeros(4, dtype=np.int32), 4) < 0
+
+
+def test_route_through_the_engine_from_cluster_count_and_cells(monkeypatch):
+    """Host logic behind the batched entries (csrc/ca_api.cu, route_for): with few clusters the ECS matrix is summed over the
+    contingency-table entries -- the reference's own formula for a pair's average, src/calculate_ecs.cpp:58-67 -- instead of per
+    (cell, partner); few HUGE clusters switch the consistency to ratio tables.  The decisions measured as the faster ones in
+    profiles/r2_table_routes.txt, the environment overrides, and the rule that ratio tables need ecc."""
+    import ctypes as C
+
+    lib = _capi.lib()
+    monkeypatch.delenv("CA_RT", raising=False)
+    monkeypatch.delenv("CA_SIM_SCAN", raising=False)
+
+    def route(kmax, n, ecc, sim):
+        rt, scan = C.c_int(-1), C.c_int(-1)
+        _capi.check(lib.ca_plan_route(kmax, n, int(ecc), int(sim), C.byref(rt), C.byref(scan)))
+        return bool(rt.value), bool(scan.value)
+
+    # (kmax, n): matrix only / ecc + matrix / ecc only
+    assert route(60, 50_000, False, True) == (False, True)        # config 4, element_sim_matrix: no gather at all
+    assert route(40, 100_000, True, True) == (False, True)        # config 3 with the matrix
+    assert route(2000, 1_000_000, True, True) == (False, False)   # config 5: long sparse rows, per cell
+    assert route(2000, 1_000_000, False, True) == (False, False)
+    assert route(2000, 1_000_000, True, False) == (False, False)  # the headline job: neither
+    assert route(12, 2700, False, True) == (False, True) and route(12, 2700, True, True) == (False, False)  # config 1
+    assert route(64, 1_000_000, True, False) == (True, False)     # few huge clusters: ratio tables (which also sum the matrix)
+    assert route(64, 1_000_000, True, True) == (True, False)
+    assert route(64, 1_000_000, False, True) == (False, True)     # ... but never without ecc
+    assert route(128, 1_000_000, True, False) == (False, False) and route(60, 50_000, True, False) == (False, False)
+    assert route(0, 0, True, True)[0] is False
+    monkeypatch.setenv("CA_RT", "1")
+    assert route(2000, 1_000_000, True, True) == (True, False) and route(2000, 1_000_000, False, True)[0] is False
+    monkeypatch.setenv("CA_RT", "0")
+    monkeypatch.setenv("CA_SIM_SCAN", "1")
+    assert route(64, 1_000_000, True, True) == (False, True) and route(2000, 1_000_000, True, False) == (False, False)
+    monkeypatch.setenv("CA_SIM_SCAN", "0")
+    assert route(60, 50_000, False, True) == (False, False)
+    rt, scan = C.c_int(), C.c_int()
+    assert lib.ca_plan_route(-1, 10, 1, 1, C.byref(rt), C.byref(scan)) < 0
