@@ -108,6 +108,8 @@ static constexpr int SM_PLANW = 960;    //   bytes inside the 8-partner tile}; [
 static constexpr int SM_DYN = 1280;     // two table buffers
 static_assert(SM_WUREC + 2 * WUREC_BYTES <= SM_PLAN && SM_PLAN + 256 <= SM_PLANW && SM_PLANW + 256 <= SM_DYN, "shared-memory map");
 static constexpr uint32_t KK_BIG = 1u << 30;  // partner has a cluster with >= 65535 cells
+// the instantiations of the kernel: per-cell everything; ratio tables (TileParams::rt); the matrix from the table entries (TileParams::sim_scan)
+static constexpr int MODE_PLAIN = 0, MODE_RT = 1, MODE_SCAN = 2;
 // ratio-table launches (RT): bytes of a table buffer the count tables may use; the ratio tables (8 bytes per entry) follow them
 __host__ __device__ __forceinline__ int rt_count_bytes(int half) { return (half / 3) & ~127; }
 
@@ -398,7 +400,7 @@ __device__ __forceinline__ void flush_sim(const TileParams& P, uint32_t simacc, 
         sts_b64(simacc + t * 8u, 0ull);
     }
 }
-// ---- the ECS matrix from the TABLES (P.sim_scan: partitions with few clusters) -----------------------------------------------
+// ---- the ECS matrix from the TABLES (MODE_SCAN launches: partitions with few clusters) -----------------------------------------------
 // sum_n ECS_ij[n] = sum_{a,b} T[a][b]^2 / max(S_i[a], S_j[b]) -- the reference's own formula for the average of a pair
 // (disjointECSaverage, src/calculate_ecs.cpp:58-67): every non-empty table entry stands for T[a][b] cells with the same ratio.
 // With K clusters a table row has K entries but n / K cells, so for small K reading the finished tables is far cheaper than
@@ -780,8 +782,9 @@ __device__ __forceinline__ PhaseHdr read_hdr(uint32_t sbase, uint32_t meta) {
 // ---- resident items: a quad of consecutive positions per thread -------------------------------------------------
 // The plain consumer: the 16 labels of a cell for a whole super-tile come with ONE 32-byte load when the work unit reaches
 // the super-tile (L = its lower tile, Lh = its upper tile).
-template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool RT>
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW, int MODE>
 __device__ __forceinline__ void consume_resident(const TileParams& P, const uint32_t sbase, const int tid, const int lane, const int warp) {
+    constexpr bool RT = MODE == MODE_RT, SCAN = MODE == MODE_SCAN;
     const int half = ((P.smem_bytes - SM_DYN) / 2) & ~127;  // RT: a buffer = count tables (a third) + ratio tables
     const uint32_t third = (uint32_t)rt_count_bytes(half);
     int m = -1;
@@ -873,7 +876,7 @@ __device__ __forceinline__ void consume_resident(const TileParams& P, const uint
             convert_tables<false, WANT_SIM>(P, meta, simacc, ph, nrows, sa_item, cbase, rbase, warp - 1, NC_RES / 32, lane);
             consumer_sync<NC_RES>();
             if (wactive) gather_ratio<UNITW>(P, meta, ph, L, rowidx, cbase, rbase, acc);
-        } else if (WANT_SIM && P.sim_scan) {  // the matrix from the tables; per-cell sums only when ecc is wanted
+        } else if (WANT_SIM && SCAN) {  // the matrix from the tables; per-cell sums only when ecc is wanted
             scan_sim<false>(P, meta, simacc, ph, nrows, sa_item, warp - 1, NC_RES / 32, lane);
             if (WANT_ECC && wactive) gather_cells<4, false, false, UNITW>(P, meta, simacc, ph, big, L, rowidx, sa, vmask, 1, lane, acc);
         } else if (wactive && !CA_DBG(P, 4))
@@ -1040,9 +1043,10 @@ __device__ __forceinline__ void consume_resident_prefetch(const TileParams& P, c
 // a longer one streams the cells from global memory in both passes.  A warp whose quad of the second chunk lies beyond the
 // item skips it (warp-uniform), so the work is counted in warps x chunks, not in whole chunks.  Labels are loaded per
 // 8-partner tile (16 bytes per cell); the sums go to ecc per phase.
-template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool RT>
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW, int MODE>
 __device__ __forceinline__ void consume_streaming(const TileParams& P, const uint32_t sbase, const int tid, const int lane, const int warp) {
     constexpr int SCHUNK = 4 * NC_STR;
+    constexpr bool RT = MODE == MODE_RT, SCAN = MODE == MODE_SCAN;
     const int half = ((P.smem_bytes - SM_DYN) / 2) & ~127;  // RT: a buffer = count tables (a third) + ratio tables
     const uint32_t third = (uint32_t)rt_count_bytes(half);
     int m = -1, npos = 0;
@@ -1159,7 +1163,7 @@ __device__ __forceinline__ void consume_streaming(const TileParams& P, const uin
                     flush4(cl, a4);
                 }
             }
-        } else if (WANT_SIM && P.sim_scan) {  // the matrix from the tables (one row per partner here)
+        } else if (WANT_SIM && SCAN) {  // the matrix from the tables (one row per partner here)
             if (wide)
                 scan_sim<true>(P, meta, simacc, ph, 1, sa, warp - 1, NC_STR / 32, lane);
             else
@@ -1179,7 +1183,7 @@ __device__ __forceinline__ void consume_streaming(const TileParams& P, const uin
     }
 }
 
-template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool STREAMING, bool RT>
+template <bool WANT_ECC, bool WANT_SIM, bool UNITW, bool STREAMING, int MODE>
 __global__ void __launch_bounds__((STREAMING ? NC_STR : NC_RES) + 32, 1) wave_kernel(const TileParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NCT = STREAMING ? NC_STR : NC_RES;
@@ -1196,16 +1200,16 @@ __global__ void __launch_bounds__((STREAMING ? NC_STR : NC_RES) + 32, 1) wave_ke
     if (threadIdx.x < 16) sts_b64(sbase + SM_SIMACC + threadIdx.x * 8u, 0ull);
     __syncthreads();
     if (warp == 0) {
-        producer_loop<UNITW>(P, sbase, half, RT ? rt_count_bytes(half) : half, lane);
+        producer_loop<UNITW>(P, sbase, half, MODE == MODE_RT ? rt_count_bytes(half) : half, lane);
         return;
     }
     const int tid = (int)threadIdx.x - 32;
     if (STREAMING)
-        consume_streaming<WANT_ECC, WANT_SIM, UNITW, RT>(P, sbase, tid, lane, warp);
-    else if (CA_TL_PREFETCH && !RT)
+        consume_streaming<WANT_ECC, WANT_SIM, UNITW, MODE>(P, sbase, tid, lane, warp);
+    else if (CA_TL_PREFETCH && MODE == MODE_PLAIN)
         consume_resident_prefetch<WANT_ECC, WANT_SIM, UNITW>(P, sbase, tid, lane, warp);
     else
-        consume_resident<WANT_ECC, WANT_SIM, UNITW, RT>(P, sbase, tid, lane, warp);
+        consume_resident<WANT_ECC, WANT_SIM, UNITW, MODE>(P, sbase, tid, lane, warp);
 }
 
 // Shared memory one block asks for and the number of table rows a resident block may own so that at least one
@@ -1256,10 +1260,10 @@ int launch_qinfo(const TileParams& p, const int32_t* d_parts, int32_t nparts, cu
     return CA_OK;
 }
 
-template <bool E, bool S, bool U, bool STREAMING, bool RT>
+template <bool E, bool S, bool U, bool STREAMING, int MODE>
 static int launch_wave_k(const TileParams& p, cudaStream_t s) {
     if (p.nwu <= 0) return CA_OK;
-    auto kern = wave_kernel<E, S, U, STREAMING, RT>;
+    auto kern = wave_kernel<E, S, U, STREAMING, MODE>;
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
     const int grid = std::min<int>(ca::ctx().sm_count, p.nwu);
     kern<<<(unsigned)grid, (STREAMING ? NC_STR : NC_RES) + 32, (size_t)p.smem_bytes, s>>>(p);
@@ -1271,8 +1275,11 @@ static int launch_wave_k(const TileParams& p, cudaStream_t s) {
 // p.streaming selects the kind of work units in p.items: the streaming kernel first (long items), then the resident one
 template <bool E, bool S, bool U>
 static int launch_wave_t(const TileParams& p, cudaStream_t s) {
-    if (E && p.rt) return p.streaming ? launch_wave_k<E, S, U, true, E>(p, s) : launch_wave_k<E, S, U, false, E>(p, s);  // ratio tables need ecc
-    return p.streaming ? launch_wave_k<E, S, U, true, false>(p, s) : launch_wave_k<E, S, U, false, false>(p, s);
+    // ratio tables need ecc, the matrix from the tables needs the matrix: the other combinations are not instantiated
+    constexpr int RTM = E ? MODE_RT : MODE_PLAIN, SCM = S ? MODE_SCAN : MODE_PLAIN;
+    if (E && p.rt) return p.streaming ? launch_wave_k<E, S, U, true, RTM>(p, s) : launch_wave_k<E, S, U, false, RTM>(p, s);
+    if (S && p.sim_scan) return p.streaming ? launch_wave_k<E, S, U, true, SCM>(p, s) : launch_wave_k<E, S, U, false, SCM>(p, s);
+    return p.streaming ? launch_wave_k<E, S, U, true, MODE_PLAIN>(p, s) : launch_wave_k<E, S, U, false, MODE_PLAIN>(p, s);
 }
 
 int launch_tile(const TileParams& p, cudaStream_t s) {
