@@ -32,7 +32,7 @@ if os.path.exists(ref) and last_json(ref):
 
 # ---- launch list
 out = ["# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline  (C5, 3 steps captured; tools/profile_c5.sh)",
-       "# wave_kernel<ECC,SIM,UNITW,STREAMING,RT>: <..,1,r> = streaming items (clusters > 3456 cells), <..,0,r> = resident items; RT = ratio tables (not at C5).",
+       "# wave_kernel<ECC,SIM,UNITW,STREAMING,MODE>: <..,1,m> = streaming items (clusters > 3456 cells), <..,0,m> = resident items; MODE 0 = per cell (C5), 1 = ratio tables, 2 = matrix from the tables.",
        "# bench.py of the same build (CUDA events, no profiler): engine (qinfo + both wave launches) %.1f ms of a %.1f ms step = %.1f %%" %
        (bench["stage_ms_per_step"]["engine_ms"], bench["ms_per_step"], 100 * bench["stage_ms_per_step"]["engine_ms"] / bench["ms_per_step"])]
 out.append(run([sys.executable, os.path.join(ROOT, "tools", "ncu_launch_summary.py"), os.path.join(G, tag + "_launches.csv")]))
