@@ -39,8 +39,19 @@ SHAPES = [(2, 40_000), (3, 20_000), (7, 7000), (8, 3457), (9, 900), (16, 130), (
           (40, 2000), (66, 1500), (5, 1), (12, 5), (24, 40_000), (48, 900)]
 
 
+# the routes through the wave kernel the host would otherwise pick by itself (csrc/ca_api.cu route_for): forced, so that every
+# random shape also goes through the matrix-from-the-tables launches and through the ratio-table launches
+ROUTES = {"own choice": {}, "matrix from the tables": {"CA_RT": "0", "CA_SIM_SCAN": "1"}, "ratio tables": {"CA_RT": "1"},
+          "per cell": {"CA_RT": "0", "CA_SIM_SCAN": "0"}}
+
+
+@pytest.mark.parametrize("route", list(ROUTES))
 @pytest.mark.parametrize("seed", range(len(SHAPES)))
-def test_random_label_sets(seed):
+def test_random_label_sets(seed, route, monkeypatch):
+    if route != "own choice" and seed % 2 == (0 if route == "per cell" else 1) and route != "matrix from the tables":
+        pytest.skip("every other shape for the forced per-cell and ratio-table routes")
+    for k, v in ROUTES[route].items():
+        monkeypatch.setenv(k, v)
     rng = np.random.default_rng(1000 + seed)
     m, n = SHAPES[seed]
     base = _partition(rng, n, int(rng.integers(0, 5)))
