@@ -1126,7 +1126,12 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
         CA_TRY(launch_qinfo(T, W.parts.as<int32_t>(), nparts, s));
     }
     CA_CUDA(cudaEventRecord(c.ev[4], s));
+    DevBuf& wu_ctr = scratch(SCR_WUCTR);  // one hand-out counter per launch
+    CA_TRY(wu_ctr.ensure(8));
+    CA_CUDA(cudaMemsetAsync(wu_ctr.p, 0, 8, s));
+    const bool wu_static = getenv("CA_WU_STATIC") != nullptr;  // tuning: work units dealt round-robin as in round 1
     for (int kind = 1; kind >= 0; kind--) {  // the long streaming items first
+        T.wu_counter = wu_static ? nullptr : wu_ctr.as<int32_t>() + kind;
         T.items = W.items.as<Item>() + (kind == 1 ? n_kind[0] : 0);
         T.wu_prefix = W.wu_prefix.as<int32_t>() + (kind == 1 ? npre0 : 0);
         T.nsuper = (int32_t)h_wu_prefix_kind[kind].size() - 1;

@@ -48,7 +48,7 @@ int ensure_init();
 // Grow-only scratch buffers every device owns one set of (released by ca_shutdown): what used to be function-local statics.
 struct DevBuf;
 enum ScratchId { SCR_ZEROS, SCR_ECC, SCR_SIM, SCR_OUT, SCR_SIG, SCR_FLAG, SCR_FIRST, SCR_SEGCUR, SCR_PAIR_A, SCR_PAIR_B, SCR_PAIR_TABLE,
-                 SCR_PAIR_SA, SCR_PAIR_SB, SCR_PAIR_ERR, SCR_PAIR_ECS, SCR_PAIR_PARTIAL, SCR_PAIR_OUT, SCR_HASH, SCR_COUNT };
+                 SCR_PAIR_SA, SCR_PAIR_SB, SCR_PAIR_ERR, SCR_PAIR_ECS, SCR_PAIR_PARTIAL, SCR_PAIR_OUT, SCR_HASH, SCR_WUCTR, SCR_COUNT };
 DevBuf& scratch(int which);
 
 // device memory comes from a small caching allocator (ca_api.cu): freed blocks are parked and reused
@@ -224,6 +224,7 @@ struct TileParams {
     int64_t perm_stride;
     int32_t m, mpad, kp;
     int32_t nsuper, nwu;      // super-tiles, work units
+    int32_t* wu_counter;      // zeroed before the launch: work units beyond the first gridDim.x are handed out in order, first come first served (null: round-robin)
     int32_t streaming;        // kind of the items of this launch: 0 resident (<= TL_CAP positions), 1 streaming
     int32_t smem_bytes;       // dynamic shared memory per block
     double inv_norm;
