@@ -38,101 +38,106 @@ int plan_blocks(const int32_t* sizes, int32_t k, int32_t align, int32_t cap, int
     struct Scratch {
         std::vector<uint64_t> keys, tmp;               // cluster indices, sorted by decreasing size
         std::vector<int32_t> head, next, bin_of, bin_rows, bin_start, member, big;
-        std::vector<int64_t> bin_used;
+        std::vector<int32_t> bin_left;  // units still free in a bin
         std::vector<uint64_t> nonempty;
     };
     static thread_local Scratch S;
 
     // `align` is a power of two in every call the library makes (cells per thread): shifts instead of divisions.  (Measured on
-    // K = 1300 clusters: 65 us per partition -- 17 the radix sort, 41 the best-fit binning, 11 the lists; the divisions were not it.)
+    // K = 500 .. 2000 clusters: 43 us per partition with a radix sort and 64-bit vectors in the best-fit loop, 31 us now; the divisions were not it.)
     const bool pow2 = (align & (align - 1)) == 0;
     const int sh = pow2 ? __builtin_ctz((unsigned)align) : 0;
     auto units = [&](int64_t x) -> int64_t { return pow2 ? (x >> sh) : x / align; };   // x / align
     auto padded = [&](int32_t s) -> int64_t { return pow2 ? (((int64_t)s + align - 1) >> sh) << sh : (int64_t)((s + align - 1) / align) * align; };
 
-    // clusters by decreasing size, ties by increasing index (what a stable sort by size gives): a stable LSD radix
-    // sort of the indices on the key (max size - size), 11 bits per pass, as many passes as the largest size needs
-    S.keys.resize(k);   // keys[c] = index permutation being sorted
-    S.tmp.resize(k);
-    int32_t smax = 0;
+    // Resident clusters by decreasing PADDED size (what the packing sees), ties by increasing index: a counting sort over the
+    // at most cap / align distinct padded sizes -- O(K + cap / align), against a comparison or radix sort of the sizes
+    // (17 of the planner's 65 us per partition at K = 1300; the planner is the pre-wave critical path of multi-GPU jobs).
+    // The few clusters beyond `cap` (streaming items) are sorted by size on their own.
+    const int32_t nb = (int32_t)units(cap) + 1;
+    S.keys.resize(k);
+    S.tmp.assign((size_t)nb + 1, 0);  // tmp[u] = clusters of u units, then the first slot of that class
+    S.big.clear();
     for (int32_t c = 0; c < k; c++) {
         if (sizes[c] <= 0) {
             set_error("plan_blocks: cluster %d has size %d (must be > 0)", c, sizes[c]);
             return CA_E_ARG;
         }
-        smax = std::max(smax, sizes[c]);
-        S.keys[c] = (uint64_t)c;
+        const int64_t p = padded(sizes[c]);
+        if (p > cap)
+            S.big.push_back(c);
+        else
+            S.tmp[(size_t)units(p)]++;
     }
-    for (int shift = 0; shift < 32 && ((uint32_t)smax >> shift) != 0; shift += 11) {
-        uint32_t hist[2049] = {0};
-        for (int32_t t = 0; t < k; t++) hist[((((uint32_t)(smax - sizes[S.keys[t]])) >> shift) & 2047u) + 1]++;
-        for (int b = 0; b < 2048; b++) hist[b + 1] += hist[b];
-        for (int32_t t = 0; t < k; t++) {
-            const uint64_t c = S.keys[t];
-            S.tmp[hist[(((uint32_t)(smax - sizes[c])) >> shift) & 2047u]++] = c;
+    {
+        uint64_t at = 0;
+        for (int32_t u = nb - 1; u >= 0; u--) {
+            const uint64_t n_u = S.tmp[(size_t)u];
+            S.tmp[(size_t)u] = at;
+            at += n_u;
         }
-        S.keys.swap(S.tmp);
     }
+    const int32_t nres = k - (int32_t)S.big.size();
+    for (int32_t c = 0; c < k; c++) {
+        const int64_t u = units(padded(sizes[c]));
+        if (u < nb) S.keys[S.tmp[(size_t)u]++] = ((uint64_t)u << 32) | (uint32_t)c;  // {units, cluster}
+    }
+    std::stable_sort(S.big.begin(), S.big.end(), [&](int32_t x, int32_t y) { return sizes[x] > sizes[y]; });
 
     // open bins by remaining capacity (in units of `align`): per-capacity LIFO lists threaded through `next` + a bitmap of
-    // the non-empty lists, so "smallest remaining capacity that still holds p" is a find-next-set-bit
-    const int32_t nb = (int32_t)units(cap) + 1;
+    // the non-empty lists, so "smallest remaining capacity that still holds p" is a find-next-set-bit.  Everything in units,
+    // arrays sized once: this loop is most of the planner's time.
+    const int32_t capu = nb - 1, nwords = (nb + 63) / 64;
     S.head.assign(nb, -1);
-    S.nonempty.assign((nb + 63) / 64, 0);
-    S.next.clear();
-    S.bin_used.clear();
-    S.bin_rows.clear();
-    S.bin_of.assign(k, -1);
-    S.big.clear();
-    auto find_from = [&](int32_t u) -> int32_t {  // first non-empty list >= u, or -1
-        for (int32_t w = u >> 6; w < (int32_t)S.nonempty.size(); w++) {
-            uint64_t bits = S.nonempty[w];
-            if (w == (u >> 6)) bits &= ~0ULL << (u & 63);
-            if (bits) return w * 64 + __builtin_ctzll(bits);
+    S.nonempty.assign(nwords, 0);
+    S.next.resize(std::max(nres, 1));
+    S.bin_left.resize(std::max(nres, 1));
+    S.bin_rows.resize(std::max(nres, 1));
+    S.bin_of.resize(std::max(k, 1));
+    int32_t* const head = S.head.data();
+    int32_t* const next = S.next.data();
+    int32_t* const bin_left = S.bin_left.data();
+    int32_t* const bin_rows = S.bin_rows.data();
+    int32_t* const bin_of = S.bin_of.data();
+    uint64_t* const nonempty = S.nonempty.data();
+    int32_t nbins = 0;
+    for (int32_t idx = 0; idx < nres; idx++) {
+        const uint64_t key = S.keys[idx];
+        const int32_t c = (int32_t)(uint32_t)key, pu = (int32_t)(key >> 32);
+        int32_t u = -1;  // best fit: the first non-empty list >= pu
+        {
+            int32_t w = pu >> 6;
+            uint64_t bits = nonempty[w] & (~0ULL << (pu & 63));
+            while (bits == 0 && ++w < nwords) bits = nonempty[w];
+            if (bits) u = w * 64 + __builtin_ctzll(bits);
         }
-        return -1;
-    };
-
-    for (int32_t idx = 0; idx < k; idx++) {
-        const int32_t c = (int32_t)S.keys[idx];
-        const int64_t p = padded(sizes[c]);
-        if (p > cap) {
-            S.big.push_back(c);
-            continue;
-        }
-        const int32_t u = find_from((int32_t)units(p));  // best fit
         int32_t b;
         if (u < 0) {
-            b = (int32_t)S.bin_used.size();
-            S.bin_used.push_back(0);
-            S.bin_rows.push_back(0);
-            S.next.push_back(-1);
+            b = nbins++;
+            bin_left[b] = capu;
+            bin_rows[b] = 0;
         } else {
-            b = S.head[u];
-            S.head[u] = S.next[b];
-            if (S.head[u] < 0) S.nonempty[u >> 6] &= ~(1ULL << (u & 63));
+            b = head[u];
+            head[u] = next[b];
+            if (head[u] < 0) nonempty[u >> 6] &= ~(1ULL << (u & 63));
         }
-        S.bin_of[c] = b;
-        S.bin_used[b] += p;
-        S.bin_rows[b]++;
-        const int64_t rem = cap - S.bin_used[b];
-        if (rem >= align && S.bin_rows[b] < max_rows) {
-            const int32_t r = (int32_t)units(rem);
-            S.next[b] = S.head[r];
-            S.head[r] = b;
-            S.nonempty[r >> 6] |= 1ULL << (r & 63);
+        bin_of[c] = b;
+        const int32_t rem = (bin_left[b] -= pu);
+        if (++bin_rows[b] < max_rows && rem >= 1) {
+            next[b] = head[rem];
+            head[rem] = b;
+            nonempty[rem >> 6] |= 1ULL << (rem & 63);
         }
     }
     // members of every bin in the order they were added (decreasing size)
-    const int32_t nbins = (int32_t)S.bin_used.size();
     S.bin_start.assign(nbins + 1, 0);
-    for (int32_t b = 0; b < nbins; b++) S.bin_start[b + 1] = S.bin_start[b] + S.bin_rows[b];
+    for (int32_t b = 0; b < nbins; b++) S.bin_start[b + 1] = S.bin_start[b] + bin_rows[b];
     S.member.resize(S.bin_start[nbins]);
-    for (int32_t b = 0; b < nbins; b++) S.bin_rows[b] = 0;  // reused as the fill cursor
-    for (int32_t idx = 0; idx < k; idx++) {
-        const int32_t c = (int32_t)S.keys[idx];
-        const int32_t b = S.bin_of[c];
-        if (b >= 0) S.member[S.bin_start[b] + S.bin_rows[b]++] = c;
+    for (int32_t b = 0; b < nbins; b++) bin_rows[b] = 0;  // reused as the fill cursor
+    for (int32_t idx = 0; idx < nres; idx++) {
+        const int32_t c = (int32_t)(uint32_t)S.keys[idx];
+        const int32_t b = bin_of[c];
+        S.member[S.bin_start[b] + bin_rows[b]++] = c;
     }
 
     int64_t pos = 0;

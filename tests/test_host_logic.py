@@ -46,7 +46,7 @@ def _plan(sizes, align=4, cap=2048, max_rows=7):
     return cs, cr, items[: 4 * ni].reshape(-1, 4), npos.value
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("seed", list(range(12)))
 def test_planner_invariants(seed):
     rng = np.random.default_rng(seed)
     k = int(rng.integers(1, 400))
