@@ -930,7 +930,8 @@ static int run_allpairs(Labels& L, const double* weights_host, int32_t rank, int
                             it.pad_ = sl;  // perm slot
                             v.push_back(it);
                         }
-                        std::stable_sort(v.begin(), v.end(), [](const Item& a, const Item& b) { return a.npos > b.npos; });
+                        // (plan_blocks emits the streaming items first, longest first, then the resident ones; work units are handed
+                        // out first come first served, so the order of the nearly equal resident items does not matter)
                         int32_t ns = 0;
                         for (const Item& it : v) ns += it.npos > TL_CAP ? 1 : 0;
                         nstream[sl] = ns;
