@@ -10,7 +10,7 @@
 // table T_ij.
 //
 // WORK UNIT = (item, span of 32 partner partitions = two 16-partner super-tiles).  Work units are numbered span-major
-// and the persistent blocks (one per SM) take them round-robin, so all SMs sweep the partner axis together and the
+// and the persistent blocks (one per SM) take them in that order, first come first served, so all SMs sweep the partner axis together and the
 // labels of the current super-tiles -- dense 32 (N+1)-byte slabs of the super-tile-major uint16 label array,
 // lab16_index() -- are fetched from HBM once and then served by L2 to every owner partition.
 //
@@ -529,7 +529,7 @@ __device__ __forceinline__ void ecc_add(const TileParams& P, int cell, double v)
 // Work unit (WU) = (item, span of WSPAN partners).  WUs are numbered span-major: WU w belongs to the
 // span s with wu_prefix[s] <= w < wu_prefix[s+1] and to item w - wu_prefix[s]; the items are sorted by their
 // first partner, so the items that have partners inside span s are a PREFIX of the item list.  Block b of
-// the persistent grid takes WUs b, b + grid, b + 2 grid, ...: all SMs sweep the partner axis together, so the label
+// the persistent grid starts with WU b and then takes the next WU nobody has taken yet (advance_wu): all SMs sweep the partner axis together, so the label
 // sectors of the current super-tile (32 bytes per cell) are fetched from HBM once and then served by L2 to every
 // owner partition -- instead of one random HBM sector read per (cell, tile, owner), which is what bounds a
 // block-per-item schedule (measured: 42 G random sectors/s, tools/gatherbench.cu).
