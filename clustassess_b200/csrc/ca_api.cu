@@ -1316,8 +1316,8 @@ static int for_each_device(const std::function<int(int)>& fn) {
 // ---- the multi-GPU job: one process, one host thread per device ----------------------------------------------------------
 // Device g holds the raw labels of the spans it owns.  Per call (when the set is not prepared yet):
 //   A  min / max, histograms, ranks of its partitions                                   | barrier: global K_max known, every lab16 allocated
-//   B  cluster sizes (to the host), relabel + transpose of its spans, stored into the lab16 array of EVERY device
-//      (peer stores over NVLink: the kernel is its own all-gather)                        | barrier: label arrays complete everywhere
+//   B  cluster sizes (to the host, and by peer stores into every device's whole-set arrays), relabel + transpose of its spans into
+//      its own lab16 array, then DMA copies of the finished slabs into the lab16 array of EVERY peer  | barrier: copies queued everywhere
 //   C  all partitions' sizes / counts to the device, table templates
 // then items, sort and the wave kernel for its own partitions against all partners, ONE ncclAllReduce (64-bit integer sums, so the
 // result does not depend on the reduction order) on the same stream, and on the primary device finish + the copy to the host.

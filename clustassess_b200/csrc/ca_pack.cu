@@ -290,8 +290,9 @@ int launch_table_template(const uint32_t* d_spack, const int32_t* d_kcount, int3
 // 32-byte writes along the partition axis.
 // ------------------------------------------------------------------------------------------------
 // Sharded label sets (one process, several GPUs): a device relabels the 32-partition spans it owns -- local block y is
-// the global span span_of_block[y] -- and stores every 32-byte sector into the lab16 array of EVERY device (dst.p[0..n),
-// peer memory over NVLink): the transposition kernel is also the all-gather, no separate copy or collective follows it.
+// the global span span_of_block[y] -- and stores every 32-byte sector into the lab16 arrays dst.p[0..n).  The kernel CAN store
+// into peer memory over NVLink (n > 1: it is then its own all-gather), but 16-byte peer stores reached only 290 GB/s of egress
+// at 8 GPUs, so multi_allpairs (ca_api.cu) passes the local array alone and lets the copy engines push the slabs to the peers.
 constexpr int TP = 32, TC = 128;
 __global__ void __launch_bounds__(256) relabel_transpose_kernel(const int32_t* __restrict__ raw, int64_t n, int32_t m,
                                                                 const int32_t* __restrict__ span_of_block,

@@ -59,7 +59,7 @@ extern "C" {
  * created on them are alive).
  * ndev > 1: ONE process drives all the listed GPUs (reference analogue: the foreach %dopar% workers of R/ECS.R:953, but
  * inside one .Call): the batched entries below -- ca_consistency[_cols], ca_sim_matrix[_cols], ca_*_resident -- shard the
- * label matrix by 32-partition spans, one host thread per device packs its share and stores the compact labels into every
+ * label matrix by 32-partition spans, one host thread per device packs its share and copies the compact labels into every
  * device's memory over NVLink, every device runs the pairs of its own partitions, and ONE ncclAllReduce (64-bit integer
  * sums) combines the per-cell sums (M x M sums likewise).  Needs peer access between the devices; libnccl.so.2 is loaded
  * at this call (without it the sums are added by a kernel that reads peer memory).  ca_device_count(): devices selected. */
