@@ -1962,7 +1962,11 @@ static int pipelined_allpairs(const int32_t* labels, const int32_t* const* cols,
                               double* sim_out, bool* handled) {
     *handled = false;
     const int32_t nspan = (m + 31) / 32;
-    if (ndevices() != 1 || nspan < 8 || (int64_t)n * m * 4 < (128ll << 20) || getenv("CA_NO_PIPELINE")) return CA_OK;
+    // Worth it from about half a gigabyte: every group costs 2-3 ms of host round trips and planning with the engine idle, which a
+    // short upload cannot pay back (config 4, 200 MB: 25.1 ms pipelined against 24.4 ms plain from pinned memory, 45 against 35 ms
+    // from a thousand separate pageable columns; config 5, 2 GB: 217 against 243 ms).  CA_PIPE_MIN_MB moves the threshold (tests).
+    const int64_t min_mb = getenv("CA_PIPE_MIN_MB") ? atoll(getenv("CA_PIPE_MIN_MB")) : 512;
+    if (ndevices() != 1 || nspan < 8 || (int64_t)n * m * 4 < (min_mb << 20) || getenv("CA_NO_PIPELINE")) return CA_OK;
     Dev& D = cur();
     Ctx& c = D.c;
     cudaStream_t s = c.stream;

@@ -29,8 +29,9 @@
  *     call -- on one GPU or sharded over several, from resident labels or from host buffers -- return identical bits.
  *     (Different calls, e.g. with and without the matrix or with and without weights, run different kernel instantiations
  *     and may differ from each other in the last bits, far below the 1e-9 bound.)
- *   - Host buffers: large jobs on one device overlap their upload with the computation (the partitions are uploaded in
- *     groups from the last one down; owner i only meets partners j > i).  CA_NO_PIPELINE=1 disables that.
+ *   - Host buffers: jobs of 512 MB of labels and more on one device overlap their upload with the computation (the partitions
+ *     are uploaded in groups from the last one down; owner i only meets partners j > i).  CA_NO_PIPELINE=1 disables that,
+ *     CA_PIPE_MIN_MB moves the threshold.
  *   - Cluster counts: the batched engine takes up to 24 799 clusters per partition; beyond that (any count that fits
  *     memory, like the reference) the single-device entries loop over the pairs with a hashed contingency table.
  */

@@ -636,6 +636,7 @@ def test_pipelined_host_path_equals_plain_path_and_oracle(monkeypatch):
     """256 partitions x 140k cells from host buffers (143 MB, 8 spans): the host entry cuts the partitions into groups from the
     top and computes each group's pairs while the next one is still being uploaded.  Same bits as the plain path
     (CA_NO_PIPELINE=1), every cell and every matrix entry against the oracle."""
+    monkeypatch.setenv("CA_PIPE_MIN_MB", "128")  # the library pipelines from 512 MB of labels on; this set has 143 MB
     L = _louvainish(256, 140_000, 20, 60, seed=77)
     m, n = L.shape
     w = (1 + np.random.default_rng(78).poisson(1.0, size=m)).astype(np.float64)
@@ -670,9 +671,10 @@ def test_pipelined_host_path_equals_plain_path_and_oracle(monkeypatch):
     assert np.abs(res["ecc"][cells] - want).max() < TOL
 
 
-def test_pipelined_host_path_bails_out_when_later_groups_have_many_more_clusters():
+def test_pipelined_host_path_bails_out_when_later_groups_have_many_more_clusters(monkeypatch):
     """The row stride of the partner arrays is fixed from the first uploaded group (the LAST partitions) with a 2x margin; when an
     earlier partition turns out to have far more clusters the pipelined path gives up and the plain path answers -- same result."""
+    monkeypatch.setenv("CA_PIPE_MIN_MB", "128")
     rng = np.random.default_rng(81)
     m, n = 256, 131_072
     L = np.stack([rng.integers(0, 40, size=n) for _ in range(m)]).astype(np.int32)
